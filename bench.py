@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the fp64 LLG Heun ensemble (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 1,000,000
+independent realisations of one 12 nm magnetite particle (K=4e4 J/m^3, Ms=400 kA/m, T=300 K,
+alpha=0.1, easy axis and initial moment along z) under a sinusoidal applied field
+(f=300 kHz, H0=20 kA/m), explicit Heun, in-kernel Philox noise.  One bench "step" = one pass
+of the hot path over that batch: every realisation is advanced by 100,000 Heun steps
+(dt=1e-12 s, i.e. 1e-7 s of the field cycle) with 101 zero-order-hold samples and the fused
+ensemble reduction — 1e11 particle-steps per pass per GPU.  N>1: every rank integrates its own
+1M realisations with disjoint Philox member indices (weak scaling) and one NCCL all-reduce
+combines the [S][4] ensemble sums per pass.
+
+value  : whole-job particle-steps/s with inputs resident in HBM, timed with CUDA events on the
+         launching stream (max over ranks).
+e2e    : same metric through the public API (`EnsembleModel.simulate`) with HOST buffers:
+         per pass, seeds/parameters go host->device and final states + ensemble sums come back.
+roofline: the integration kernel against the FP64 pipe: W_alg = 98 flop per particle-step
+          over the kernel's CUDA-event duration, against the device's DFMA
+         rate measured in this run by the library's own register-resident DFMA-chain kernel
+         (MEASURED_PEAKS.json holds no fp64 figure).
+cpu_baseline / --impl reference: the UNMODIFIED reference `simulation::full_dynamics`
+         (compiled into oracle/_ref from its own sources) over a bounded sample of the same
+         workload on the host cores, one realisation per call, fanned out by an OpenMP pragma
+         that lives in our harness (the reference itself has no threads; its fan-out is joblib).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'particle-steps/s (fp64 LLG Heun ensemble)'
+UNIT = 'particle-steps/s'
+W_ALG = 98.0   # fp64 flop per N=1 Heun particle-step
+
+WORKLOAD = dict(
+    name='C3: 1M x 1-particle, sine field 300 kHz / 20 kA/m, Heun dt=1e-12 s, 100k steps per pass',
+    R=1_000_000, radius=12e-9, anisotropy=4e4, Ms=4e5, alpha=0.1, T=300.0,
+    dt=1e-12, t_end=1e-7, S=101, field_shape='sine', H0=2e4, f=3e5, random_state=1001)
+
+
+def workload_arrays(R):
+    w = WORKLOAD
+    return dict(radius=np.array([w['radius']]), anisotropy=np.array([w['anisotropy']]),
+                axis=np.array([[0.0, 0.0, 1.0]]), m0=np.array([[0.0, 0.0, 1.0]]), location=np.zeros((1, 3)))
+
+
+def member_seeds(R, random_state):
+    # magpy/model.py:202-203
+    np.random.seed(random_state)
+    return np.random.randint(np.iinfo(np.int32).max, size=R)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference on the host cores
+# --------------------------------------------------------------------------------------
+def load_cpu_reference():
+    """(kind, callable) — compiled reference if oracle/_ref exists, else the oracle port."""
+    import ctypes as C
+    ref = os.path.join(ROOT, 'oracle', '_ref', 'libmagpy_ref.so')
+    orc = os.path.join(ROOT, 'oracle', 'libsllg_oracle.so')
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    w = WORKLOAD
+    arr = workload_arrays(1)
+    field_code = {'sine': 0, 'square': 1, 'constant': 2}[w['field_shape']]
+    if os.path.exists(ref):
+        lib = C.CDLL(ref)
+        lib.ref_ensemble.restype = C.c_double
+        lib.ref_num_threads.restype = C.c_int
+        cores = lib.ref_num_threads()
+
+        def run(seeds):
+            seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+            sums = np.zeros((w['S'], 4))
+            el = lib.ref_ensemble(
+                C.c_size_t(len(seeds)), P(seeds), C.c_size_t(1), P(arr['radius']), P(arr['anisotropy']),
+                P(arr['axis']), C.c_size_t(0), P(arr['m0']), C.c_size_t(0), P(arr['location']),
+                C.c_double(w['Ms']), C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0),
+                C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']),
+                C.c_int(field_code), C.c_double(w['H0']), C.c_double(w['f']), C.c_int(0), P(sums), None)
+            if el < 0:
+                raise RuntimeError('reference ensemble failed')
+            return el
+        return 'reference', cores, run
+    if not os.path.exists(orc):
+        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')])
+    lib = C.CDLL(orc)
+    lib.orc_ensemble.restype = C.c_double
+    cores = os.cpu_count() or 1
+
+    def run(seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        sums = np.zeros((w['S'], 4))
+        t0 = time.perf_counter()
+        lib.orc_ensemble(
+            C.c_size_t(len(seeds)), P(seeds), C.c_int(1), P(arr['radius']), P(arr['anisotropy']), P(arr['axis']),
+            C.c_size_t(0), P(arr['m0']), C.c_size_t(0), P(arr['location']), C.c_double(w['Ms']),
+            C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0), C.c_double(1e-9),
+            C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']), C.c_int(field_code),
+            C.c_double(w['H0']), C.c_double(w['f']), P(sums), None)
+        return time.perf_counter() - t0
+    return 'port', cores, run
+
+
+def steps_per_member():
+    """Steps the reference executes per member for the workload: the schedule of
+    lib/simulation.cpp:342-355 evaluated in plain Python (no product code on this path)."""
+    w = WORKLOAD
+    KB, MU0, GYROMAG = 1.38064852e-23, 1.25663706e-6, 1.76086e11   # include/constants.hpp:10-12
+    H_k = 2 * w['anisotropy'] / MU0 / w['Ms']
+    tau = GYROMAG * MU0 * H_k / (1 + w['alpha'] * w['alpha'])
+    dt, T = w['dt'] * tau, w['t_end'] * tau
+    Ts = T / (w['S'] - 1)
+    lim = (w['S'] - 1) * Ts
+    s = max(int(lim / dt) - 2, 0)
+    while s * dt <= lim:
+        s += 1
+    return s
+
+
+def cpu_sample(run, cores, n_steps, target_seconds):
+    """Time the CPU path on a bounded sample: calibrate, then one batch of ~target_seconds."""
+    seeds = member_seeds(1 << 16, WORKLOAD['random_state'])
+    n0 = max(cores, 8)
+    el0 = run(seeds[:n0])
+    rate0 = n0 * n_steps / el0
+    n1 = int(min(len(seeds), max(n0, rate0 * target_seconds / n_steps)))
+    n1 = max(cores, (n1 // cores) * cores)
+    el1 = run(seeds[:n1])
+    return n1 * n_steps / el1, n1, el1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    kind, cores, run = load_cpu_reference()
+    n_steps = steps_per_member()
+    seeds = member_seeds(1 << 16, WORKLOAD['random_state'])
+    # bounded sample per step: ~5 s of host work, calibrated once
+    el = run(seeds[:max(cores, 8)])
+    rate = max(cores, 8) * n_steps / el
+    n = int(max(cores, min(len(seeds), rate * 5.0 / n_steps)))
+    n = max(cores, (n // cores) * cores)
+    for _ in range(args.warmup):
+        run(seeds[:n])
+    t = 0.0
+    for _ in range(args.steps):
+        t += run(seeds[:n])
+    value = args.steps * n * n_steps / t
+    sample = '%d realisations x %d Heun steps per step (of the 1M-realisation workload), %d host threads' % (n, n_steps, cores)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD['name'], 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def ours(args):
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    import magpy_b200 as mp
+    from magpy_b200 import core
+
+    if core.device_count() == 0:
+        raise RuntimeError('bench.py needs a CUDA device: magpy_b200 has no CPU fallback')
+    w = WORKLOAD
+    R = w['R']
+    arr = workload_arrays(R)
+    seeds_all = member_seeds(R * world, w['random_state'])
+    seeds = seeds_all[rank * R:(rank + 1) * R]
+
+    peak_tflops, max_mhz = core.fp64_peak(local_rank)
+
+    plan = core.EnsemblePlan(arr['radius'], arr['anisotropy'], arr['axis'], arr['m0'], arr['location'], w['Ms'],
+                             w['alpha'], w['T'], False, True, False, w['dt'], w['t_end'], w['S'], seeds,
+                             field_shape=w['field_shape'], field_amplitude=w['H0'], field_frequency=w['f'],
+                             device=local_rank, stream_offset=rank * R, return_trajectories=False,
+                             return_sums=True, return_final=True, gauss='f32')
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sums_t = None
+    if dist is not None:
+        sums_t = torch.zeros(w['S'] * 4, dtype=torch.float64, device='cuda')
+        ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def one_pass():
+        """One pass of the hot path; returns (device ms incl. all-reduce, integrate-kernel ms, stats)."""
+        plan.run()
+        st = plan.sync()
+        ms = st['device_ms']
+        if dist is not None:
+            # the plan's [S][4] sums live in device memory: all-reduce them in place over NCCL
+            ptr, n = plan.sums_device_ptr()
+            view = torch.as_tensor(_DevView(ptr, n), device='cuda')
+            ar0.record()
+            dist.all_reduce(view)
+            ar1.record()
+            torch.cuda.synchronize()
+            ms += ar0.elapsed_time(ar1)
+        return ms, st['integrate_ms'], st
+
+    for _ in range(max(args.warmup, 0)):
+        one_pass()
+    launches0 = plan.sync()['kernel_launches']
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_dev = t_int = 0.0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ms, ims, st = one_pass()
+        t_dev += ms
+        t_int += ims
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    gpu_launches = st['kernel_launches'] - launches0
+    n_steps = st['steps_per_member']
+    ps_per_pass = R * n_steps
+
+    ms_per_step = t_dev / args.steps
+    if dist is not None:
+        tt = torch.tensor([ms_per_step, t_int / args.steps], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_per_step, int_ms = float(tt[0]), float(tt[1])
+    else:
+        int_ms = t_int / args.steps
+    value = world * ps_per_pass / (ms_per_step * 1e-3)
+    out = plan.fetch()
+    mean_mz = float(out['sums'][-1, 2] / R / w['Ms'])
+    del plan
+
+    # end to end through the public API with host buffers (H2D + D2H inside the timed region)
+    base = mp.Model(arr['radius'], arr['anisotropy'], arr['axis'], arr['m0'], arr['location'], w['Ms'], w['alpha'],
+                    w['T'], field_shape=w['field_shape'], field_frequency=w['f'], field_amplitude=w['H0'])
+    ens = mp.EnsembleModel(R, base)
+    e2e_passes = max(1, min(args.steps, 2))
+    ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'] + rank, implicit_solve=False, device=local_rank,
+                 stream_offset=rank * R, return_trajectories=False)   # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for i in range(e2e_passes):
+        res = ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'] + rank, implicit_solve=False,
+                           device=local_rank, stream_offset=rank * R, return_trajectories=False)
+        h2d += sum(s['h2d_bytes'] for s in res.stats)
+        d2h += sum(s['d2h_bytes'] for s in res.stats)
+        if dist is not None:
+            s_t = torch.from_numpy(res._sums).cuda()
+            dist.all_reduce(s_t)
+            res._sums[...] = s_t.cpu().numpy()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_passes
+    if dist is not None:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt[0])
+    e2e_value = world * ps_per_pass / e2e_s
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    achieved = W_ALG * ps_per_pass / (int_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, 'profiles', 'heun_single_traffic.json')
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+    cpu = None
+    try:
+        kind, cores, run = load_cpu_reference()
+        v, n, el = cpu_sample(run, cores, n_steps + 1, 12.0)
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind,
+               'sample': '%d realisations x %d Heun steps of the same workload in %.1f s' % (n, n_steps + 1, el)}
+    except Exception as exc:   # the baseline is reported, never required for the GPU number
+        cpu = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'unavailable', 'sample': str(exc)}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': w['name'], 'realisations_per_gpu': R, 'particles': 1, 'heun_steps_per_pass': n_steps,
+                   'samples': w['S'], 'rng': 'Philox4x32-10 + fp32 Box-Muller (in kernel)',
+                   'l2': 'state is register resident; no input is re-read between passes (0 B/step steady-state HBM '
+                         'traffic), so no L2 flush applies',
+                   'timing': 'CUDA events on the launching stream, max over ranks',
+                   'mean_mz_over_Ms_at_end': mean_mz, 'wall_s_timed_region': wall},
+        'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                     'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': traffic,
+                     'kernel': 'heun_single_kernel', 'kernel_ms_per_launch': int_ms,
+                     'algorithmic_flop_per_particle_step': W_ALG,
+                     'peak_source': 'measured in this run: library DFMA-chain kernel (fp64_peak); '
+                                    'MEASURED_PEAKS.json has no fp64 figure'},
+        'cpu_baseline': cpu,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d // e2e_passes,
+                'd2h_bytes_per_step': d2h // e2e_passes, 'api': 'EnsembleModel.simulate', 'passes': e2e_passes},
+        'gpu_launches': int(gpu_launches),
+        'clocks': clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+class _DevView:
+    """Minimal __cuda_array_interface__ wrapper so torch can all-reduce the plan's sums in place."""
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<f8', 'data': (ptr, False), 'version': 2,
+                                         'strides': None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,172 @@
+/* magpy_b200.h — C ABI of the B200-native ensemble stochastic-LLG integrator.
+ *
+ * This is the drop-in boundary for ONE path of owlas/magpy: everything that
+ * magpy/core.pyx reaches through `simulation::full_dynamics`.  Each entry point
+ * names the reference interface it replaces (paths relative to the reference
+ * repository).  Plain pointers and sizes only; the caller owns every buffer;
+ * nothing allocated by the library is ever returned (except opaque plan handles
+ * that must be released with magpy_b200_plan_destroy).  No C++ exception
+ * crosses this boundary: every function returns an int status and
+ * magpy_b200_last_error() describes the most recent failure on this thread.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * returns MAGPY_B200_ERR_NO_DEVICE.
+ */
+#ifndef MAGPY_B200_H
+#define MAGPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAGPY_B200_ABI_VERSION 1
+
+/* status codes */
+#define MAGPY_B200_OK 0
+#define MAGPY_B200_ERR_BAD_ARG 1   /* invalid argument (message says which)            */
+#define MAGPY_B200_ERR_NO_DEVICE 2 /* no usable CUDA device / bad device index          */
+#define MAGPY_B200_ERR_CUDA 3      /* CUDA runtime error                                */
+#define MAGPY_B200_ERR_NOMEM 4     /* request does not fit device or host memory        */
+
+/* field shapes: same numbering as `enum field::options` (include/field.hpp:95-97)
+ * and `cpdef enum options` (magpy/core.pyx:38-42). */
+#define MAGPY_B200_FIELD_SINE 0
+#define MAGPY_B200_FIELD_SQUARE 1
+#define MAGPY_B200_FIELD_CONSTANT 2
+
+/* Gaussian transform applied to the Philox4x32-10 words (replaces lib/rng.cpp:14-24) */
+#define MAGPY_B200_GAUSS_F32 0 /* Box-Muller in fp32 on the SFU, widened to fp64 (default) */
+#define MAGPY_B200_GAUSS_F64 1 /* Box-Muller in fp64 from 53-bit uniforms                  */
+
+/* Statistics returned by every run (replaces the error codes the reference computes
+ * and drops at lib/simulation.cpp:368-369 and the joblib progress lines of
+ * magpy/model.py:204). */
+typedef struct magpy_b200_stats {
+    uint64_t steps_per_member;     /* integrator steps executed per member                 */
+    uint64_t particle_steps;       /* members * particles * steps                          */
+    uint64_t newton_iterations;    /* implicit only: total quasi-Newton iterations          */
+    uint64_t newton_max_iterations;/* implicit only: largest count in a single step         */
+    uint64_t newton_failures;      /* implicit only: steps that hit max_iter or a zero pivot */
+    uint64_t kernel_launches;      /* CUDA kernels launched by this call                    */
+    double device_ms;              /* CUDA-event time of the device work (launch stream)    */
+    double integrate_ms;           /* CUDA-event time of the integration kernels alone      */
+    uint64_t h2d_bytes;            /* host->device bytes copied by this call                */
+    uint64_t d2h_bytes;            /* device->host bytes copied by this call                */
+} magpy_b200_stats;
+
+/* One ensemble of `n_members` independent clusters that share geometry and material
+ * (radius, anisotropy, location, Ms, damping, T, field) and may differ in anisotropy
+ * axes and initial magnetisation — replaces the joblib fan-out of
+ * `EnsembleModel.simulate` (magpy/model.py:159-208) + one
+ * `simulation::full_dynamics` call per member (lib/simulation.cpp:476-624). */
+typedef struct magpy_b200_ensemble {
+    uint32_t abi_version;            /* = MAGPY_B200_ABI_VERSION                              */
+    int32_t device;                  /* CUDA device ordinal                                   */
+    uint64_t n_members;              /* R                                                     */
+    uint32_t n_particles;            /* N                                                     */
+    const double* radius;            /* [N]    m                                              */
+    const double* anisotropy;        /* [N]    J/m^3                                          */
+    const double* location;          /* [N][3] m                                              */
+    const double* anisotropy_axis;   /* [N][3] if axis_stride==0 else [R][N][3]               */
+    uint64_t axis_stride;            /* doubles between members: 0 (shared) or 3N             */
+    const double* magnetisation_direction; /* [N][3] or [R][N][3] initial unit vectors        */
+    uint64_t m0_stride;              /* 0 (shared) or 3N                                      */
+    double magnetisation;            /* Ms, A/m                                               */
+    double damping;                  /* alpha                                                 */
+    double temperature;              /* K                                                     */
+    int32_t renorm, interactions, use_implicit;
+    double implicit_tol;             /* eps of the quasi-Newton solve                         */
+    double time_step, end_time;      /* s                                                     */
+    uint64_t max_samples;            /* S >= 2                                                */
+    int32_t field_shape;             /* MAGPY_B200_FIELD_*                                    */
+    double field_amplitude;          /* A/m                                                   */
+    double field_frequency;          /* Hz                                                    */
+    /* noise: Philox4x32-10 keyed by the member's seed, counter = (step, particle, member
+     * index + stream_offset); or Wiener increments injected by the caller (RngArray
+     * semantics, lib/rng.cpp:67-94) */
+    const int64_t* seeds;            /* [R]                                                   */
+    uint64_t stream_offset;          /* global index of member 0 (shards use disjoint ranges) */
+    int32_t gauss_mode;              /* MAGPY_B200_GAUSS_*                                    */
+    const double* injected_dw;       /* NULL, or [R][injected_steps][3N] unit-variance draws  */
+    uint64_t injected_steps;
+    /* outputs: host pointers, each may be NULL */
+    double* out_time;                /* [S] s                                                 */
+    double* out_field;               /* [S] A/m                                               */
+    double* out_trajectories;        /* [R][N][3][S] A/m                                      */
+    double* out_sums;                /* [S][4]: sum over members of cluster-summed Mx,My,Mz
+                                        and of (cluster Mz)^2, A/m                            */
+    double* out_final;               /* [R][N][3] state at the last sample, A/m               */
+} magpy_b200_ensemble;
+
+typedef struct magpy_b200_plan magpy_b200_plan; /* opaque: device-resident ensemble */
+
+/* ---- library -------------------------------------------------------------------- */
+int magpy_b200_abi_version(void);
+const char* magpy_b200_last_error(void);
+int magpy_b200_device_count(int* count);
+
+/* physical constants exactly as include/constants.hpp:10-12 (replaces
+ * core.get_KB / get_mu0 / get_gamma, magpy/core.pyx:29-34) */
+double magpy_b200_get_KB(void);
+double magpy_b200_get_mu0(void);
+double magpy_b200_get_gamma(void);
+
+/* ---- one cluster ------------------------------------------------------------------
+ * Replaces `simulation::full_dynamics` SI overload (include/simulation.hpp:74-94,
+ * lib/simulation.cpp:476-624) as bound by magpy/core.pyx:72-93.  Argument meaning and
+ * order follow that overload; outputs replace `std::vector<simulation::results>`
+ * (include/simulation.hpp:32-48): out_time[S], out_field[S], out_m[N][3][S]. */
+int magpy_b200_simulate(const double* radius, const double* anisotropy, const double* anisotropy_axis,
+                        const double* magnetisation_direction, const double* location, size_t n_particles,
+                        double magnetisation, double damping, double temperature, int renorm,
+                        int interactions, int use_implicit, double eps, double time_step, double end_time,
+                        size_t max_samples, int64_t seed, int field_shape, double field_amplitude,
+                        double field_frequency, double* out_time, double* out_field, double* out_m,
+                        magpy_b200_stats* stats);
+
+/* ---- ensembles -------------------------------------------------------------------- */
+/* Host buffers in, host buffers out (upload, integrate, reduce, download). */
+int magpy_b200_simulate_ensemble(const magpy_b200_ensemble* args, magpy_b200_stats* stats);
+
+/* Device-resident variant: create uploads inputs and allocates outputs once; run
+ * re-integrates from the initial state (asynchronously on the plan's stream);
+ * fetch copies the requested outputs into the host pointers of `args`. */
+int magpy_b200_plan_create(const magpy_b200_ensemble* args, magpy_b200_plan** plan);
+int magpy_b200_plan_run(magpy_b200_plan* plan);
+int magpy_b200_plan_sync(magpy_b200_plan* plan, magpy_b200_stats* stats);
+int magpy_b200_plan_fetch(magpy_b200_plan* plan, double* out_time, double* out_field,
+                          double* out_trajectories, double* out_sums, double* out_final);
+/* device address of the [S][4] ensemble-sum buffer (for an in-place NCCL all-reduce) */
+int magpy_b200_plan_sums_device_ptr(magpy_b200_plan* plan, void** dptr, size_t* n_doubles);
+int magpy_b200_plan_destroy(magpy_b200_plan* plan);
+
+/* ---- host helpers that mirror reference arithmetic ---------------------------------- */
+/* SI -> reduced units (lib/simulation.cpp:498-549): out[0]=V_av [1]=K_av [2]=H_k
+ * [3]=time_factor [4]=dt_red [5]=T_red [6]=h0 [7]=f_red [8]=dipolar prefactor;
+ * k_red/v_red/sigma are [N]. */
+int magpy_b200_reduce_units(const double* radius, const double* anisotropy, size_t n_particles,
+                            double magnetisation, double damping, double temperature, double time_step,
+                            double end_time, double field_amplitude, double field_frequency,
+                            double* k_red, double* v_red, double* sigma, double* out_scalars);
+/* cumulative step count per sample of the zero-order-hold schedule
+ * (lib/simulation.cpp:171-174, 342-355, 392-405): cum[k] = steps executed when sample k
+ * is stored; sample k holds the state after cum[k]-1 steps. */
+int magpy_b200_schedule(double dt_red, double t_end_red, size_t max_samples, uint64_t* cum);
+
+/* ---- device self-tests used by the parity suite (tiny kernels) ----------------------- */
+/* raw Philox4x32-10 words computed on the device */
+int magpy_b200_philox_words(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* the n Gaussian draws member `member` / particle `particle` consumes at `step` (3 values) */
+int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t particle, uint64_t first_step,
+                         uint64_t n_steps, int gauss_mode, double* out /* [n_steps][3] */);
+/* sustained FP64 FMA rate of the device (TFLOP/s), measured with a register-resident
+ * DFMA chain kernel — the roofline denominator for the integration kernels */
+int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGPY_B200_H */

@@ -1,0 +1,484 @@
+# cython: language_level=3, boundscheck=False, wraparound=False
+"""magpy_b200.core — Cython layer over the C ABI of libmagpy_b200 (include/magpy_b200.h).
+
+Drop-in for the sLLG entry points of the reference's ``magpy/core.pyx``:
+
+* ``simulate(...)`` keeps the exact Python signature, defaults and return dict of
+  ``magpy/core.pyx:128-203`` (which binds ``simulation::full_dynamics``,
+  ``magpy/core.pyx:72-93``); a bad ``field_shape`` still raises ``KeyError``
+  (``magpy/core.pyx:158-161``).
+* ``get_KB / get_mu0 / get_gamma`` as ``magpy/core.pyx:29-34``.
+* ``simulate_ensemble(...)`` / ``EnsemblePlan`` are the batched entry that replaces the
+  per-member joblib fan-out of ``magpy/model.py:202-207``.
+
+The GIL is released around every library call.  There is no CPU fallback: without a
+CUDA device the library returns an error and this module raises ``RuntimeError``.
+"""
+import numpy as np
+cimport numpy as np
+from libc.stdint cimport int32_t, int64_t, uint32_t, uint64_t
+from libc.string cimport memset
+
+np.import_array()
+
+cdef extern from "magpy_b200.h" nogil:
+    int MAGPY_B200_ABI_VERSION
+    int MAGPY_B200_OK
+    int MAGPY_B200_ERR_BAD_ARG
+    int MAGPY_B200_ERR_NO_DEVICE
+    int MAGPY_B200_ERR_CUDA
+    int MAGPY_B200_ERR_NOMEM
+    int MAGPY_B200_FIELD_SINE
+    int MAGPY_B200_FIELD_SQUARE
+    int MAGPY_B200_FIELD_CONSTANT
+    int MAGPY_B200_GAUSS_F32
+    int MAGPY_B200_GAUSS_F64
+
+    ctypedef struct magpy_b200_stats:
+        uint64_t steps_per_member
+        uint64_t particle_steps
+        uint64_t newton_iterations
+        uint64_t newton_max_iterations
+        uint64_t newton_failures
+        uint64_t kernel_launches
+        double device_ms
+        double integrate_ms
+        uint64_t h2d_bytes
+        uint64_t d2h_bytes
+
+    ctypedef struct magpy_b200_ensemble:
+        uint32_t abi_version
+        int32_t device
+        uint64_t n_members
+        uint32_t n_particles
+        const double* radius
+        const double* anisotropy
+        const double* location
+        const double* anisotropy_axis
+        uint64_t axis_stride
+        const double* magnetisation_direction
+        uint64_t m0_stride
+        double magnetisation
+        double damping
+        double temperature
+        int32_t renorm
+        int32_t interactions
+        int32_t use_implicit
+        double implicit_tol
+        double time_step
+        double end_time
+        uint64_t max_samples
+        int32_t field_shape
+        double field_amplitude
+        double field_frequency
+        const int64_t* seeds
+        uint64_t stream_offset
+        int32_t gauss_mode
+        const double* injected_dw
+        uint64_t injected_steps
+        double* out_time
+        double* out_field
+        double* out_trajectories
+        double* out_sums
+        double* out_final
+
+    ctypedef struct magpy_b200_plan:
+        pass
+
+    int magpy_b200_abi_version()
+    const char* magpy_b200_last_error()
+    int magpy_b200_device_count(int* count)
+    double magpy_b200_get_KB()
+    double magpy_b200_get_mu0()
+    double magpy_b200_get_gamma()
+    int magpy_b200_simulate(const double*, const double*, const double*, const double*, const double*, size_t,
+                            double, double, double, int, int, int, double, double, double, size_t, int64_t, int,
+                            double, double, double*, double*, double*, magpy_b200_stats*)
+    int magpy_b200_simulate_ensemble(const magpy_b200_ensemble*, magpy_b200_stats*)
+    int magpy_b200_plan_create(const magpy_b200_ensemble*, magpy_b200_plan**)
+    int magpy_b200_plan_run(magpy_b200_plan*)
+    int magpy_b200_plan_sync(magpy_b200_plan*, magpy_b200_stats*)
+    int magpy_b200_plan_fetch(magpy_b200_plan*, double*, double*, double*, double*, double*)
+    int magpy_b200_plan_sums_device_ptr(magpy_b200_plan*, void**, size_t*)
+    int magpy_b200_plan_destroy(magpy_b200_plan*)
+    int magpy_b200_reduce_units(const double*, const double*, size_t, double, double, double, double, double,
+                                double, double, double*, double*, double*, double*)
+    int magpy_b200_schedule(double, double, size_t, uint64_t*)
+    int magpy_b200_philox_words(int, const uint32_t*, const uint32_t*, uint32_t*)
+    int magpy_b200_gaussians(int, int64_t, uint64_t, uint32_t, uint64_t, uint64_t, int, double*)
+    int magpy_b200_fp64_peak(int, double*, double*)
+
+
+# field::options numbering (include/field.hpp:95-97, magpy/core.pyx:38-42)
+SINE = 0
+SQUARE = 1
+CONSTANT = 2
+
+_FIELD_LOOKUP = {'constant': CONSTANT, 'sine': SINE, 'square': SQUARE}
+_GAUSS_LOOKUP = {'f32': 0, 'f64': 1}
+
+
+cdef _raise(int rc):
+    msg = magpy_b200_last_error().decode('utf-8', 'replace')
+    if rc == MAGPY_B200_ERR_BAD_ARG:
+        raise ValueError(msg)
+    if rc == MAGPY_B200_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+cdef dict _stats_dict(magpy_b200_stats* st):
+    return {
+        'steps_per_member': st.steps_per_member,
+        'particle_steps': st.particle_steps,
+        'newton_iterations': st.newton_iterations,
+        'newton_max_iterations': st.newton_max_iterations,
+        'newton_failures': st.newton_failures,
+        'kernel_launches': st.kernel_launches,
+        'device_ms': st.device_ms,
+        'integrate_ms': st.integrate_ms,
+        'h2d_bytes': st.h2d_bytes,
+        'd2h_bytes': st.d2h_bytes,
+    }
+
+
+cpdef get_KB():
+    return magpy_b200_get_KB()
+
+cpdef get_mu0():
+    return magpy_b200_get_mu0()
+
+cpdef get_gamma():
+    return magpy_b200_get_gamma()
+
+cpdef int abi_version():
+    return magpy_b200_abi_version()
+
+cpdef int device_count():
+    cdef int n = 0
+    magpy_b200_device_count(&n)
+    return n
+
+
+cpdef simulate(
+    np.ndarray[double, ndim=1, mode='c'] radius,
+    np.ndarray[double, ndim=1, mode='c'] anisotropy,
+    np.ndarray[double, ndim=2, mode='c'] anisotropy_axis,
+    np.ndarray[double, ndim=2, mode='c'] magnetisation_direction,
+    np.ndarray[double, ndim=2, mode='c'] location,
+    double magnetisation,
+    double damping,
+    double temperature,
+    bint renorm,
+    bint interactions,
+    bint use_implicit,
+    double time_step,
+    double end_time,
+    int max_samples,
+    long seed,
+    str field_shape='constant',
+    double field_amplitude=0.0,
+    double field_frequency=0.0,
+    double implicit_tol=1e-9 ):
+    """Same signature and return dict as the reference's ``core.simulate``
+    (magpy/core.pyx:128-203); the noise is the in-kernel Philox stream keyed by `seed`."""
+    cdef size_t n_particles = radius.shape[0]
+    if (anisotropy.shape[0] != n_particles or anisotropy_axis.shape[0] != n_particles
+            or magnetisation_direction.shape[0] != n_particles or location.shape[0] != n_particles
+            or anisotropy_axis.shape[1] != 3 or magnetisation_direction.shape[1] != 3 or location.shape[1] != 3):
+        raise ValueError('per-particle arrays must have matching lengths and 3 components')
+    if max_samples < 2:
+        raise ValueError('max_samples must be >= 2')
+    cdef int field_code = _FIELD_LOOKUP[field_shape]   # KeyError on a bad shape, as the reference
+    cdef np.ndarray[double, ndim=1] t = np.empty(max_samples)
+    cdef np.ndarray[double, ndim=1] fld = np.empty(max_samples)
+    cdef np.ndarray[double, ndim=3] m = np.empty((n_particles, 3, max_samples))
+    cdef magpy_b200_stats st
+    cdef int rc
+    cdef const double* p_r = &radius[0]
+    cdef const double* p_k = &anisotropy[0]
+    cdef const double* p_ax = &anisotropy_axis[0, 0]
+    cdef const double* p_m0 = &magnetisation_direction[0, 0]
+    cdef const double* p_loc = &location[0, 0]
+    cdef double* p_t = &t[0]
+    cdef double* p_f = &fld[0]
+    cdef double* p_m = &m[0, 0, 0]
+    cdef int c_renorm = renorm, c_inter = interactions, c_impl = use_implicit
+    cdef size_t c_S = max_samples
+    cdef int64_t c_seed = seed
+    with nogil:
+        rc = magpy_b200_simulate(p_r, p_k, p_ax, p_m0, p_loc, n_particles, magnetisation, damping, temperature,
+                                 c_renorm, c_inter, c_impl, implicit_tol, time_step, end_time, c_S, c_seed,
+                                 field_code, field_amplitude, field_frequency, p_t, p_f, p_m, &st)
+    if rc != 0:
+        _raise(rc)
+    return {
+        'N': n_particles,
+        'time': t,
+        'field': fld,
+        'x': {i: m[i, 0] for i in range(n_particles)},
+        'y': {i: m[i, 1] for i in range(n_particles)},
+        'z': {i: m[i, 2] for i in range(n_particles)},
+    }
+
+
+cdef class _EnsembleArgs:
+    """Owns the numpy buffers a magpy_b200_ensemble points into."""
+    cdef magpy_b200_ensemble a
+    cdef object keep
+    cdef public object time, field, trajectories, sums, final
+    cdef public size_t R, N, S
+
+    def __cinit__(self):
+        memset(&self.a, 0, sizeof(magpy_b200_ensemble))
+        self.keep = []
+
+
+cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
+                               double magnetisation, double damping, double temperature, bint renorm,
+                               bint interactions, bint use_implicit, double time_step, double end_time,
+                               max_samples, seeds, str field_shape, double field_amplitude,
+                               double field_frequency, double implicit_tol, int device, stream_offset,
+                               bint return_trajectories, bint return_sums, bint return_final, str gauss,
+                               injected_dw):
+    cdef _EnsembleArgs e = _EnsembleArgs()
+    cdef np.ndarray[double, ndim=1, mode='c'] c_radius = np.ascontiguousarray(radius, dtype=np.float64).reshape(-1)
+    cdef size_t N = c_radius.shape[0]
+    cdef np.ndarray[double, ndim=1, mode='c'] c_anis = np.ascontiguousarray(anisotropy, dtype=np.float64).reshape(-1)
+    cdef np.ndarray[double, ndim=2, mode='c'] c_loc = np.ascontiguousarray(location, dtype=np.float64).reshape(-1, 3)
+    if N == 0 or c_anis.shape[0] != N or c_loc.shape[0] != N:
+        raise ValueError('radius, anisotropy and location must describe the same number of particles')
+    cdef np.ndarray[np.int64_t, ndim=1, mode='c'] c_seeds = np.ascontiguousarray(seeds, dtype=np.int64).reshape(-1)
+    cdef size_t R = c_seeds.shape[0]
+    if R == 0:
+        raise ValueError('seeds must hold one seed per ensemble member')
+    if int(max_samples) < 2:
+        raise ValueError('max_samples must be >= 2')
+    cdef size_t S = int(max_samples)
+    ax = np.ascontiguousarray(anisotropy_axis, dtype=np.float64)
+    m0 = np.ascontiguousarray(magnetisation_direction, dtype=np.float64)
+    for name, arr in (('anisotropy_axis', ax), ('magnetisation_direction', m0)):
+        if arr.shape not in ((N, 3), (R, N, 3)):
+            raise ValueError('%s must have shape (N,3) or (R,N,3), got %r' % (name, arr.shape))
+    cdef np.ndarray[double, ndim=1, mode='c'] c_ax = ax.reshape(-1)
+    cdef np.ndarray[double, ndim=1, mode='c'] c_m0 = m0.reshape(-1)
+    cdef np.ndarray[double, ndim=1, mode='c'] c_dw
+    e.keep = [c_radius, c_anis, c_loc, c_seeds, c_ax, c_m0]
+    e.R, e.N, e.S = R, N, S
+
+    e.a.abi_version = MAGPY_B200_ABI_VERSION
+    e.a.device = device
+    e.a.n_members = R
+    e.a.n_particles = N
+    e.a.radius = &c_radius[0]
+    e.a.anisotropy = &c_anis[0]
+    e.a.location = &c_loc[0, 0]
+    e.a.anisotropy_axis = &c_ax[0]
+    e.a.axis_stride = 3 * N if ax.ndim == 3 else 0
+    e.a.magnetisation_direction = &c_m0[0]
+    e.a.m0_stride = 3 * N if m0.ndim == 3 else 0
+    e.a.magnetisation = magnetisation
+    e.a.damping = damping
+    e.a.temperature = temperature
+    e.a.renorm = renorm
+    e.a.interactions = interactions
+    e.a.use_implicit = use_implicit
+    e.a.implicit_tol = implicit_tol
+    e.a.time_step = time_step
+    e.a.end_time = end_time
+    e.a.max_samples = S
+    e.a.field_shape = _FIELD_LOOKUP[field_shape]
+    e.a.field_amplitude = field_amplitude
+    e.a.field_frequency = field_frequency
+    e.a.seeds = <const int64_t*> &c_seeds[0]
+    e.a.stream_offset = int(stream_offset)
+    e.a.gauss_mode = _GAUSS_LOOKUP[gauss]
+    if injected_dw is not None:
+        dw = np.ascontiguousarray(injected_dw, dtype=np.float64)
+        if dw.ndim != 3 or dw.shape[0] != R or dw.shape[2] != 3 * N:
+            raise ValueError('injected_dw must have shape (R, steps, 3N)')
+        c_dw = dw.reshape(-1)
+        e.keep.append(c_dw)
+        e.a.injected_dw = &c_dw[0]
+        e.a.injected_steps = dw.shape[1]
+
+    cdef np.ndarray[double, ndim=1] o_time = np.empty(S)
+    cdef np.ndarray[double, ndim=1] o_field = np.empty(S)
+    cdef np.ndarray[double, ndim=4] o_traj
+    cdef np.ndarray[double, ndim=2] o_sums
+    cdef np.ndarray[double, ndim=3] o_final
+    e.time, e.field = o_time, o_field
+    e.a.out_time = &o_time[0]
+    e.a.out_field = &o_field[0]
+    if return_trajectories:
+        o_traj = np.empty((R, N, 3, S))
+        e.trajectories = o_traj
+        e.a.out_trajectories = &o_traj[0, 0, 0, 0]
+    if return_sums:
+        o_sums = np.empty((S, 4))
+        e.sums = o_sums
+        e.a.out_sums = &o_sums[0, 0]
+    if return_final:
+        o_final = np.empty((R, N, 3))
+        e.final = o_final
+        e.a.out_final = &o_final[0, 0, 0]
+    return e
+
+
+def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
+                      double magnetisation, double damping, double temperature, bint renorm, bint interactions,
+                      bint use_implicit, double time_step, double end_time, max_samples, seeds,
+                      str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
+                      double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=True,
+                      bint return_sums=True, bint return_final=True, str gauss='f32', injected_dw=None):
+    """Integrate R = len(seeds) independent members of one cluster in a single call.
+
+    `anisotropy_axis` and `magnetisation_direction` are (N,3) (shared) or (R,N,3).
+    Returns a dict with 'time' [S], 'field' [S], 'trajectories' [R,N,3,S] | None,
+    'sums' [S,4] | None (sum over members of cluster Mx,My,Mz and Mz^2), 'final' [R,N,3] | None
+    and 'stats'.  `injected_dw` (R, steps, 3N) replaces the Philox stream by caller-supplied
+    unit-variance increments (the reference's RngArray hook, lib/rng.cpp:67-94)."""
+    cdef _EnsembleArgs e = _build_args(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
+                                       magnetisation, damping, temperature, renorm, interactions, use_implicit,
+                                       time_step, end_time, max_samples, seeds, field_shape, field_amplitude,
+                                       field_frequency, implicit_tol, device, stream_offset, return_trajectories,
+                                       return_sums, return_final, gauss, injected_dw)
+    cdef magpy_b200_stats st
+    cdef int rc
+    with nogil:
+        rc = magpy_b200_simulate_ensemble(&e.a, &st)
+    if rc != 0:
+        _raise(rc)
+    return {'N': e.N, 'R': e.R, 'time': e.time, 'field': e.field, 'trajectories': e.trajectories,
+            'sums': e.sums, 'final': e.final, 'stats': _stats_dict(&st)}
+
+
+cdef class EnsemblePlan:
+    """Device-resident ensemble: inputs are uploaded once, `run()` re-integrates from the
+    initial state on the plan's CUDA stream, `sync()` waits and returns the stats (CUDA-event
+    times), `fetch()` downloads the outputs requested at construction."""
+    cdef magpy_b200_plan* plan
+    cdef _EnsembleArgs e
+
+    def __cinit__(self):
+        self.plan = NULL
+
+    def __init__(self, radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
+                 double magnetisation, double damping, double temperature, bint renorm, bint interactions,
+                 bint use_implicit, double time_step, double end_time, max_samples, seeds,
+                 str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
+                 double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=False,
+                 bint return_sums=True, bint return_final=True, str gauss='f32', injected_dw=None):
+        self.e = _build_args(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
+                             magnetisation, damping, temperature, renorm, interactions, use_implicit,
+                             time_step, end_time, max_samples, seeds, field_shape, field_amplitude,
+                             field_frequency, implicit_tol, device, stream_offset, return_trajectories,
+                             return_sums, return_final, gauss, injected_dw)
+        cdef int rc
+        with nogil:
+            rc = magpy_b200_plan_create(&self.e.a, &self.plan)
+        if rc != 0:
+            self.plan = NULL
+            _raise(rc)
+
+    def __dealloc__(self):
+        if self.plan != NULL:
+            magpy_b200_plan_destroy(self.plan)
+            self.plan = NULL
+
+    def run(self):
+        cdef int rc
+        with nogil:
+            rc = magpy_b200_plan_run(self.plan)
+        if rc != 0:
+            _raise(rc)
+
+    def sync(self):
+        cdef magpy_b200_stats st
+        cdef int rc
+        with nogil:
+            rc = magpy_b200_plan_sync(self.plan, &st)
+        if rc != 0:
+            _raise(rc)
+        return _stats_dict(&st)
+
+    def fetch(self):
+        cdef int rc
+        with nogil:
+            rc = magpy_b200_plan_fetch(self.plan, self.e.a.out_time, self.e.a.out_field,
+                                       self.e.a.out_trajectories, self.e.a.out_sums, self.e.a.out_final)
+        if rc != 0:
+            _raise(rc)
+        return {'N': self.e.N, 'R': self.e.R, 'time': self.e.time, 'field': self.e.field,
+                'trajectories': self.e.trajectories, 'sums': self.e.sums, 'final': self.e.final}
+
+    def sums_device_ptr(self):
+        """(device address, number of doubles) of the [S][4] ensemble-sum buffer (reduced units)."""
+        cdef void* p = NULL
+        cdef size_t n = 0
+        cdef int rc = magpy_b200_plan_sums_device_ptr(self.plan, &p, &n)
+        if rc != 0:
+            _raise(rc)
+        return <size_t> p, n
+
+
+def reduce_units(radius, anisotropy, double magnetisation, double damping, double temperature,
+                 double time_step, double end_time, double field_amplitude=0.0, double field_frequency=0.0):
+    """SI -> reduced units exactly as lib/simulation.cpp:498-549."""
+    cdef np.ndarray[double, ndim=1, mode='c'] r = np.ascontiguousarray(radius, dtype=np.float64).reshape(-1)
+    cdef np.ndarray[double, ndim=1, mode='c'] k = np.ascontiguousarray(anisotropy, dtype=np.float64).reshape(-1)
+    cdef size_t N = r.shape[0]
+    cdef np.ndarray[double, ndim=1] k_red = np.empty(N), v_red = np.empty(N), sigma = np.empty(N), sc = np.empty(9)
+    cdef int rc = magpy_b200_reduce_units(&r[0], &k[0], N, magnetisation, damping, temperature, time_step,
+                                          end_time, field_amplitude, field_frequency, &k_red[0], &v_red[0],
+                                          &sigma[0], &sc[0])
+    if rc != 0:
+        _raise(rc)
+    names = ('V_av', 'K_av', 'H_k', 'time_factor', 'dt_red', 'T_red', 'h0', 'f_red', 'dipolar_prefactor')
+    out = dict(zip(names, sc.tolist()))
+    out.update(k_red=k_red, v_red=v_red, sigma=sigma)
+    return out
+
+
+def schedule(double dt_red, double t_end_red, max_samples):
+    """Cumulative step count per sample of the zero-order-hold schedule (lib/simulation.cpp:342-405)."""
+    cdef size_t S = int(max_samples)
+    cdef np.ndarray[np.uint64_t, ndim=1] cum = np.zeros(S, dtype=np.uint64)
+    cdef int rc = magpy_b200_schedule(dt_red, t_end_red, S, <uint64_t*> &cum[0])
+    if rc != 0:
+        _raise(rc)
+    return cum
+
+
+def philox_words(ctr, key, int device=0):
+    cdef uint32_t c[4]
+    cdef uint32_t k[2]
+    cdef uint32_t o[4]
+    for i in range(4):
+        c[i] = ctr[i]
+    k[0], k[1] = key[0], key[1]
+    cdef int rc = magpy_b200_philox_words(device, c, k, o)
+    if rc != 0:
+        _raise(rc)
+    return [o[0], o[1], o[2], o[3]]
+
+
+def gaussians(seed, member, particle, first_step, n_steps, str gauss='f32', int device=0):
+    """The (n_steps, 3) unit-variance draws the kernels use for (seed, member, particle)."""
+    cdef np.ndarray[double, ndim=2] out = np.empty((int(n_steps), 3))
+    cdef int rc = magpy_b200_gaussians(device, int(seed), int(member), int(particle), int(first_step),
+                                       int(n_steps), _GAUSS_LOOKUP[gauss], &out[0, 0])
+    if rc != 0:
+        _raise(rc)
+    return out
+
+
+def fp64_peak(int device=0):
+    """Measured sustained FP64 FMA rate of the device in TFLOP/s and the max SM clock in MHz."""
+    cdef double tf = 0.0, mhz = 0.0
+    cdef int rc
+    with nogil:
+        rc = magpy_b200_fp64_peak(device, &tf, &mhz)
+    if rc != 0:
+        _raise(rc)
+    return tf, mhz

@@ -1,0 +1,856 @@
+// magpy_b200.cu — host side of the B200-native ensemble sLLG integrator and its C ABI
+// (include/magpy_b200.h).  Replaces, for one path only, the reference's
+//   lib/simulation.cpp  (SI->reduced conversion :498-549, schedule :171-174/:342-405,
+//                        rescale :610-621)
+//   magpy/model.py:202-207 (per-member fan-out)
+// and drives the kernels in kernels.cuh.  No CPU integration path exists here: without a
+// CUDA device every compute entry point fails with MAGPY_B200_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/magpy_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+// include/constants.hpp:10-12, digit for digit (MU0 is the reference's truncated value)
+constexpr double kKB = 1.38064852e-23;
+constexpr double kMU0 = 1.25663706e-6;
+constexpr double kGYROMAG = 1.76086e11;
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(e__ == cudaErrorMemoryAllocation ? MAGPY_B200_ERR_NOMEM : MAGPY_B200_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);  \
+    } while (0)
+
+int select_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MAGPY_B200_ERR_NO_DEVICE,
+                    "no CUDA device available (%s); magpy_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(MAGPY_B200_ERR_NO_DEVICE, "device %d out of range [0,%d)", device, n);
+    CU_TRY(cudaSetDevice(device));
+    return MAGPY_B200_OK;
+}
+
+// ---- reference host arithmetic --------------------------------------------------------
+struct Reduced {
+    double V_av, K_av, H_k, tau, dt, T, h0, f, dip_pre;
+    std::vector<double> k_red, v_red, sigma;
+};
+
+// lib/simulation.cpp:498-549 (same evaluation order)
+void reduce_units(const double* radius, const double* anisotropy, size_t N, double Ms, double alpha, double T,
+                  double dt, double t_end, double H0, double f, Reduced& out) {
+    std::vector<double> vol(N);
+    double vsum = 0.0, ksum = 0.0;
+    for (size_t i = 0; i < N; ++i) {
+        vol[i] = 4.0 / 3.0 * M_PI * radius[i] * radius[i] * radius[i];
+        vsum += vol[i];
+        ksum += anisotropy[i];
+    }
+    out.V_av = vsum / N;
+    out.K_av = ksum / N;
+    out.k_red.resize(N);
+    out.v_red.resize(N);
+    out.sigma.resize(N);
+    for (size_t i = 0; i < N; ++i) {
+        out.v_red[i] = vol[i] / out.V_av;
+        out.k_red[i] = anisotropy[i] / out.K_av;
+    }
+    out.H_k = 2 * out.K_av / kMU0 / Ms;
+    out.tau = kGYROMAG * kMU0 * out.H_k / (1 + alpha * alpha);
+    out.dt = dt * out.tau;
+    out.T = t_end * out.tau;
+    for (size_t i = 0; i < N; ++i)
+        out.sigma[i] = std::sqrt(alpha * kKB * T / (out.K_av * vol[i]) / (1 + alpha * alpha));
+    out.h0 = H0 / out.H_k;
+    out.f = f / out.tau;
+    out.dip_pre = kMU0 * Ms * Ms / 8.0 / M_PI / out.K_av;  // lib/field.cpp:212-215
+}
+
+// lib/field.cpp:23-54 + lib/simulation.cpp:553-573
+double applied_field(int shape, double t, double h, double f) {
+    switch (shape) {
+        case MAGPY_B200_FIELD_SINE: return h * std::sin(2 * M_PI * f * t);
+        case MAGPY_B200_FIELD_SQUARE: return h * (int(t * f * 2) % 2 ? -1 : 1);
+        default: return h;
+    }
+}
+
+// Zero-order-hold schedule (lib/simulation.cpp:342-355) without walking every step:
+// cum[k] = smallest step count s >= cum[k-1] with fl(s*dt) > fl(k*Ts).
+int build_schedule(double dt, double T, size_t S, std::vector<uint64_t>& cum) {
+    cum.assign(S, 0);
+    const double Ts = T / (S - 1);
+    uint64_t prev = 0;
+    for (size_t k = 1; k < S; ++k) {
+        const double lim = (double)(unsigned int)k * Ts;
+        double est = std::floor(lim / dt);
+        if (!(est >= 0.0) || est > 4.0e9) return 1;
+        uint64_t s = (uint64_t)est;
+        s = s > 2 ? s - 2 : 0;
+        if (s < prev) s = prev;
+        while ((double)s * dt <= lim) ++s;          // first s that breaks the loop condition
+        while (s > prev && (double)(s - 1) * dt > lim) --s;
+        if (s > 0xFFFFFFF0ull) return 1;            // the reference's step counter is 32-bit
+        cum[k] = s;
+        prev = s;
+    }
+    return 0;
+}
+
+// ---- device buffers -------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct Chunk {
+    uint64_t j0, j1;
+    uint32_t k0, k1;
+};
+
+}  // namespace
+
+struct magpy_b200_plan {
+    int device = 0;
+    uint64_t R = 0;
+    uint32_t N = 0, n = 0;
+    uint64_t S = 0;
+    bool implicit = false, want_traj = false, injected = false;
+    int gauss_mode = 0, field_shape = MAGPY_B200_FIELD_CONSTANT;
+    double Ms = 0;
+    Reduced red;
+    std::vector<uint64_t> target;   // state index stored by sample k
+    std::vector<Chunk> chunks;
+    uint64_t total_steps = 0;
+    mb::RunParams base{};
+    unsigned grid = 0;
+    dim3 block{1, 1, 1};
+    size_t smem = 0;
+    int np = 1;
+    bool use_table = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
+    DevBuf<double> d_state0, d_state, d_axis, d_kred, d_sig, d_dip, d_traj, d_sums, d_partial, d_tab, d_dW, d_stage;
+    DevBuf<int64_t> d_seeds;
+    DevBuf<uint64_t> d_target;
+    DevBuf<unsigned long long> d_newton;
+    uint64_t launches = 0, h2d = 0, d2h = 0;
+    uint64_t max_chunk_steps = 0;
+    uint32_t max_chunk_samples = 0;
+    bool ran = false;
+
+    ~magpy_b200_plan() {
+        cudaSetDevice(device);
+        for (auto e : ev_k) cudaEventDestroy(e);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int launch_transpose(magpy_b200_plan* pl, const double* in, double* out, uint64_t batches, uint64_t rows,
+                     uint64_t cols, uint64_t in_bs, uint64_t in_rs, uint64_t out_bs, uint64_t out_rs, double scale);
+
+// ---- kernel dispatch ------------------------------------------------------------------
+template <int NOISE, bool TAB>
+int launch_integrate_nt(magpy_b200_plan* pl, const mb::RunParams& P) {
+    const dim3 g(pl->grid), b = pl->block;
+    if (pl->N == 1) {
+        if (pl->implicit) mb::imid_single_kernel<NOISE, TAB><<<g, b, 0, pl->stream>>>(P);
+        else mb::heun_single_kernel<NOISE, TAB><<<g, b, 0, pl->stream>>>(P);
+    } else if (pl->implicit) {
+        switch (pl->np) {
+            case 1: mb::imid_cluster_kernel<NOISE, TAB, 1><<<g, b, pl->smem, pl->stream>>>(P); break;
+            case 2: mb::imid_cluster_kernel<NOISE, TAB, 2><<<g, b, pl->smem, pl->stream>>>(P); break;
+            default: mb::imid_cluster_kernel<NOISE, TAB, 4><<<g, b, pl->smem, pl->stream>>>(P); break;
+        }
+    } else {
+        switch (pl->np) {
+            case 1: mb::heun_cluster_kernel<NOISE, TAB, 1><<<g, b, pl->smem, pl->stream>>>(P); break;
+            case 2: mb::heun_cluster_kernel<NOISE, TAB, 2><<<g, b, pl->smem, pl->stream>>>(P); break;
+            case 4: mb::heun_cluster_kernel<NOISE, TAB, 4><<<g, b, pl->smem, pl->stream>>>(P); break;
+            default: mb::heun_cluster_kernel<NOISE, TAB, 8><<<g, b, pl->smem, pl->stream>>>(P); break;
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    pl->launches++;
+    return MAGPY_B200_OK;
+}
+
+template <int NOISE, bool TAB>
+int set_smem_attr_nt(magpy_b200_plan* pl) {
+    if (pl->N == 1 || pl->smem <= 48 * 1024) return MAGPY_B200_OK;
+    const int bytes = (int)pl->smem;
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (pl->implicit) {
+        switch (pl->np) {
+            case 1: CU_TRY(cudaFuncSetAttribute(mb::imid_cluster_kernel<NOISE, TAB, 1>, attr, bytes)); break;
+            case 2: CU_TRY(cudaFuncSetAttribute(mb::imid_cluster_kernel<NOISE, TAB, 2>, attr, bytes)); break;
+            default: CU_TRY(cudaFuncSetAttribute(mb::imid_cluster_kernel<NOISE, TAB, 4>, attr, bytes)); break;
+        }
+    } else {
+        switch (pl->np) {
+            case 1: CU_TRY(cudaFuncSetAttribute(mb::heun_cluster_kernel<NOISE, TAB, 1>, attr, bytes)); break;
+            case 2: CU_TRY(cudaFuncSetAttribute(mb::heun_cluster_kernel<NOISE, TAB, 2>, attr, bytes)); break;
+            case 4: CU_TRY(cudaFuncSetAttribute(mb::heun_cluster_kernel<NOISE, TAB, 4>, attr, bytes)); break;
+            default: CU_TRY(cudaFuncSetAttribute(mb::heun_cluster_kernel<NOISE, TAB, 8>, attr, bytes)); break;
+        }
+    }
+    return MAGPY_B200_OK;
+}
+
+#define DISPATCH_NT(fn, pl, ...)                                                                      \
+    ((pl)->injected                                                                                   \
+         ? ((pl)->use_table ? fn<mb::NOISE_INJECTED, true>(__VA_ARGS__) : fn<mb::NOISE_INJECTED, false>(__VA_ARGS__)) \
+     : (pl)->gauss_mode == MAGPY_B200_GAUSS_F64                                                       \
+         ? ((pl)->use_table ? fn<mb::NOISE_PHILOX_F64, true>(__VA_ARGS__)                             \
+                            : fn<mb::NOISE_PHILOX_F64, false>(__VA_ARGS__))                           \
+         : ((pl)->use_table ? fn<mb::NOISE_PHILOX_F32, true>(__VA_ARGS__)                             \
+                            : fn<mb::NOISE_PHILOX_F32, false>(__VA_ARGS__)))
+
+int launch_transpose(magpy_b200_plan* pl, const double* in, double* out, uint64_t batches, uint64_t rows,
+                     uint64_t cols, uint64_t in_bs, uint64_t in_rs, uint64_t out_bs, uint64_t out_rs,
+                     double scale) {
+    // batches go through gridDim.z in slices of 65535
+    const dim3 b(32, 8);
+    for (uint64_t b0 = 0; b0 < batches; b0 += 65535) {
+        const uint64_t nb = std::min<uint64_t>(65535, batches - b0);
+        const uint64_t gy = (rows + 31) / 32;
+        if (gy > 65535) return fail(MAGPY_B200_ERR_BAD_ARG, "transpose rows too large");
+        const dim3 g((unsigned)((cols + 31) / 32), (unsigned)gy, (unsigned)nb);
+        mb::transpose_kernel<<<g, b, 0, pl->stream>>>(in + b0 * in_bs, out + b0 * out_bs, rows, cols, in_bs, in_rs,
+                                                     out_bs, out_rs, scale);
+        CU_TRY(cudaGetLastError());
+        pl->launches++;
+    }
+    return MAGPY_B200_OK;
+}
+
+int validate(const magpy_b200_ensemble* a) {
+    if (!a) return fail(MAGPY_B200_ERR_BAD_ARG, "args is NULL");
+    if (a->abi_version != MAGPY_B200_ABI_VERSION)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "abi_version %u != %d", a->abi_version, MAGPY_B200_ABI_VERSION);
+    if (a->n_members == 0) return fail(MAGPY_B200_ERR_BAD_ARG, "n_members must be >= 1");
+    if (a->n_members > 0xFFFFFFFFull) return fail(MAGPY_B200_ERR_BAD_ARG, "n_members must be < 2^32");
+    if (a->n_particles == 0) return fail(MAGPY_B200_ERR_BAD_ARG, "n_particles must be >= 1");
+    if (!a->radius || !a->anisotropy || !a->location || !a->anisotropy_axis || !a->magnetisation_direction)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "radius/anisotropy/location/anisotropy_axis/magnetisation_direction must not be NULL");
+    const uint64_t n = 3ull * a->n_particles;
+    if (a->axis_stride != 0 && a->axis_stride != n) return fail(MAGPY_B200_ERR_BAD_ARG, "axis_stride must be 0 or 3N");
+    if (a->m0_stride != 0 && a->m0_stride != n) return fail(MAGPY_B200_ERR_BAD_ARG, "m0_stride must be 0 or 3N");
+    if (a->max_samples < 2) return fail(MAGPY_B200_ERR_BAD_ARG, "max_samples must be >= 2 (lib/simulation.cpp:174)");
+    if (a->max_samples > 0x7FFFFFFFull) return fail(MAGPY_B200_ERR_BAD_ARG, "max_samples too large");
+    if (!(a->time_step > 0.0) || !(a->end_time > 0.0)) return fail(MAGPY_B200_ERR_BAD_ARG, "time_step and end_time must be > 0");
+    if (a->field_shape != MAGPY_B200_FIELD_SINE && a->field_shape != MAGPY_B200_FIELD_SQUARE &&
+        a->field_shape != MAGPY_B200_FIELD_CONSTANT)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "Must specify valid field::options enum (lib/simulation.cpp:570-572)");
+    if (!a->injected_dw && !a->seeds) return fail(MAGPY_B200_ERR_BAD_ARG, "seeds must not be NULL unless injected_dw is given");
+    if (a->gauss_mode != MAGPY_B200_GAUSS_F32 && a->gauss_mode != MAGPY_B200_GAUSS_F64)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "gauss_mode must be MAGPY_B200_GAUSS_F32 or _F64");
+    if (!(a->magnetisation > 0.0)) return fail(MAGPY_B200_ERR_BAD_ARG, "magnetisation must be > 0");
+    if (a->use_implicit) {
+        if (a->n_particles > 32) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 32 particles per cluster");
+    } else if (a->n_particles > 128) {
+        return fail(MAGPY_B200_ERR_BAD_ARG, "Heun supports at most 128 particles per cluster");
+    }
+    return MAGPY_B200_OK;
+}
+
+int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
+    int rc = validate(a);
+    if (rc) return rc;
+    rc = select_device(a->device);
+    if (rc) return rc;
+    pl->device = a->device;
+    pl->R = a->n_members;
+    pl->N = a->n_particles;
+    pl->n = 3 * pl->N;
+    pl->S = a->max_samples;
+    pl->implicit = a->use_implicit != 0;
+    pl->gauss_mode = a->gauss_mode;
+    pl->field_shape = a->field_shape;
+    pl->Ms = a->magnetisation;
+    pl->injected = a->injected_dw != nullptr;
+    pl->want_traj = a->out_trajectories != nullptr;
+    const uint64_t R = pl->R, n = pl->n;
+    const uint32_t N = pl->N;
+
+    reduce_units(a->radius, a->anisotropy, N, a->magnetisation, a->damping, a->temperature, a->time_step,
+                 a->end_time, a->field_amplitude, a->field_frequency, pl->red);
+    const Reduced& rd = pl->red;
+    if (!(rd.dt > 0.0) || !std::isfinite(rd.dt) || !std::isfinite(rd.T))
+        return fail(MAGPY_B200_ERR_BAD_ARG, "non-finite reduced time step (check anisotropy / magnetisation)");
+
+    std::vector<uint64_t> cum;
+    if (build_schedule(rd.dt, rd.T, pl->S, cum))
+        return fail(MAGPY_B200_ERR_BAD_ARG, "end_time/time_step exceeds the 32-bit step counter of the reference");
+    pl->target.resize(pl->S);
+    pl->target[0] = 0;
+    for (size_t k = 1; k < pl->S; ++k) pl->target[k] = cum[k] - 1;
+    pl->total_steps = pl->target[pl->S - 1];
+    if (pl->injected && a->injected_steps < pl->total_steps)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "injected_dw holds %llu steps but the schedule needs %llu",
+                    (unsigned long long)a->injected_steps, (unsigned long long)pl->total_steps);
+
+    // launch geometry
+    if (N == 1) {
+        pl->block = dim3(mb::SINGLE_THREADS);
+        pl->grid = (unsigned)((R + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
+        pl->smem = 0;
+        pl->np = 1;
+    } else {
+        const uint32_t max_slots = pl->implicit ? 8 : 16;
+        int np = 1;
+        while ((N + np - 1) / np > max_slots) np *= 2;
+        pl->np = np;
+        const uint32_t slots = (N + np - 1) / np;
+        pl->block = dim3(mb::CL_LANES, slots);
+        pl->grid = (unsigned)((R + mb::CL_LANES - 1) / mb::CL_LANES);
+        pl->smem = ((size_t)2 * N * 3 + (size_t)3 * slots) * mb::CL_LANES * sizeof(double);
+        if (pl->smem > 227 * 1024) return fail(MAGPY_B200_ERR_BAD_ARG, "cluster too large for shared memory");
+    }
+    pl->use_table = a->field_shape != MAGPY_B200_FIELD_CONSTANT;
+
+    // chunking: bound the field table / injected-noise window and the partial-sum buffer
+    const uint64_t max_steps = 4ull << 20;
+    const uint64_t max_partial_doubles = (512ull << 20) / 8;
+    uint32_t max_samples_chunk = (uint32_t)std::max<uint64_t>(1, max_partial_doubles / (4ull * pl->grid));
+    pl->chunks.clear();
+    {
+        uint64_t j = 0;
+        uint32_t k = 0;
+        const uint32_t S = (uint32_t)pl->S;
+        while (k < S || j < pl->total_steps) {
+            Chunk c{j, j, k, k};
+            while (c.k1 < S && c.k1 - c.k0 < max_samples_chunk && pl->target[c.k1] - c.j0 <= max_steps) {
+                c.j1 = pl->target[c.k1];
+                ++c.k1;
+            }
+            if (c.k1 == c.k0) {  // next sample is further than max_steps away: advance without sampling
+                c.j1 = std::min(pl->target[c.k0], c.j0 + max_steps);
+            }
+            pl->chunks.push_back(c);
+            j = c.j1;
+            k = c.k1;
+            if (k >= S && j >= pl->total_steps) break;
+        }
+    }
+    for (const Chunk& c : pl->chunks) {
+        pl->max_chunk_steps = std::max(pl->max_chunk_steps, c.j1 - c.j0);
+        pl->max_chunk_samples = std::max(pl->max_chunk_samples, c.k1 - c.k0);
+    }
+
+    // memory budget
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    double need = 8.0 * (3.0 * n * R + (double)n * R /*axis*/ + 4.0 * pl->S + 4.0 * pl->max_chunk_samples * pl->grid +
+                         2.0 * pl->max_chunk_steps + (double)N * N * 4);
+    if (pl->want_traj) need += 8.0 * 2.0 * (double)pl->S * n * R;
+    if (pl->injected) need += 8.0 * 2.0 * (double)pl->total_steps * n * R;
+    if (need > 0.9 * (double)free_b)
+        return fail(MAGPY_B200_ERR_NOMEM, "request needs %.1f GB of device memory, %.1f GB free", need / 1e9, free_b / 1e9);
+
+    CU_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreate(&pl->ev_begin));
+    CU_TRY(cudaEventCreate(&pl->ev_end));
+    pl->ev_k.resize(2 * pl->chunks.size());
+    for (auto& e : pl->ev_k) CU_TRY(cudaEventCreate(&e));
+
+    // uploads
+    CU_TRY(pl->d_state0.alloc(n * R));
+    CU_TRY(pl->d_state.alloc(n * R));
+    CU_TRY(pl->d_kred.alloc(N));
+    CU_TRY(pl->d_sig.alloc(N));
+    CU_TRY(pl->d_seeds.alloc(R));
+    CU_TRY(pl->d_target.alloc(pl->S));
+    CU_TRY(pl->d_sums.alloc(pl->S * 4));
+    CU_TRY(pl->d_partial.alloc((size_t)4 * pl->max_chunk_samples * pl->grid));
+    CU_TRY(pl->d_newton.alloc(3));
+    if (pl->use_table) CU_TRY(pl->d_tab.alloc(2 * std::max<uint64_t>(1, pl->max_chunk_steps)));
+    CU_TRY(cudaMemcpyAsync(pl->d_kred.p, rd.k_red.data(), N * 8, cudaMemcpyHostToDevice, pl->stream));
+    CU_TRY(cudaMemcpyAsync(pl->d_sig.p, rd.sigma.data(), N * 8, cudaMemcpyHostToDevice, pl->stream));
+    CU_TRY(cudaMemcpyAsync(pl->d_target.p, pl->target.data(), pl->S * 8, cudaMemcpyHostToDevice, pl->stream));
+    pl->h2d += N * 16 + pl->S * 8;
+    std::vector<int64_t> zero_seeds;
+    const int64_t* seeds = a->seeds;
+    if (!seeds) {
+        zero_seeds.assign(R, 0);
+        seeds = zero_seeds.data();
+    }
+    CU_TRY(cudaMemcpyAsync(pl->d_seeds.p, seeds, R * 8, cudaMemcpyHostToDevice, pl->stream));
+    pl->h2d += R * 8;
+
+    // per-member arrays arrive [R][n]; the device wants [n][R]
+    const bool need_stage = a->m0_stride || a->axis_stride || pl->injected || true;
+    (void)need_stage;
+    {
+        size_t stage = n * R;
+        if (pl->injected) stage = std::max<size_t>(stage, (size_t)pl->total_steps * n * R);
+        if (pl->want_traj) stage = std::max<size_t>(stage, (size_t)pl->S * n * R);
+        CU_TRY(pl->d_stage.alloc(stage));
+    }
+    if (a->m0_stride) {
+        CU_TRY(cudaMemcpyAsync(pl->d_stage.p, a->magnetisation_direction, n * R * 8, cudaMemcpyHostToDevice, pl->stream));
+        pl->h2d += n * R * 8;
+        rc = launch_transpose(pl, pl->d_stage.p, pl->d_state0.p, 1, R, n, 0, n, 0, R, 1.0);
+        if (rc) return rc;
+    } else {
+        std::vector<double> rep(n * R);
+        for (uint64_t q = 0; q < n; ++q) std::fill_n(rep.begin() + q * R, R, a->magnetisation_direction[q]);
+        CU_TRY(cudaMemcpyAsync(pl->d_state0.p, rep.data(), n * R * 8, cudaMemcpyHostToDevice, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->h2d += n * R * 8;
+    }
+    if (a->axis_stride) {
+        CU_TRY(pl->d_axis.alloc(n * R));
+        CU_TRY(cudaMemcpyAsync(pl->d_stage.p, a->anisotropy_axis, n * R * 8, cudaMemcpyHostToDevice, pl->stream));
+        pl->h2d += n * R * 8;
+        rc = launch_transpose(pl, pl->d_stage.p, pl->d_axis.p, 1, R, n, 0, n, 0, R, 1.0);
+        if (rc) return rc;
+    } else {
+        CU_TRY(pl->d_axis.alloc(n));
+        CU_TRY(cudaMemcpyAsync(pl->d_axis.p, a->anisotropy_axis, n * 8, cudaMemcpyHostToDevice, pl->stream));
+        pl->h2d += n * 8;
+    }
+    if (pl->injected) {
+        // host [R][steps][n] -> device [steps][n][R]
+        const uint64_t T = pl->total_steps;
+        CU_TRY(pl->d_dW.alloc(std::max<uint64_t>(1, T * n * R)));
+        if (T > 0) {
+            if (a->injected_steps == T) {
+                CU_TRY(cudaMemcpyAsync(pl->d_stage.p, a->injected_dw, T * n * R * 8, cudaMemcpyHostToDevice, pl->stream));
+            } else {
+                CU_TRY(cudaMemcpy2DAsync(pl->d_stage.p, T * n * 8, a->injected_dw, a->injected_steps * n * 8, T * n * 8, R,
+                                         cudaMemcpyHostToDevice, pl->stream));
+            }
+            pl->h2d += T * n * R * 8;
+            rc = launch_transpose(pl, pl->d_stage.p, pl->d_dW.p, 1, R, T * n, 0, T * n, 0, R, 1.0);
+            if (rc) return rc;
+        }
+    }
+    // dipolar pair table (lib/distances.cpp:20-113, lib/simulation.cpp:577-583, lib/field.cpp:187-225)
+    if (N > 1) {
+        std::vector<double> tab((size_t)N * N * 4, 0.0);
+        const double lscale = std::pow(rd.V_av, 1. / 3);
+        for (uint32_t i = 0; i < N; ++i)
+            for (uint32_t jx = 0; jx < N; ++jx) {
+                if (i == jx) continue;
+                double d[3];
+                for (int c = 0; c < 3; ++c) d[c] = a->location[3 * jx + c] - a->location[3 * i + c];
+                const double mag = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                const double cube = std::pow(mag / lscale, 3);
+                double* t = &tab[((size_t)i * N + jx) * 4];
+                t[0] = d[0] / mag; t[1] = d[1] / mag; t[2] = d[2] / mag;
+                t[3] = rd.dip_pre * (rd.v_red[jx] / cube);
+            }
+        CU_TRY(pl->d_dip.alloc(tab.size()));
+        CU_TRY(cudaMemcpyAsync(pl->d_dip.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->h2d += tab.size() * 8;
+    }
+    if (pl->want_traj) CU_TRY(pl->d_traj.alloc((size_t)pl->S * n * R));
+    CU_TRY(cudaStreamSynchronize(pl->stream));
+
+    rc = DISPATCH_NT(set_smem_attr_nt, pl, pl);
+    if (rc) return rc;
+
+    mb::RunParams& P = pl->base;
+    P.R = R;
+    P.N = N;
+    P.renorm = a->renorm;
+    P.interactions = (a->interactions != 0 && N > 1) ? 1 : 0;
+    P.alpha = a->damping;
+    P.dt = rd.dt;
+    P.sqrt_dt = std::sqrt(rd.dt);
+    P.eps = a->implicit_tol;
+    P.clampA = std::sqrt(2 * 1000.0 * std::abs(std::log(rd.dt)));  // lib/integrators.cpp:598-599
+    P.h_const = rd.h0;
+    P.k_red = pl->d_kred.p;
+    P.sig = pl->d_sig.p;
+    P.dip = pl->d_dip.p;
+    P.axis = pl->d_axis.p;
+    P.axis_cs = a->axis_stride ? R : 1;
+    P.axis_rs = a->axis_stride ? 1 : 0;
+    P.seeds = pl->d_seeds.p;
+    P.stream_offset = a->stream_offset;
+    P.state = pl->d_state.p;
+    P.target = pl->d_target.p;
+    P.field_tab = pl->d_tab.p;
+    P.dW = pl->d_dW.p;
+    P.dW_j0 = 0;
+    P.traj = pl->d_traj.p;
+    P.partial = pl->d_partial.p;
+    P.newton = pl->d_newton.p;
+    return MAGPY_B200_OK;
+}
+
+int plan_run(magpy_b200_plan* pl) {
+    CU_TRY(cudaSetDevice(pl->device));
+    const uint64_t nR = (uint64_t)pl->n * pl->R;
+    CU_TRY(cudaEventRecord(pl->ev_begin, pl->stream));
+    CU_TRY(cudaMemcpyAsync(pl->d_state.p, pl->d_state0.p, nR * 8, cudaMemcpyDeviceToDevice, pl->stream));
+    CU_TRY(cudaMemsetAsync(pl->d_newton.p, 0, 3 * sizeof(unsigned long long), pl->stream));
+    CU_TRY(cudaMemsetAsync(pl->d_sums.p, 0, pl->S * 4 * 8, pl->stream));
+    const double second = pl->implicit ? pl->red.dt / 2 : pl->red.dt;
+    size_t ci = 0;
+    for (const Chunk& c : pl->chunks) {
+        mb::RunParams P = pl->base;
+        P.j0 = c.j0; P.j1 = c.j1; P.k0 = c.k0; P.k1 = c.k1;
+        const uint64_t ns = c.j1 - c.j0;
+        if (pl->use_table && ns > 0) {
+            mb::field_table_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, pl->stream>>>(
+                pl->d_tab.p, c.j0, ns, pl->red.dt, second, pl->field_shape, pl->red.h0, pl->red.f);
+            CU_TRY(cudaGetLastError());
+            pl->launches++;
+        }
+        CU_TRY(cudaEventRecord(pl->ev_k[2 * ci], pl->stream));
+        int rc = DISPATCH_NT(launch_integrate_nt, pl, pl, P);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(pl->ev_k[2 * ci + 1], pl->stream));
+        if (c.k1 > c.k0) {
+            mb::reduce_partials_kernel<<<c.k1 - c.k0, 256, 0, pl->stream>>>(pl->d_partial.p, pl->d_sums.p, c.k0, pl->grid);
+            CU_TRY(cudaGetLastError());
+            pl->launches++;
+        }
+        ++ci;
+    }
+    CU_TRY(cudaEventRecord(pl->ev_end, pl->stream));
+    pl->ran = true;
+    return MAGPY_B200_OK;
+}
+
+int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
+    CU_TRY(cudaSetDevice(pl->device));
+    CU_TRY(cudaStreamSynchronize(pl->stream));
+    if (!st) return MAGPY_B200_OK;
+    std::memset(st, 0, sizeof *st);
+    st->steps_per_member = pl->total_steps;
+    st->particle_steps = pl->total_steps * pl->R * pl->N;
+    st->kernel_launches = pl->launches;
+    st->h2d_bytes = pl->h2d;
+    st->d2h_bytes = pl->d2h;
+    if (pl->ran) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, pl->ev_begin, pl->ev_end));
+        st->device_ms = ms;
+        double acc = 0.0;
+        for (size_t i = 0; i < pl->chunks.size(); ++i) {
+            CU_TRY(cudaEventElapsedTime(&ms, pl->ev_k[2 * i], pl->ev_k[2 * i + 1]));
+            acc += ms;
+        }
+        st->integrate_ms = acc;
+        unsigned long long nw[3];
+        CU_TRY(cudaMemcpy(nw, pl->d_newton.p, sizeof nw, cudaMemcpyDeviceToHost));
+        st->newton_iterations = nw[0];
+        st->newton_max_iterations = nw[1];
+        st->newton_failures = nw[2];
+    }
+    return MAGPY_B200_OK;
+}
+
+int plan_fetch(magpy_b200_plan* pl, double* out_time, double* out_field, double* out_traj, double* out_sums,
+               double* out_final) {
+    CU_TRY(cudaSetDevice(pl->device));
+    const Reduced& rd = pl->red;
+    const uint64_t S = pl->S, n = pl->n, R = pl->R;
+    const double Ts = rd.T / (S - 1);
+    // lib/simulation.cpp:398-401 then :613-616
+    if (out_time)
+        for (uint64_t k = 0; k < S; ++k) out_time[k] = ((double)(unsigned int)k * Ts) / rd.tau;
+    if (out_field)
+        for (uint64_t k = 0; k < S; ++k)
+            out_field[k] = applied_field(pl->field_shape, (double)(unsigned int)k * Ts, rd.h0, rd.f) * rd.H_k;
+    if (out_sums) {
+        CU_TRY(cudaMemcpyAsync(out_sums, pl->d_sums.p, S * 4 * 8, cudaMemcpyDeviceToHost, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->d2h += S * 4 * 8;
+        for (uint64_t k = 0; k < S; ++k) {
+            out_sums[4 * k + 0] *= pl->Ms;
+            out_sums[4 * k + 1] *= pl->Ms;
+            out_sums[4 * k + 2] *= pl->Ms;
+            out_sums[4 * k + 3] *= pl->Ms * pl->Ms;
+        }
+    }
+    if (out_final) {
+        int rc = launch_transpose(pl, pl->d_state.p, pl->d_stage.p, 1, n, R, 0, R, 0, n, pl->Ms);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(out_final, pl->d_stage.p, n * R * 8, cudaMemcpyDeviceToHost, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->d2h += n * R * 8;
+    }
+    if (out_traj) {
+        if (!pl->want_traj) return fail(MAGPY_B200_ERR_BAD_ARG, "plan was created without out_trajectories");
+        // device [S][n][R] -> host [R][n][S], scaled to A/m (lib/simulation.cpp:617-620)
+        int rc = launch_transpose(pl, pl->d_traj.p, pl->d_stage.p, n, S, R, R, n * R, S, n * S, pl->Ms);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(out_traj, pl->d_stage.p, S * n * R * 8, cudaMemcpyDeviceToHost, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->d2h += S * n * R * 8;
+    }
+    return MAGPY_B200_OK;
+}
+
+}  // namespace
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+extern "C" {
+
+int magpy_b200_abi_version(void) { return MAGPY_B200_ABI_VERSION; }
+const char* magpy_b200_last_error(void) { return g_error.c_str(); }
+
+int magpy_b200_device_count(int* count) {
+    if (!count) return fail(MAGPY_B200_ERR_BAD_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return MAGPY_B200_OK;
+}
+
+double magpy_b200_get_KB(void) { return kKB; }
+double magpy_b200_get_mu0(void) { return kMU0; }
+double magpy_b200_get_gamma(void) { return kGYROMAG; }
+
+int magpy_b200_reduce_units(const double* radius, const double* anisotropy, size_t N, double Ms, double alpha,
+                            double T, double dt, double t_end, double H0, double f, double* k_red, double* v_red,
+                            double* sigma, double* out) {
+    if (!radius || !anisotropy || N == 0 || !out) return fail(MAGPY_B200_ERR_BAD_ARG, "bad arguments");
+    Reduced r;
+    reduce_units(radius, anisotropy, N, Ms, alpha, T, dt, t_end, H0, f, r);
+    for (size_t i = 0; i < N; ++i) {
+        if (k_red) k_red[i] = r.k_red[i];
+        if (v_red) v_red[i] = r.v_red[i];
+        if (sigma) sigma[i] = r.sigma[i];
+    }
+    out[0] = r.V_av; out[1] = r.K_av; out[2] = r.H_k; out[3] = r.tau; out[4] = r.dt;
+    out[5] = r.T; out[6] = r.h0; out[7] = r.f; out[8] = r.dip_pre;
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_schedule(double dt_red, double t_end_red, size_t S, uint64_t* cum) {
+    if (S < 2 || !cum || !(dt_red > 0)) return fail(MAGPY_B200_ERR_BAD_ARG, "bad arguments");
+    std::vector<uint64_t> c;
+    if (build_schedule(dt_red, t_end_red, S, c)) return fail(MAGPY_B200_ERR_BAD_ARG, "step count exceeds 32 bits");
+    std::copy(c.begin(), c.end(), cum);
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_plan_create(const magpy_b200_ensemble* args, magpy_b200_plan** plan) {
+    if (!plan) return fail(MAGPY_B200_ERR_BAD_ARG, "plan is NULL");
+    *plan = nullptr;
+    magpy_b200_plan* pl = new (std::nothrow) magpy_b200_plan();
+    if (!pl) return fail(MAGPY_B200_ERR_NOMEM, "out of host memory");
+    int rc;
+    try {
+        rc = plan_build(args, pl);
+    } catch (const std::bad_alloc&) {
+        rc = fail(MAGPY_B200_ERR_NOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        rc = fail(MAGPY_B200_ERR_BAD_ARG, "%s", e.what());
+    }
+    if (rc) {
+        delete pl;
+        return rc;
+    }
+    *plan = pl;
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_plan_run(magpy_b200_plan* plan) {
+    if (!plan) return fail(MAGPY_B200_ERR_BAD_ARG, "plan is NULL");
+    return plan_run(plan);
+}
+
+int magpy_b200_plan_sync(magpy_b200_plan* plan, magpy_b200_stats* stats) {
+    if (!plan) return fail(MAGPY_B200_ERR_BAD_ARG, "plan is NULL");
+    return plan_sync(plan, stats);
+}
+
+int magpy_b200_plan_fetch(magpy_b200_plan* plan, double* out_time, double* out_field, double* out_trajectories,
+                          double* out_sums, double* out_final) {
+    if (!plan) return fail(MAGPY_B200_ERR_BAD_ARG, "plan is NULL");
+    try {
+        return plan_fetch(plan, out_time, out_field, out_trajectories, out_sums, out_final);
+    } catch (const std::exception& e) {
+        return fail(MAGPY_B200_ERR_NOMEM, "%s", e.what());
+    }
+}
+
+int magpy_b200_plan_sums_device_ptr(magpy_b200_plan* plan, void** dptr, size_t* n_doubles) {
+    if (!plan || !dptr) return fail(MAGPY_B200_ERR_BAD_ARG, "bad arguments");
+    *dptr = plan->d_sums.p;
+    if (n_doubles) *n_doubles = plan->S * 4;
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_plan_destroy(magpy_b200_plan* plan) {
+    delete plan;
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_simulate_ensemble(const magpy_b200_ensemble* args, magpy_b200_stats* stats) {
+    magpy_b200_plan* pl = nullptr;
+    int rc = magpy_b200_plan_create(args, &pl);
+    if (rc) return rc;
+    rc = plan_run(pl);
+    if (!rc) rc = plan_sync(pl, nullptr);
+    if (!rc)
+        rc = magpy_b200_plan_fetch(pl, args->out_time, args->out_field, args->out_trajectories, args->out_sums,
+                                   args->out_final);
+    if (!rc) rc = plan_sync(pl, stats);
+    delete pl;
+    return rc;
+}
+
+int magpy_b200_simulate(const double* radius, const double* anisotropy, const double* anisotropy_axis,
+                        const double* magnetisation_direction, const double* location, size_t n_particles,
+                        double magnetisation, double damping, double temperature, int renorm, int interactions,
+                        int use_implicit, double eps, double time_step, double end_time, size_t max_samples,
+                        int64_t seed, int field_shape, double field_amplitude, double field_frequency,
+                        double* out_time, double* out_field, double* out_m, magpy_b200_stats* stats) {
+    magpy_b200_ensemble a;
+    std::memset(&a, 0, sizeof a);
+    a.abi_version = MAGPY_B200_ABI_VERSION;
+    a.device = 0;
+    a.n_members = 1;
+    a.n_particles = (uint32_t)n_particles;
+    a.radius = radius;
+    a.anisotropy = anisotropy;
+    a.location = location;
+    a.anisotropy_axis = anisotropy_axis;
+    a.magnetisation_direction = magnetisation_direction;
+    a.magnetisation = magnetisation;
+    a.damping = damping;
+    a.temperature = temperature;
+    a.renorm = renorm;
+    a.interactions = interactions;
+    a.use_implicit = use_implicit;
+    a.implicit_tol = eps;
+    a.time_step = time_step;
+    a.end_time = end_time;
+    a.max_samples = max_samples;
+    a.field_shape = field_shape;
+    a.field_amplitude = field_amplitude;
+    a.field_frequency = field_frequency;
+    a.seeds = &seed;
+    a.gauss_mode = MAGPY_B200_GAUSS_F32;
+    a.out_time = out_time;
+    a.out_field = out_field;
+    a.out_trajectories = out_m;  // [1][N][3][S]
+    if (n_particles == 0 || n_particles > 0xFFFFFFFFull) return fail(MAGPY_B200_ERR_BAD_ARG, "n_particles out of range");
+    if (!out_m) return fail(MAGPY_B200_ERR_BAD_ARG, "out_m is NULL");
+    return magpy_b200_simulate_ensemble(&a, stats);
+}
+
+int magpy_b200_philox_words(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    DevBuf<uint32_t> d;
+    CU_TRY(d.alloc(4));
+    mb::philox_words_kernel<<<1, 1>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], d.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, d.p, 16, cudaMemcpyDeviceToHost));
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t particle, uint64_t first_step,
+                         uint64_t n_steps, int gauss_mode, double* out) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (!out || n_steps == 0) return fail(MAGPY_B200_ERR_BAD_ARG, "bad arguments");
+    DevBuf<double> d;
+    CU_TRY(d.alloc(3 * n_steps));
+    const unsigned g = (unsigned)((n_steps + 255) / 256);
+    if (gauss_mode == MAGPY_B200_GAUSS_F64)
+        mb::gaussians_kernel<1><<<g, 256>>>((uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p);
+    else
+        mb::gaussians_kernel<0><<<g, 256>>>((uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, d.p, 3 * n_steps * 8, cudaMemcpyDeviceToHost));
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (!tflops) return fail(MAGPY_B200_ERR_BAD_ARG, "tflops is NULL");
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+    DevBuf<double> d;
+    CU_TRY(d.alloc((size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(cudaEventRecord(e0));
+        mb::fp64_peak_kernel<<<blocks, threads>>>(d.p, iters, 0.999999, 1e-7);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)blocks * threads * iters * 64.0 * 2.0;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    return MAGPY_B200_OK;
+}
+
+}  // extern "C"

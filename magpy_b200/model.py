@@ -1,0 +1,185 @@
+"""``Model`` / ``EnsembleModel`` with the interface of the reference's ``magpy/model.py``.
+
+``Model`` is unchanged in meaning (magpy/model.py:16-115).  ``EnsembleModel.simulate``
+(magpy/model.py:159-208) keeps its signature and the derivation of the per-member seeds
+from `random_state`, but replaces the joblib process pool by ONE batched device call per
+group of members that share geometry and material (members may differ freely in
+`anisotropy_axis` and `magnetisation_direction` inside a group).
+"""
+import numpy as np
+
+from . import core
+from .results import Results, EnsembleResults
+
+_PER_MEMBER_FAST = ('anisotropy_axis', 'magnetisation_direction')
+_TRAJ_BYTES_AUTO = 2 << 30
+
+
+class Model:
+    """A cluster of interacting magnetic nanoparticles (magpy/model.py:16-68).
+
+    Args:
+        radius (list of double): radius of each spherical particle [m]
+        anisotropy (list of double): uniaxial anisotropy constant of each particle [J/m^3]
+        anisotropy_axis (list of ndarray[double,3]): unit anisotropy axis of each particle
+        magnetisation_direction (list of ndarray[double,3]): initial magnetisation direction
+        location (list of ndarray[double,3]): particle coordinates [m]
+        magnetisation (double): saturation magnetisation of all particles [A/m]
+        damping (double): damping constant of all particles
+        temperature (double): ambient temperature [K]
+        field_shape (str, optional): 'constant', 'square' or 'sine' (applied along z)
+        field_frequency (double, optional): [Hz]
+        field_amplitude (double, optional): [A/m]
+    """
+    def __init__(self, radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
+                 magnetisation, damping, temperature, field_shape='constant', field_frequency=0.0,
+                 field_amplitude=0.0):
+        self.radius = np.array(radius)
+        self.anisotropy = np.array(anisotropy)
+        self.anisotropy_axis = np.array(anisotropy_axis)
+        self.magnetisation_direction = np.array(magnetisation_direction)
+        self.location = np.array(location)
+        self.magnetisation = magnetisation
+        self.damping = damping
+        self.temperature = temperature
+        self.field_shape = field_shape
+        self.field_frequency = field_frequency
+        self.field_amplitude = field_amplitude
+
+    def simulate(self, end_time, time_step, max_samples, seed=1001, renorm=False, interactions=True,
+                 implicit_solve=True, implicit_tol=1e-9):
+        """Simulate the cluster; same arguments and defaults as magpy/model.py:70-115."""
+        res = core.simulate(
+            np.ascontiguousarray(self.radius, dtype=np.float64).reshape(-1),
+            np.ascontiguousarray(self.anisotropy, dtype=np.float64).reshape(-1),
+            np.ascontiguousarray(self.anisotropy_axis, dtype=np.float64).reshape(-1, 3),
+            np.ascontiguousarray(self.magnetisation_direction, dtype=np.float64).reshape(-1, 3),
+            np.ascontiguousarray(self.location, dtype=np.float64).reshape(-1, 3),
+            self.magnetisation, self.damping, self.temperature, renorm, interactions,
+            implicit_solve, time_step, end_time, max_samples, seed,
+            self.field_shape, self.field_amplitude, self.field_frequency, implicit_tol)
+        return Results(**res)
+
+
+def _group_key(params, keys):
+    parts = []
+    for k in keys:
+        v = params[k]
+        if isinstance(v, np.ndarray):
+            parts.append((k, v.shape, v.tobytes()))
+        else:
+            parts.append((k, v))
+    return tuple(parts)
+
+
+class EnsembleModel:
+    """Ensemble of particle clusters (magpy/model.py:118-156).
+
+    Args:
+        N (int): number of clusters in the ensemble
+        base_model (Model): default parameters of every member
+        **kwargs: a Model parameter name and a list of `N` values, one per member
+    """
+    def __init__(self, N, base_model, **kwargs):
+        self.ensemble_size = N
+        self.base_model_params = base_model.__dict__
+        for key, vals in kwargs.items():
+            if key not in self.base_model_params:
+                raise TypeError("__init__() got an unexpected keyword argument '%s'" % key)
+            if len(vals) < N:
+                raise IndexError('list index out of range')
+        self._overrides = kwargs
+        self._models = None
+
+    @property
+    def model_params(self):
+        return [dict(self.base_model_params, **{key: self._overrides[key][i] for key in self._overrides})
+                for i in range(self.ensemble_size)]
+
+    @property
+    def models(self):
+        # built on demand: the reference deep-copies N Models eagerly (magpy/model.py:149-156)
+        if self._models is None:
+            self._models = [Model(**params) for params in self.model_params]
+        return self._models
+
+    def _member_seeds(self, random_state):
+        # magpy/model.py:202-203
+        np.random.seed(random_state)
+        return np.random.randint(np.iinfo(np.int32).max, size=self.ensemble_size)
+
+    def simulate(self, end_time, time_step, max_samples, random_state, renorm=False, interactions=True,
+                 n_jobs=1, implicit_solve=True, implicit_tol=1e-9, device=0, stream_offset=0,
+                 return_trajectories=None, gauss='f32', shard=None):
+        """Simulate every member; arguments up to `implicit_tol` as magpy/model.py:159-208.
+
+        `n_jobs` is accepted and ignored (the ensemble runs as one device launch).
+        Extra keyword arguments (defaults keep the reference behaviour):
+            device (int): CUDA device ordinal.
+            stream_offset (int): global index of member 0 (used when an ensemble is sharded).
+            return_trajectories (bool|None): keep per-member trajectories; None = keep them
+                when they take less than 2 GiB.
+            gauss ('f32'|'f64'): Gaussian transform of the in-kernel Philox stream.
+            shard ((rank, world_size)|None): integrate only this rank's contiguous slice of the
+                members (magpy_b200.sharding.shard_bounds) and all-reduce the ensemble sums over the
+                initialised torch.distributed group; per-member outputs then cover the local slice.
+        """
+        R = self.ensemble_size
+        seeds = self._member_seeds(random_state)
+        lo, hi = 0, R
+        if shard is not None:
+            from .sharding import shard_bounds
+            lo, hi = shard_bounds(R, shard[1], shard[0])
+            if hi == lo:
+                raise ValueError('ensemble of %d members cannot be sharded over %d ranks' % (R, shard[1]))
+        base = self.base_model_params
+        N = int(np.asarray(base['radius']).reshape(-1).shape[0])
+        if return_trajectories is None:
+            return_trajectories = (hi - lo) * N * 3 * int(max_samples) * 8 <= _TRAJ_BYTES_AUTO
+
+        other_keys = [k for k in self._overrides if k not in _PER_MEMBER_FAST]
+        if other_keys:
+            groups = {}
+            for i in range(lo, hi):
+                params = {k: np.asarray(self._overrides[k][i]) if isinstance(base[k], np.ndarray)
+                          else self._overrides[k][i] for k in other_keys}
+                groups.setdefault(_group_key(params, other_keys), []).append(i)
+            groups = [np.asarray(v) for v in groups.values()]
+        else:
+            groups = [np.arange(lo, hi)]
+
+        S = int(max_samples)
+        traj = np.empty((hi - lo, N, 3, S)) if return_trajectories else None
+        final = np.empty((hi - lo, N, 3))
+        sums = np.zeros((S, 4))
+        time = field = None
+        stats = []
+        for idx in groups:
+            first = int(idx[0])
+            params = dict(base, **{k: self._overrides[k][first] for k in other_keys})
+
+            def member_array(key):
+                if key in self._overrides:
+                    return np.ascontiguousarray(
+                        np.asarray([self._overrides[key][i] for i in idx], dtype=np.float64).reshape(len(idx), N, 3))
+                return np.ascontiguousarray(np.asarray(base[key], dtype=np.float64).reshape(N, 3))
+
+            out = core.simulate_ensemble(
+                params['radius'], params['anisotropy'], member_array('anisotropy_axis'),
+                member_array('magnetisation_direction'), params['location'], params['magnetisation'],
+                params['damping'], params['temperature'], renorm, interactions, implicit_solve, time_step,
+                end_time, S, seeds[idx], params['field_shape'], params['field_amplitude'],
+                params['field_frequency'], implicit_tol, device=device,
+                stream_offset=int(stream_offset) + first, return_trajectories=return_trajectories,
+                return_sums=True, return_final=True, gauss=gauss)
+            if time is None:
+                time, field = out['time'], out['field']
+            if return_trajectories:
+                traj[idx - lo] = out['trajectories']
+            final[idx - lo] = out['final']
+            sums += out['sums']
+            stats.append(out['stats'])
+        if shard is not None:
+            from .sharding import allreduce_sums
+            allreduce_sums(sums)
+        return EnsembleResults.from_arrays(time, field, R, trajectories=traj, sums=sums, final=final, stats=stats)

@@ -126,6 +126,39 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* The three unit-variance draws the product uses for (seed, member, particle, step):
+ * restatement of magpy_b200/csrc/rng.cuh (philox_gauss3) for the parity tests.
+ * mode 0: fp32 Box-Muller of one Philox block (device uses SFU approximations, so compare
+ *         with a ~1e-5 tolerance); mode 1: fp64 Box-Muller from 53-bit uniforms, two blocks. */
+void orc_philox_gauss3(uint64_t seed, uint32_t member, uint32_t particle, uint64_t step, int mode, double out[3]) {
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32), particle, member}, w[4];
+    orc_philox4x32_10(ctr, key, w);
+    if (mode == 0) {
+        const float u1 = fmaf((float)w[0], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        const float u2 = fmaf((float)w[2], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        const float r1 = sqrtf(-2.0f * logf(u1)), r2 = sqrtf(-2.0f * logf(u2));
+        const float a1 = 6.2831853071795865f * ((float)w[1] * 2.3283064365386963e-10f);
+        const float a2 = 6.2831853071795865f * ((float)w[3] * 2.3283064365386963e-10f);
+        out[0] = (double)(r1 * cosf(a1));
+        out[1] = (double)(r1 * sinf(a1));
+        out[2] = (double)(r2 * cosf(a2));
+    } else {
+        const double two53 = 1.1102230246251565e-16;
+        double u1 = ((double)(((((uint64_t)w[1]) << 32) | w[0]) >> 11) + 0.5) * two53;
+        double u2 = ((double)(((((uint64_t)w[3]) << 32) | w[2]) >> 11) + 0.5) * two53;
+        double r = sqrt(-2.0 * log(u1));
+        out[0] = r * cos(2.0 * M_PI * u2);
+        out[1] = r * sin(2.0 * M_PI * u2);
+        ctr[2] = particle | (1u << 24);
+        orc_philox4x32_10(ctr, key, w);
+        u1 = ((double)(((((uint64_t)w[1]) << 32) | w[0]) >> 11) + 0.5) * two53;
+        u2 = ((double)(((((uint64_t)w[3]) << 32) | w[2]) >> 11) + 0.5) * two53;
+        r = sqrt(-2.0 * log(u1));
+        out[2] = r * cos(2.0 * M_PI * u2);
+    }
+}
+
 /* ------------------------------------------------------------------------- *
  * Leaf functions                                                             *
  * ------------------------------------------------------------------------- */
@@ -186,6 +219,22 @@ double orc_field_value(int shape, double t, double h, double f) {
         case ORC_SQUARE: return h * (((int)(t * f * 2)) % 2 ? -1 : 1);
         default: return h;
     }
+}
+
+/* lib/field.cpp:187-225 (prefactor :212-215, pair term :217-225): adds, for every i, the
+ * dipolar field of all j != i, j ascending. dists [N][N][3] unit vectors, dist_cubes [N][N]. */
+void orc_multi_add_dipolar(double* field, double ms, double k_av, const double* v_red, const double* mag,
+                           const double* dists, const double* dist_cubes, int N) {
+    const double pre = ORC_MU0 * ms * ms / 8.0 / M_PI / k_av;
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            if (j == i) continue;
+            const double* mj = mag + 3 * j;
+            const double* d = dists + (size_t)i * N * 3 + j * 3;
+            const double dotp = mj[0] * d[0] + mj[1] * d[1] + mj[2] * d[2];
+            const double t1 = v_red[j] / dist_cubes[i * N + j];
+            for (int c = 0; c < 3; ++c) field[3 * i + c] += pre * t1 * (3 * dotp * d[c] - mj[c]);
+        }
 }
 
 /* ------------------------------------------------------------------------- *
@@ -366,18 +415,8 @@ static void llg_heff(const orc_llg* S, double* h, const double* m, double t) {
     }
     const double happ = orc_field_value(S->field_shape, t, S->h0, S->f_red);
     for (int n = 0; n < N; ++n) h[3 * n + 2] += happ;
-    if (S->interactions) {
-        const double pre = ORC_MU0 * S->Ms * S->Ms / 8.0 / M_PI / S->K_av; /* lib/field.cpp:212-215 */
-        for (int i = 0; i < N; ++i)
-            for (int j = 0; j < N; ++j) {
-                if (j == i) continue;
-                const double* mj = m + 3 * j;
-                const double* d = S->runit + (size_t)i * N * 3 + j * 3;
-                const double dotp = mj[0] * d[0] + mj[1] * d[1] + mj[2] * d[2];
-                const double t1 = S->v_red[j] / S->rcube[i * N + j];
-                for (int c = 0; c < 3; ++c) h[3 * i + c] += pre * t1 * (3 * dotp * d[c] - mj[c]);
-            }
-    }
+    if (S->interactions)
+        orc_multi_add_dipolar(h, S->Ms, S->K_av, S->v_red, m, S->runit, S->rcube, N);
 }
 
 /* lib/llg.cpp:332-348 (drift :257-266, dense diffusion :296-324) */
@@ -493,8 +532,10 @@ void orc_schedule(double dt_red, double T_red, size_t S, uint64_t* cum) {
  * noise: dW_inject == NULL  -> RngMtNorm(seed,1.0) stream (:586)              *
  *        dW_inject != NULL  -> consumed in order, 3N values per step          *
  *                              (RngArray semantics, lib/rng.cpp:67-94)        *
- * out_m layout [particle][component][sample]; iters[2] = {total, max} quasi-  *
- * Newton iterations; returns number of steps whose implicit solve failed.     *
+ * out_m layout [particle][component][sample]; iters[3] = {total, max, count of *
+ * the last executed step} quasi-Newton iterations (the last executed step is   *
+ * never observed by a sample; the product skips it); returns number of steps    *
+ * whose implicit solve failed.                                                  *
  * ------------------------------------------------------------------------- */
 long orc_simulate(int N, const double* radius, const double* anisotropy, const double* axis, const double* m0,
                   const double* location, double Ms, double alpha, double T, int renorm, int interactions,
@@ -539,7 +580,7 @@ long orc_simulate(int N, const double* radius, const double* anisotropy, const d
     unsigned int step = 0;
     double t = 0;
     size_t used = 0;
-    long fails = 0, it_total = 0, it_max = 0;
+    long fails = 0, it_total = 0, it_max = 0, it_last = 0;
     for (unsigned int k = 1; k < S; ++k) {
         while (t <= k * Ts) {
             for (int i = 0; i < n3; ++i) p[i] = nx[i];
@@ -555,6 +596,7 @@ long orc_simulate(int N, const double* radius, const double* anisotropy, const d
                                                    ipiv, &it);
                 if (e) ++fails;
                 it_total += it;
+                it_last = it;
                 if (it > it_max) it_max = it;
             } else {
                 orc_heun_step(nx, p, w, llg_sde, &sys, n3, n3, t, dtr, work);
@@ -576,7 +618,7 @@ long orc_simulate(int N, const double* radius, const double* anisotropy, const d
         out_field[s] *= H_k;
     }
     for (size_t j = 0; j < (size_t)n3 * S; ++j) out_m[j] *= Ms;
-    if (iters) { iters[0] = it_total; iters[1] = it_max; }
+    if (iters) { iters[0] = it_total; iters[1] = it_max; iters[2] = it_last; }
 
     free(k_red); free(v_red); free(sigma); free(runit); free(rcube);
     free(sys.heff); free(sys.hjac); free(work); free(ipiv); free(p); free(nx); free(w);

@@ -1,0 +1,259 @@
+"""Host-side logic and the C-ABI surface, runnable without a GPU: exported symbols, the
+reference's host arithmetic (unit conversion, schedule) against the oracle, error behaviour,
+the Results/EnsembleResults/EnsembleModel mirror of the reference API, and the world_size-2
+sharding path over gloo (the device call replaced by the oracle, as a stand-in checker)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(ROOT, 'magpy_b200', 'libmagpy_b200.so')
+
+
+@pytest.fixture(scope='module')
+def orc():
+    return ol.load_oracle()
+
+
+@pytest.fixture(scope='module')
+def core():
+    import magpy_b200.core as core
+    return core
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'magpy_b200.h')).read()
+    names = sorted(set(re.findall(r'\b(magpy_b200_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(names) >= 18
+    lib = C.CDLL(LIB)
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.magpy_b200_abi_version.restype = C.c_int
+    assert lib.magpy_b200_abi_version() == int(re.search(r'#define MAGPY_B200_ABI_VERSION (\d+)', hdr).group(1))
+    # every declared entry cites the reference interface it replaces
+    assert hdr.count('lib/') + hdr.count('magpy/') + hdr.count('include/') >= 15
+
+
+def test_constants(core):
+    # include/constants.hpp:10-12 (MU0 is the reference's truncated value, not 4 pi 1e-7)
+    assert core.get_KB() == 1.38064852e-23
+    assert core.get_mu0() == 1.25663706e-6
+    assert core.get_gamma() == 1.76086e11
+
+
+def test_reduce_units_matches_oracle_bitwise(orc, core):
+    rng = np.random.default_rng(5)
+    for N in (1, 2, 7, 64):
+        c = ol.make_case(N=N, radius=7e-9 * (1 + rng.random(N)), anisotropy=1e5 * (0.5 + rng.random(N)), Ms=4.3e5,
+                         alpha=0.07, T=311.0, dt=3e-13, t_end=2e-9, H0=1.7e4, f=2.5e5, rng=rng)
+        want = ol.reduced_scalars(orc, c)
+        got = core.reduce_units(c.radius, c.anisotropy, c.Ms, c.alpha, c.T, c.dt, c.t_end, c.H0, c.f)
+        for k in ('V_av', 'K_av', 'H_k', 'time_factor', 'dt_red', 'T_red', 'h0', 'f_red', 'dipolar_prefactor'):
+            assert got[k] == want[k], k
+        for k in ('k_red', 'v_red', 'sigma'):
+            assert np.array_equal(got[k], want[k]), k
+
+
+def test_config1_reduced_values(core):
+    r = core.reduce_units([12e-9], [4e4], 4e5, 0.1, 300.0, 1e-14, 1e-9)
+    assert np.isclose(r['V_av'], 7.238e-24, rtol=1e-3) and np.isclose(r['H_k'], 159154.9, rtol=1e-6)
+    assert np.isclose(r['time_factor'], 3.4868e10, rtol=1e-4) and np.isclose(r['sigma'][0], 0.03764, rtol=1e-3)
+
+
+def test_schedule_matches_literal_loop(orc, core):
+    rng = np.random.default_rng(2)
+    cases = [(3.4868514851485146e-4, 34.868514851485145, 1000), (0.3, 1.0, 11), (1.0, 10.0, 11), (0.1, 1.0, 11),
+             (0.7, 0.5, 5), (1e-3, 1.0, 2), (0.25, 100.0, 401)]
+    cases += [(float(rng.uniform(1e-4, 0.5)), float(rng.uniform(0.5, 40)), int(rng.integers(2, 300))) for _ in range(40)]
+    for dt, T, S in cases:
+        assert np.array_equal(core.schedule(dt, T, S), ol.schedule(orc, dt, T, S)), (dt, T, S)
+
+
+def test_argument_errors_do_not_need_a_device(core):
+    c = ol.make_case(N=2)
+    args = (c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True, False, c.dt, c.t_end)
+    with pytest.raises(KeyError):            # magpy/core.pyx:158-161
+        core.simulate(*args, 10, 1, field_shape='sawtooth')
+    with pytest.raises(ValueError):
+        core.simulate(*args, 1, 1)
+    with pytest.raises(ValueError):
+        core.simulate(c.radius, c.anisotropy[:1], c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True, False,
+                      c.dt, c.t_end, 10, 1)
+    with pytest.raises(ValueError):
+        core.simulate_ensemble(c.radius, c.anisotropy, c.axis[None][:, :1], c.m0, c.location, c.Ms, c.alpha, c.T, False,
+                               True, False, c.dt, c.t_end, 10, [1, 2, 3])
+    with pytest.raises(KeyError):
+        core.simulate_ensemble(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False,
+                               True, False, c.dt, c.t_end, 10, [1, 2, 3], gauss='f16')
+
+
+def test_no_cpu_fallback(core):
+    if core.device_count() > 0:
+        pytest.skip('a CUDA device is present')
+    c = ol.make_case(N=1)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        core.simulate(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True, False, c.dt,
+                      c.t_end, 10, 1)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        core.fp64_peak()
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, 'magpy_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.pyx', '.cu', '.cuh', '.h', '.cpp')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'sllg_oracle' not in src and 'libmagpy_ref' not in src and 'oracle_lib' not in src, f
+
+
+def _fake_results(R=6, N=2, S=9, seed=0):
+    rng = np.random.default_rng(seed)
+    traj = rng.normal(size=(R, N, 3, S))
+    time = np.linspace(0, 1e-6, S)
+    field = 1e4 * np.sin(2 * np.pi * 2e6 * time)
+    M = traj.sum(axis=1)
+    sums = np.stack([M[:, 0].sum(0), M[:, 1].sum(0), M[:, 2].sum(0), (M[:, 2] ** 2).sum(0)], axis=1)
+    return time, field, traj, sums
+
+
+def test_results_api_matches_reference_semantics():
+    from magpy_b200 import Results, EnsembleResults, get_mu0
+    time, field, traj, sums = _fake_results()
+    R, N = traj.shape[:2]
+    members = [Results(time, field, {p: traj[i, p, 0] for p in range(N)}, {p: traj[i, p, 1] for p in range(N)},
+                       {p: traj[i, p, 2] for p in range(N)}, N) for i in range(R)]
+    a = EnsembleResults(members)                                   # the reference's constructor
+    b = EnsembleResults.from_arrays(time, field, R, trajectories=traj, sums=sums, final=traj[..., -1])
+    c = EnsembleResults.from_arrays(time, field, R, sums=sums, final=traj[..., -1])   # 1M-member style: no trajectories
+    # magpy/results.py:61-75 (sum over particles), :134-151 (mean over members)
+    assert np.allclose(members[0].magnetisation('x'), traj[0, :, 0].sum(0))
+    for d in 'xyz':
+        want = np.mean([m.magnetisation(d) for m in members], axis=0)
+        for e in (a, b, c):
+            assert np.allclose(e.ensemble_magnetisation(d), want)
+    assert np.allclose(np.array(a.magnetisation()), np.array(b.magnetisation()))
+    assert a.final_state()[2]['y'][1] == traj[2, 1, 1, -1] == b.final_state()[2]['y'][1] == c.final_state()[2]['y'][1]
+    # magpy/results.py:167-217 with the missing get_mu0 import repaired
+    want = -get_mu0() * np.trapezoid(field, b.ensemble_magnetisation())
+    for e in (a, b, c):
+        assert np.isclose(e.energy_dissipated(), want)
+    mask = time >= time[-1] - 1 / 2e6
+    want = -get_mu0() * np.trapezoid(field[mask], b.ensemble_magnetisation()[mask])
+    assert np.isclose(b.final_cycle_energy_dissipated(2e6), want)
+    assert len(b.results) == R and np.array_equal(b.results[-1].z[1], traj[-1, 1, 2])
+    with pytest.raises(ValueError):
+        c.magnetisation()
+    se = b.ensemble_magnetisation_stderr()
+    assert np.allclose(se, traj[:, :, 2].sum(1).std(axis=0, ddof=1) / np.sqrt(R))
+
+
+def test_ensemble_model_seeds_and_grouping(monkeypatch):
+    import magpy_b200 as mp
+    from magpy_b200 import model as model_mod
+    base = mp.Model([7e-9, 7e-9], [1e5, 1e5], [[0, 0, 1.0]] * 2, [[0, 0, 1.0]] * 2, [[0, 0, 0], [0, 0, 9e-9]], 4e5, 0.1, 330.0)
+    R = 7
+    rng = np.random.default_rng(0)
+    axes = rng.normal(size=(R, 2, 3))
+    temps = [300.0, 300.0, 310.0, 300.0, 310.0, 320.0, 300.0]
+    ens = mp.EnsembleModel(R, base, anisotropy_axis=list(axes), temperature=temps)
+    assert len(ens.models) == R and ens.models[2].temperature == 310.0      # magpy/model.py:146-156
+    calls = []
+
+    def fake(radius, anisotropy, axis, m0, location, Ms, alpha, T, renorm, inter, impl, dt, t_end, S, seeds, shape,
+             H0, f, tol, **kw):
+        calls.append(dict(T=T, seeds=np.array(seeds), axis=np.array(axis), kw=kw))
+        n = len(seeds)
+        return {'N': 2, 'R': n, 'time': np.arange(S) * 1.0, 'field': np.zeros(S),
+                'trajectories': np.ones((n, 2, 3, S)) * T, 'sums': np.ones((S, 4)) * n, 'final': np.ones((n, 2, 3)) * T,
+                'stats': {}}
+    monkeypatch.setattr(model_mod.core, 'simulate_ensemble', fake)
+    res = ens.simulate(1e-9, 1e-12, 5, random_state=42, implicit_solve=False, n_jobs=8)
+    # seeds exactly as magpy/model.py:202-203
+    np.random.seed(42)
+    want = np.random.randint(np.iinfo(np.int32).max, size=R)
+    assert sorted(c['T'] for c in calls) == [300.0, 310.0, 320.0]
+    for c in calls:
+        idx = [i for i, t in enumerate(temps) if t == c['T']]
+        assert np.array_equal(c['seeds'], want[idx])
+        assert np.array_equal(c['axis'], axes[idx])
+        assert c['kw']['stream_offset'] == idx[0]
+    assert np.array_equal(res.final_state_array()[:, 0, 0], temps)
+    assert np.allclose(res.ensemble_magnetisation(), 1.0)
+    with pytest.raises(TypeError):
+        mp.EnsembleModel(3, base, no_such_parameter=[1, 2, 3])
+
+
+def test_shard_bounds():
+    from magpy_b200.sharding import shard_bounds
+    for R, G in ((10, 3), (8, 8), (1000000, 8), (5, 8), (7, 2)):
+        spans = [shard_bounds(R, G, r) for r in range(G)]
+        assert spans[0][0] == 0 and spans[-1][1] == R
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) == -(-R // G)
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import torch.distributed as dist
+import oracle_lib as ol
+import magpy_b200 as mp
+from magpy_b200 import model as model_mod
+
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+orc = ol.load_oracle()
+
+def oracle_backed(radius, anisotropy, axis, m0, location, Ms, alpha, T, renorm, inter, impl, dt, t_end, S, seeds, shape,
+                  H0, f, tol, **kw):
+    # stand-in for the device call (no GPU in this test): the CPU oracle, member by member
+    c = ol.make_case(N=len(radius), radius=radius, anisotropy=anisotropy, axis=np.asarray(axis).reshape(-1, 3)[:len(radius)],
+                     m0=np.asarray(m0).reshape(-1, 3)[:len(radius)], location=location, Ms=Ms, alpha=alpha, T=T,
+                     renorm=renorm, interactions=inter, implicit=impl, eps=tol, dt=dt, t_end=t_end, S=S,
+                     field_shape=shape, H0=H0, f=f)
+    tr = np.stack([ol.oracle_simulate(orc, c, seed=int(s))[2] for s in seeds])
+    t, fl = ol.oracle_simulate(orc, c, seed=1)[:2]
+    M = tr.sum(axis=1)
+    sums = np.stack([M[:, 0].sum(0), M[:, 1].sum(0), M[:, 2].sum(0), (M[:, 2] ** 2).sum(0)], axis=1)
+    return dict(N=c.N, R=len(seeds), time=t, field=fl, trajectories=tr, sums=sums, final=tr[..., -1],
+                stats=dict(offset=kw['stream_offset']))
+
+model_mod.core.simulate_ensemble = oracle_backed
+base = mp.Model([7e-9, 7e-9], [1e5, 1e5], [[0, 0, 1.0]] * 2, [[0, 0, 1.0]] * 2, [[0, 0, 0], [0, 0, 9e-9]], 4e5, 0.1, 330.0,
+                field_shape='sine', field_frequency=5e9, field_amplitude=1e4)
+ens = mp.EnsembleModel(9, base)
+res = ens.simulate(5e-11, 1e-12, 11, random_state=3, implicit_solve=False, shard=(rank, world))
+full = ens.simulate(5e-11, 1e-12, 11, random_state=3, implicit_solve=False)
+lo, hi = mp.sharding.shard_bounds(9, world, rank)
+assert res.stats[0]['offset'] == lo
+assert res.final_state_array().shape[0] == hi - lo
+assert np.allclose(res.final_state_array(), full.final_state_array()[lo:hi], rtol=0, atol=0)
+assert np.allclose(res.ensemble_magnetisation('z'), full.ensemble_magnetisation('z'), rtol=1e-13)
+assert np.allclose(res.ensemble_magnetisation_stderr(), full.ensemble_magnetisation_stderr(), rtol=1e-9)
+assert np.isclose(res.energy_dissipated(), full.energy_dissipated(), rtol=1e-10)
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_sharded_ensemble_world_size_2_gloo(tmp_path):
+    import socket
+    from magpy_b200 import sharding  # noqa: F401
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER.format(root=ROOT, tests=HERE, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), '2'], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

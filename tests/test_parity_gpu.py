@@ -1,0 +1,180 @@
+"""GPU parity: the CUDA path (through magpy_b200.core -> C ABI) against the CPU oracle on the
+same inputs and the same Wiener increments.  Bar (north_star): 1e-10 relative in fp64."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope='module')
+def orc():
+    return ol.load_oracle()
+
+
+@pytest.fixture(scope='module')
+def core():
+    import magpy_b200.core as core
+    return core
+
+
+def gpu_run(core, c, seeds, dW=None, axis=None, m0=None, **kw):
+    return core.simulate_ensemble(
+        c.radius, c.anisotropy, c.axis if axis is None else axis, c.m0 if m0 is None else m0, c.location,
+        c.Ms, c.alpha, c.T, c.renorm, c.interactions, c.implicit, c.dt, c.t_end, c.S, seeds,
+        field_shape=c.field_shape, field_amplitude=c.H0, field_frequency=c.f, implicit_tol=c.eps,
+        injected_dw=dW, **kw)
+
+
+def injected_pair(orc, core, c, seeds, per_member=False):
+    """Oracle vs GPU with the reference's mt19937_64/normal stream of each member's seed injected."""
+    n_steps = ol.steps_executed(orc, c)
+    R = len(seeds)
+    rng = np.random.default_rng(7)
+    axis = m0 = None
+    if per_member:
+        def unit(v):
+            return v / np.linalg.norm(v, axis=-1, keepdims=True)
+        axis = unit(rng.normal(size=(R, c.N, 3)))
+        m0 = unit(rng.normal(size=(R, c.N, 3)))
+    dW = np.stack([ol.mt_normal(orc, int(s), n_steps * 3 * c.N).reshape(n_steps, 3 * c.N) for s in seeds])
+    ref = []
+    newton = []
+    for i, s in enumerate(seeds):
+        t, fl, m, it, fails = ol.oracle_simulate(orc, c, seed=int(s), axis=None if axis is None else axis[i],
+                                                 m0=None if m0 is None else m0[i])
+        ref.append(m)
+        newton.append(it)
+    ref = np.stack(ref)
+    out = gpu_run(core, c, seeds, dW=dW, axis=axis, m0=m0)
+    return t, fl, ref, out, newton
+
+
+def assert_traj(ref, out, c):
+    err = np.abs(out['trajectories'] - ref).max() / c.Ms
+    assert err <= TOL, 'max |dm|/Ms = %.3e' % err
+    # fused ensemble sums and final states are consistent with the trajectories
+    M = out['trajectories'].sum(axis=1)                      # [R,3,S]
+    sums = np.stack([M[:, 0].sum(0), M[:, 1].sum(0), M[:, 2].sum(0), (M[:, 2] ** 2).sum(0)], axis=1)
+    scale = np.array([c.Ms, c.Ms, c.Ms, c.Ms ** 2]) * len(ref) * c.N
+    assert np.abs(out['sums'] - sums).max() / scale.max() < 1e-12
+    assert np.abs((out['sums'] - sums) / scale).max() < 1e-12
+    assert np.array_equal(out['final'], out['trajectories'][..., -1])
+
+
+def test_philox_words_match_random123_and_oracle(orc, core):
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(core.philox_words(ctr, key)) == want
+        assert tuple(ol.philox(orc, ctr, key)) == want
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        ctr = [int(x) for x in rng.integers(0, 2 ** 32, 4)]
+        key = [int(x) for x in rng.integers(0, 2 ** 32, 2)]
+        assert core.philox_words(ctr, key) == ol.philox(orc, ctr, key)
+
+
+@pytest.mark.parametrize('mode,tol', [('f64', 1e-13), ('f32', 2e-5)])
+def test_gaussian_stream_matches_oracle(orc, core, mode, tol):
+    seed, member, particle, first, n = 123456789012345, 77, 3, 1000, 4096
+    got = core.gaussians(seed, member, particle, first, n, gauss=mode)
+    want = np.array([ol.philox_gauss3(orc, seed, member, particle, first + i, 0 if mode == 'f32' else 1)
+                     for i in range(n)])
+    assert np.abs(got - want).max() < tol
+    # sanity of the stream itself
+    big = core.gaussians(seed, 1, 0, 1, 400000, gauss=mode).ravel()
+    assert abs(big.mean()) < 5 / np.sqrt(big.size)
+    assert abs(big.var() - 1) < 5 * np.sqrt(2 / big.size)
+    assert abs((big ** 4).mean() - 3) < 0.05
+
+
+@pytest.mark.parametrize('field_shape,H0,f,renorm', [
+    ('constant', 0.0, 0.0, False), ('constant', 3e4, 0.0, True), ('sine', 2e4, 3e9, False), ('square', 2e4, 5e9, False)])
+def test_heun_single_injected(orc, core, field_shape, H0, f, renorm):
+    c = ol.make_case(N=1, dt=1e-14, t_end=2e-11, S=64, field_shape=field_shape, H0=H0, f=f, renorm=renorm,
+                     axis=[[0, 0, 1.0]], m0=[[1.0, 0, 0]])
+    seeds = np.array([1001, 5, 77, 123456, 9, 31337, 2, 42, 8, 100])
+    t, fl, ref, out, _ = injected_pair(orc, core, c, seeds)
+    assert_traj(ref, out, c)
+    assert np.allclose(out['time'], t, rtol=0, atol=0) and np.allclose(out['field'], fl, rtol=1e-15, atol=0)
+
+
+def test_heun_single_config1_full_length(orc, core):
+    """BASELINE config 1: 12 nm particle, Heun dt=1e-14 to 1e-9 s (1e5 steps), pathwise."""
+    c = ol.make_case(N=1, dt=1e-14, t_end=1e-9, S=1000, axis=[[0, 0, 1.0]], m0=[[1.0, 0, 0]])
+    seeds = np.array([1001, 2002, 3003, 4004])
+    t, fl, ref, out, _ = injected_pair(orc, core, c, seeds)
+    assert_traj(ref, out, c)
+
+
+def test_heun_single_per_member_axes_and_ragged_block(orc, core):
+    c = ol.make_case(N=1, dt=2e-14, t_end=1e-11, S=33, field_shape='sine', H0=1e4, f=1e10)
+    seeds = np.arange(1, 131 + 1) * 17            # 131 members: not a multiple of the CTA size
+    t, fl, ref, out, _ = injected_pair(orc, core, c, seeds, per_member=True)
+    assert_traj(ref, out, c)
+
+
+@pytest.mark.parametrize('field_shape,H0,f,renorm,eps', [
+    ('constant', 0.0, 0.0, False, 1e-9), ('sine', 2e4, 3e9, False, 1e-9), ('constant', 1e4, 0.0, True, 1e-6)])
+def test_implicit_single_injected(orc, core, field_shape, H0, f, renorm, eps):
+    c = ol.make_case(N=1, dt=1e-13, t_end=5e-11, S=40, implicit=True, eps=eps, field_shape=field_shape, H0=H0, f=f,
+                     renorm=renorm, axis=[[0, 0, 1.0]], m0=[[1.0, 0, 0]])
+    seeds = np.array([1001, 5, 77, 123456, 9, 31337])
+    t, fl, ref, out, newton = injected_pair(orc, core, c, seeds)
+    assert_traj(ref, out, c)
+    # the quasi-Newton iteration is reproduced, not just its fixed point: same iteration counts
+    # (the oracle also runs the reference's last, never-sampled step; the product skips it)
+    assert out['stats']['newton_iterations'] == sum(n[0] - n[2] for n in newton)
+    assert out['stats']['newton_max_iterations'] <= max(n[1] for n in newton)
+    assert out['stats']['newton_failures'] == 0
+
+
+@pytest.mark.parametrize('N,interactions,renorm', [(2, True, False), (3, True, True), (5, False, False), (8, True, False),
+                                                   (20, True, False), (40, True, False)])
+def test_heun_cluster_injected(orc, core, N, interactions, renorm):
+    rng = np.random.default_rng(N)
+    c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
+                     dt=1e-13, t_end=3e-11, S=25, interactions=interactions, renorm=renorm, field_shape='sine',
+                     H0=1e4, f=1e10, T=330.0, rng=rng)
+    seeds = np.arange(1, 36) * 101               # 35 members: ragged last CTA
+    t, fl, ref, out, _ = injected_pair(orc, core, c, seeds, per_member=(N <= 3))
+    assert_traj(ref, out, c)
+
+
+@pytest.mark.parametrize('N,interactions', [(2, True), (3, False), (5, True), (12, True)])
+def test_implicit_cluster_injected(orc, core, N, interactions):
+    rng = np.random.default_rng(100 + N)
+    c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
+                     dt=1e-12, t_end=4e-11, S=21, implicit=True, interactions=interactions, T=330.0, rng=rng)
+    seeds = np.arange(1, 34) * 13
+    t, fl, ref, out, newton = injected_pair(orc, core, c, seeds, per_member=(N == 2))
+    assert_traj(ref, out, c)
+    assert out['stats']['newton_iterations'] == sum(n[0] - n[2] for n in newton)
+
+
+def test_single_simulate_api_and_schedule_edges(orc, core):
+    """core.simulate keeps the reference's dict; sampling finer than the time step repeats states."""
+    c = ol.make_case(N=2, dt=1e-12, t_end=1e-11, S=40, implicit=False)    # Ts < dt: zero-order hold repeats
+    res = core.simulate(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True, False,
+                        c.dt, c.t_end, c.S, 1234)
+    assert set(res) == {'N', 'time', 'field', 'x', 'y', 'z'} and res['N'] == 2
+    t, fl, m, _, _ = ol.oracle_simulate(orc, c, seed=1)
+    assert np.array_equal(res['time'], t)
+    # identical hold pattern: consecutive samples equal exactly where the oracle's are
+    same_ref = np.all(m[:, :, 1:] == m[:, :, :-1], axis=(0, 1))
+    got = np.stack([[res['x'][i], res['y'][i], res['z'][i]] for i in range(2)])
+    same_got = np.all(got[:, :, 1:] == got[:, :, :-1], axis=(0, 1))
+    assert np.array_equal(same_ref, same_got)
+    assert np.allclose(got[:, :, 0], c.m0 * c.Ms)
+    with pytest.raises(KeyError):
+        core.simulate(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True, False,
+                      c.dt, c.t_end, c.S, 1234, field_shape='triangle')
+    with pytest.raises(ValueError):
+        core.simulate(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True, False,
+                      c.dt, c.t_end, 1, 1234)
