@@ -63,6 +63,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// unit-variance draws (implicit kernels clamp them before scaling, lib/integrators.cpp:598-602)
 template <int NOISE>
 __device__ __forceinline__ V3 draw_noise(const RunParams& P, uint32_t k0, uint32_t k1, uint64_t j, uint32_t particle,
                                          uint32_t member, uint64_t r) {
@@ -75,6 +76,24 @@ __device__ __forceinline__ V3 draw_noise(const RunParams& P, uint32_t k0, uint32
         return V3{g.x, g.y, g.z};
     }
 }
+
+// Heun kernels: the scaled increment c*w with c = sigma*sqrt(dt).  In the fp32 Gaussian mode the
+// scale is folded into the Box-Muller radius (neg2ln2_c2 = -2 ln2 c^2), so no fp64 multiply is
+// spent on the noise; the injected and fp64 modes multiply in fp64.
+template <int NOISE>
+__device__ __forceinline__ V3 draw_scaled(const RunParams& P, uint32_t k0, uint32_t k1, uint64_t j, uint32_t particle,
+                                          uint32_t member, uint64_t r, double c, float neg2ln2_c2) {
+    if (NOISE == NOISE_PHILOX_F32) {
+        float x, y, z;
+        philox_gauss3_f32(k0, k1, j + 1, particle, member, neg2ln2_c2, x, y, z);
+        return V3{widen_f32(x), widen_f32(y), widen_f32(z)};
+    } else {
+        const V3 w = draw_noise<NOISE>(P, k0, k1, j, particle, member, r);
+        return V3{c * w.x, c * w.y, c * w.z};
+    }
+}
+
+__device__ __forceinline__ float scale_to_bm(double c) { return (float)(-1.3862943611198906 * c * c); }
 
 // CTA-level sum of 4 values per thread over a 1-D block of NW warps into partial[slot][4]
 template <int NW>
@@ -101,18 +120,38 @@ __device__ __forceinline__ void cta_partial_sums(double v0, double v1, double v2
 // ---------------------------------------------------------------------------------
 constexpr int SINGLE_THREADS = 128;
 
+// One Heun step of a single macrospin in 40 fp64 instructions (47 with a general easy axis).
+// With u = g + alpha (m x g) the LLG increment is f(m,g) = -m x u, so the predictor
+// x~ = m + f(m,g) and the corrector m' = (m + x~)/2 + f(x~,g~)/2 are accumulated directly in the
+// FMAs of the second cross product (no separate adds, and f1 is never materialised).
+template <bool AXIS_Z>
 __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V3& edt, const double alpha,
                                                const double dt, const V3& cw, const double hz0, const double hz1) {
-    // stage 1: g = h(m,t) dt + sigma sqrt(dt) w ;  x~ = m + f(m,g)
-    double s = dot(m, e);
-    V3 g{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz0, dt, cw.z))};
-    const V3 f1 = llg_f(m, g, alpha);
-    const V3 mt{m.x + f1.x, m.y + f1.y, m.z + f1.z};
+    // stage 1: g = h(m,t) dt + sigma sqrt(dt) w
+    V3 g;
+    if (AXIS_Z) {  // easy axis = z: h = (k m_z + h_app) z, two fp64 ops instead of seven
+        g = V3{cw.x, cw.y, fma(m.z, edt.z, fma(hz0, dt, cw.z))};
+    } else {
+        const double s = dot(m, e);
+        g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz0, dt, cw.z))};
+    }
+    V3 p = cross(m, g);
+    V3 u{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
+    const V3 mt{fma(-m.y, u.z, fma(m.z, u.y, m.x)), fma(-m.z, u.x, fma(m.x, u.z, m.y)),
+                fma(-m.x, u.y, fma(m.y, u.x, m.z))};
     // stage 2 at (x~, t+dt), same Wiener increment
-    s = dot(mt, e);
-    g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz1, dt, cw.z))};
-    const V3 f2 = llg_f(mt, g, alpha);
-    return V3{fma(0.5, f1.x + f2.x, m.x), fma(0.5, f1.y + f2.y, m.y), fma(0.5, f1.z + f2.z, m.z)};
+    if (AXIS_Z) {
+        g = V3{cw.x, cw.y, fma(mt.z, edt.z, fma(hz1, dt, cw.z))};
+    } else {
+        const double s = dot(mt, e);
+        g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz1, dt, cw.z))};
+    }
+    p = cross(mt, g);
+    u = V3{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
+    const V3 hm{0.5 * mt.x, 0.5 * mt.y, 0.5 * mt.z};
+    const V3 h{fma(0.5, m.x, hm.x), fma(0.5, m.y, hm.y), fma(0.5, m.z, hm.z)};
+    return V3{fma(-hm.y, u.z, fma(hm.z, u.y, h.x)), fma(-hm.z, u.x, fma(hm.x, u.z, h.y)),
+              fma(-hm.x, u.y, fma(hm.y, u.x, h.z))};
 }
 
 __device__ __forceinline__ void renormalise(V3& m) {
@@ -120,7 +159,7 @@ __device__ __forceinline__ void renormalise(V3& m) {
     m.x *= inv; m.y *= inv; m.z *= inv;
 }
 
-template <int NOISE, bool FIELD_TAB>
+template <int NOISE, bool FIELD_TAB, bool AXIS_Z>
 __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
@@ -128,11 +167,14 @@ __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __gri
     const uint64_t r = live ? r_raw : P.R - 1;
 
     V3 m{P.state[r], P.state[P.R + r], P.state[2 * P.R + r]};
-    const V3 e{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
+    V3 e{0.0, 0.0, 1.0};
+    if (!AXIS_Z)
+        e = V3{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
     const double alpha = P.alpha, dt = P.dt;
     const double kdt = P.k_red[0] * dt;
     const V3 edt{e.x * kdt, e.y * kdt, e.z * kdt};
     const double c = P.sig[0] * P.sqrt_dt;
+    const float bm_scale = scale_to_bm(c);
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t member = (uint32_t)(r + P.stream_offset);
@@ -141,15 +183,15 @@ __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __gri
     uint64_t j = P.j0;
     for (uint32_t k = P.k0; k <= P.k1; ++k) {
         const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+#pragma unroll 2
         for (; j < tgt; ++j) {
-            const V3 w = draw_noise<NOISE>(P, key0, key1, j, 0u, member, r);
-            const V3 cw{c * w.x, c * w.y, c * w.z};
+            const V3 cw = draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, c, bm_scale);
             double hz0 = P.h_const, hz1 = P.h_const;
             if (FIELD_TAB) {
                 const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - P.j0));
                 hz0 = h.x; hz1 = h.y;
             }
-            m = heun_single_step(m, e, edt, alpha, dt, cw, hz0, hz1);
+            m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
             if (renorm) renormalise(m);
         }
         if (k < P.k1) {
@@ -312,6 +354,7 @@ constexpr int CL_LANES = 32;
 struct Own {  // per-thread, per-owned-particle constants
     V3 e;
     double kred, sr;
+    float bm;  // -2 ln2 (sigma sqrt(dt))^2: Box-Muller scale of this particle's increments
     uint32_t p;
     bool valid;
 };
@@ -366,6 +409,7 @@ __global__ void __launch_bounds__(512) heun_cluster_kernel(const __grid_constant
                       P.axis[(c0 + 2) * P.axis_cs + r * P.axis_rs]};
         own[q].kred = P.k_red[own[q].p];
         own[q].sr = P.sig[own[q].p];
+        own[q].bm = scale_to_bm(own[q].sr * P.sqrt_dt);
         m[q] = V3{P.state[c0 * P.R + r], P.state[(c0 + 1) * P.R + r], P.state[(c0 + 2) * P.R + r]};
         if (own[q].valid) {
             double* d = sm_m + c0 * CL_LANES + lane;
@@ -387,9 +431,7 @@ __global__ void __launch_bounds__(512) heun_cluster_kernel(const __grid_constant
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 if (!own[q].valid) continue;
-                const V3 w = draw_noise<NOISE>(P, key0, key1, j, own[q].p, member, r);
-                const double c = own[q].sr * P.sqrt_dt;
-                cw[q] = V3{c * w.x, c * w.y, c * w.z};
+                cw[q] = draw_scaled<NOISE>(P, key0, key1, j, own[q].p, member, r, own[q].sr * P.sqrt_dt, own[q].bm);
                 const V3 h = cluster_field(P, sm_m, own[q], m[q], hz0, lane);
                 const V3 g{fma(h.x, dt, cw[q].x), fma(h.y, dt, cw[q].y), fma(h.z, dt, cw[q].z)};
                 f1[q] = llg_f(m[q], g, alpha);

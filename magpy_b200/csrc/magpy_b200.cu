@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -169,6 +170,7 @@ struct magpy_b200_plan {
     size_t smem = 0;
     int np = 1;
     bool use_table = false;
+    bool axis_z = false;   // N = 1 and one shared easy axis exactly along +z: specialised Heun kernel
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
@@ -201,7 +203,8 @@ int launch_integrate_nt(magpy_b200_plan* pl, const mb::RunParams& P) {
     const dim3 g(pl->grid), b = pl->block;
     if (pl->N == 1) {
         if (pl->implicit) mb::imid_single_kernel<NOISE, TAB><<<g, b, 0, pl->stream>>>(P);
-        else mb::heun_single_kernel<NOISE, TAB><<<g, b, 0, pl->stream>>>(P);
+        else if (pl->axis_z) mb::heun_single_kernel<NOISE, TAB, true><<<g, b, 0, pl->stream>>>(P);
+        else mb::heun_single_kernel<NOISE, TAB, false><<<g, b, 0, pl->stream>>>(P);
     } else if (pl->implicit) {
         switch (pl->np) {
             case 1: mb::imid_cluster_kernel<NOISE, TAB, 1><<<g, b, pl->smem, pl->stream>>>(P); break;
@@ -354,9 +357,15 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         if (pl->smem > 227 * 1024) return fail(MAGPY_B200_ERR_BAD_ARG, "cluster too large for shared memory");
     }
     pl->use_table = a->field_shape != MAGPY_B200_FIELD_CONSTANT;
+    pl->axis_z = N == 1 && a->axis_stride == 0 && a->anisotropy_axis[0] == 0.0 && a->anisotropy_axis[1] == 0.0 &&
+                 a->anisotropy_axis[2] == 1.0;
 
     // chunking: bound the field table / injected-noise window and the partial-sum buffer
-    const uint64_t max_steps = 4ull << 20;
+    uint64_t max_steps = 4ull << 20;
+    if (const char* env = std::getenv("MAGPY_B200_MAX_CHUNK_STEPS")) {   // test hook: force many small launches
+        const long long v = std::atoll(env);
+        if (v > 0) max_steps = (uint64_t)v;
+    }
     const uint64_t max_partial_doubles = (512ull << 20) / 8;
     uint32_t max_samples_chunk = (uint32_t)std::max<uint64_t>(1, max_partial_doubles / (4ull * pl->grid));
     pl->chunks.clear();
@@ -825,22 +834,27 @@ int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz) {
     if (!tflops) return fail(MAGPY_B200_ERR_BAD_ARG, "tflops is NULL");
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
-    DevBuf<double> d;
-    CU_TRY(d.alloc((size_t)blocks * threads));
+    const int iters = 2048;
     cudaEvent_t e0, e1;
     CU_TRY(cudaEventCreate(&e0));
     CU_TRY(cudaEventCreate(&e1));
     double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
-        CU_TRY(cudaEventRecord(e0));
-        mb::fp64_peak_kernel<<<blocks, threads>>>(d.p, iters, 0.999999, 1e-7);
-        CU_TRY(cudaEventRecord(e1));
-        CU_TRY(cudaEventSynchronize(e1));
-        float ms = 0.f;
-        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = (double)blocks * threads * iters * 64.0 * 2.0;
-        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    // best over a few launch shapes (resident warps per scheduler) and repetitions
+    const int shapes[3][2] = {{128, 8}, {128, 4}, {256, 8}};   // threads per CTA, CTAs per SM
+    for (const auto& sh : shapes) {
+        const int threads = sh[0], blocks = prop.multiProcessorCount * sh[1];
+        DevBuf<double> d;
+        CU_TRY(d.alloc((size_t)blocks * threads));
+        for (int rep = 0; rep < 4; ++rep) {
+            CU_TRY(cudaEventRecord(e0));
+            mb::fp64_peak_kernel<<<blocks, threads>>>(d.p, iters, 0.999999, 1e-7);
+            CU_TRY(cudaEventRecord(e1));
+            CU_TRY(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            const double flops = (double)blocks * threads * iters * 64.0 * 2.0;
+            if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

@@ -1,15 +1,18 @@
 // rng.cuh — in-kernel counter-based Gaussian stream (replaces lib/rng.cpp:14-24,
 // std::mt19937_64 + std::normal_distribution, which cannot be reproduced on the device
-// at speed).  Philox4x32-10 (Salmon et al. SC'11) is a pure function of
-//   key     = 64-bit seed of the ensemble member (magpy/model.py:202-203 seeds)
-//   counter = (step index, particle | block<<24, global member index)
-// so the Wiener increment of (member, particle, step) does not depend on how the
-// ensemble is chunked in time, laid out over CTAs, or sharded over GPUs.
+// at speed).  Philox4x32-10 (Salmon et al. SC'11) is used as a pure function of
+//   counter = (step index [32 bit, like the reference's step counter], global member index,
+//              seed low word, seed high word)   -- the member's seed of magpy/model.py:202-203
+//   key     = (particle | block<<24, MB_PHILOX_KEY1)
+// so the Wiener increment of (member, particle, step) does not depend on how the ensemble is
+// chunked in time, laid out over CTAs, or sharded over GPUs.  Everything that varies per thread
+// sits in the counter: the key schedule (20 adds per block) is warp-uniform and, for the
+// single-particle kernels, a compile-time constant.
 //
 // Two Gaussian transforms of the Philox words:
 //   GAUSS_F32: Box-Muller in fp32 on the otherwise idle FP32/SFU pipes, widened to fp64
-//              by integer bit manipulation (keeps the FP64 pipe for the integrator).
-//              One Philox call yields the 3 draws of a particle-step.
+//              (keeps the FP64 pipe for the integrator).  One Philox call yields the 3 draws of
+//              a particle-step.
 //   GAUSS_F64: Box-Muller in fp64 from 53-bit uniforms (two Philox calls per particle-step).
 #pragma once
 #include <cstdint>
@@ -17,16 +20,31 @@
 
 namespace mb {
 
+// 32x32 -> 64 bit product as one IMAD.WIDE.U32 whose halves are read straight from the
+// register pair (the plain C++ form makes ptxas add a zero carry word to every high half)
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+    unsigned long long p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+#else
+    const uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+}
+
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
                                                        uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1;
-        c3 = (uint32_t)p0;
+        uint32_t h0, l0, h1, l1;
+        mulhilo32(0xD2511F53u, c0, h0, l0);
+        mulhilo32(0xCD9E8D57u, c2, h1, l1);
+        const uint32_t n0 = h1 ^ c1 ^ k0;
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
         c0 = n0;
         c2 = n2;
         k0 += 0x9E3779B9u;
@@ -34,43 +52,78 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
     }
 }
 
-// exact float -> double widening without the (quarter-rate) F2F.F64.F32 conversion:
-// rebias the exponent (+896) and shift the mantissa.  Exact for normal floats; a zero or
-// denormal input (probability < 2^-100 per Gaussian) maps to a value below 2^-126.
+// float -> double widening.  Measured on B200 (profiles/README.md): one F2F.F64.F32 on the XU
+// pipe beats the 5-instruction integer re-biasing of exponent and mantissa by 5 % end to end,
+// because the kernel is bound by issue slots, not by the XU pipe.
 __device__ __forceinline__ double widen_f32(float f) {
+#ifdef MB_WIDEN_INT
     const uint32_t b = __float_as_uint(f);
     const uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);
     const uint32_t lo = b << 29;
     return __hiloint2double((int)hi, (int)lo);
+#else
+    return (double)f;
+#endif
 }
 
-// (0,1] uniform from 32 bits, then r = sqrt(-2 ln u)
-__device__ __forceinline__ float bm_radius_f32(uint32_t x) {
-    const float u = fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    return sqrtf(-2.0f * __logf(u));
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Box-Muller radius times `amp`:  amp * sqrt(-2 ln u),  u in (0,1) from 32 bits.
+// neg2ln2_amp2 = -2 ln(2) amp^2 folds the scale into the one multiply that follows lg2, so a
+// scaled draw costs the same as a unit one.  The integer is converted toward zero so that u
+// never rounds to 1 (which would make the radius 0 * inf).  Branch free: 2 MUFU + 4 FP32.
+__device__ __forceinline__ float bm_radius_f32(uint32_t x, float neg2ln2_amp2) {
+    const float u = fmaf(__uint2float_rz(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float y = lg2_approx(u) * neg2ln2_amp2;
+    return y * rsqrt_approx(y);
+}
+
+#define MB_TWO_PI_2M32 1.4629180792671596e-9f /* 2 pi 2^-32 */
+#define MB_PHILOX_KEY1 0xB2005EEDu
+#define MB_NEG_2LN2 (-1.3862943611198906f)
+
+// three draws of N(0, amp^2) in fp32 from one Philox block: (member, particle, step) -> words
+// (w0,w1,w2,w3); pair 1 = radius(w0), angle(w1) gives x = r cos, y = r sin; pair 2 = radius(w2),
+// angle(w3) gives z = r cos.
+__device__ __forceinline__ void philox_gauss3_f32(uint32_t seed_lo, uint32_t seed_hi, uint64_t step,
+                                                  uint32_t particle, uint32_t member, float neg2ln2_amp2,
+                                                  float& gx, float& gy, float& gz) {
+    uint32_t c0 = (uint32_t)step, c1 = member, c2 = seed_lo, c3 = seed_hi;
+    philox4x32_10(c0, c1, c2, c3, particle, MB_PHILOX_KEY1);
+    const float r1 = bm_radius_f32(c0, neg2ln2_amp2), r2 = bm_radius_f32(c2, neg2ln2_amp2);
+    const float a1 = (float)c1 * MB_TWO_PI_2M32, a2 = (float)c3 * MB_TWO_PI_2M32;
+    gx = r1 * __cosf(a1);
+    gy = r1 * __sinf(a1);
+    gz = r2 * __cosf(a2);
 }
 
 struct Gauss3 {
     double x, y, z;
 };
 
+// unit-variance draws in fp64 (validation mode and the implicit kernels' unscaled draws)
 template <int GAUSS_MODE>
-__device__ __forceinline__ Gauss3 philox_gauss3(uint32_t k0, uint32_t k1, uint64_t step, uint32_t particle,
-                                                uint32_t member) {
+__device__ __forceinline__ Gauss3 philox_gauss3(uint32_t seed_lo, uint32_t seed_hi, uint64_t step,
+                                                uint32_t particle, uint32_t member) {
     Gauss3 g;
     if (GAUSS_MODE == 0) {
-        uint32_t c0 = (uint32_t)step, c1 = (uint32_t)(step >> 32), c2 = particle, c3 = member;
-        philox4x32_10(c0, c1, c2, c3, k0, k1);
-        const float r1 = bm_radius_f32(c0), r2 = bm_radius_f32(c2);
-        float s1, co1;
-        __sincosf(6.2831853071795865f * ((float)c1 * 2.3283064365386963e-10f), &s1, &co1);
-        const float co2 = __cosf(6.2831853071795865f * ((float)c3 * 2.3283064365386963e-10f));
-        g.x = widen_f32(r1 * co1);
-        g.y = widen_f32(r1 * s1);
-        g.z = widen_f32(r2 * co2);
+        float x, y, z;
+        philox_gauss3_f32(seed_lo, seed_hi, step, particle, member, MB_NEG_2LN2, x, y, z);
+        g.x = widen_f32(x);
+        g.y = widen_f32(y);
+        g.z = widen_f32(z);
     } else {
-        uint32_t c0 = (uint32_t)step, c1 = (uint32_t)(step >> 32), c2 = particle, c3 = member;
-        philox4x32_10(c0, c1, c2, c3, k0, k1);
+        uint32_t c0 = (uint32_t)step, c1 = member, c2 = seed_lo, c3 = seed_hi;
+        philox4x32_10(c0, c1, c2, c3, particle, MB_PHILOX_KEY1);
         const double two53 = 1.1102230246251565e-16;  // 2^-53
         double u1 = ((double)((((uint64_t)c1 << 32) | c0) >> 11) + 0.5) * two53;
         double u2 = ((double)((((uint64_t)c3 << 32) | c2) >> 11) + 0.5) * two53;
@@ -78,8 +131,8 @@ __device__ __forceinline__ Gauss3 philox_gauss3(uint32_t k0, uint32_t k1, uint64
         sincospi(2.0 * u2, &s, &c);
         g.x = r * c;
         g.y = r * s;
-        c0 = (uint32_t)step; c1 = (uint32_t)(step >> 32); c2 = particle | (1u << 24); c3 = member;
-        philox4x32_10(c0, c1, c2, c3, k0, k1);
+        c0 = (uint32_t)step; c1 = member; c2 = seed_lo; c3 = seed_hi;
+        philox4x32_10(c0, c1, c2, c3, particle | (1u << 24), MB_PHILOX_KEY1);
         u1 = ((double)((((uint64_t)c1 << 32) | c0) >> 11) + 0.5) * two53;
         u2 = ((double)((((uint64_t)c3 << 32) | c2) >> 11) + 0.5) * two53;
         r = sqrt(-2.0 * log(u1));

@@ -128,18 +128,28 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 /* The three unit-variance draws the product uses for (seed, member, particle, step):
  * restatement of magpy_b200/csrc/rng.cuh (philox_gauss3) for the parity tests.
+ * counter = (step, member, seed_lo, seed_hi), key = (particle | block<<24, 0xB2005EED).
  * mode 0: fp32 Box-Muller of one Philox block (device uses SFU approximations, so compare
  *         with a ~1e-5 tolerance); mode 1: fp64 Box-Muller from 53-bit uniforms, two blocks. */
+static float u32_to_float_rz(uint32_t x) { /* cvt.rz.f32.u32 */
+    if (x >= (1u << 24)) {
+        int sh = 8 - __builtin_clz(x);
+        x &= ~((1u << sh) - 1u);
+    }
+    return (float)x;
+}
+
 void orc_philox_gauss3(uint64_t seed, uint32_t member, uint32_t particle, uint64_t step, int mode, double out[3]) {
-    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32), particle, member}, w[4];
+    uint32_t key[2] = {particle, 0xB2005EEDu};
+    const uint32_t ctr[4] = {(uint32_t)step, member, (uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t w[4];
     orc_philox4x32_10(ctr, key, w);
     if (mode == 0) {
-        const float u1 = fmaf((float)w[0], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-        const float u2 = fmaf((float)w[2], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-        const float r1 = sqrtf(-2.0f * logf(u1)), r2 = sqrtf(-2.0f * logf(u2));
-        const float a1 = 6.2831853071795865f * ((float)w[1] * 2.3283064365386963e-10f);
-        const float a2 = 6.2831853071795865f * ((float)w[3] * 2.3283064365386963e-10f);
+        const float K = -1.3862943611198906f, A = 1.4629180792671596e-9f;
+        const float u1 = fmaf(u32_to_float_rz(w[0]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        const float u2 = fmaf(u32_to_float_rz(w[2]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        const float r1 = sqrtf(log2f(u1) * K), r2 = sqrtf(log2f(u2) * K);
+        const float a1 = (float)w[1] * A, a2 = (float)w[3] * A;
         out[0] = (double)(r1 * cosf(a1));
         out[1] = (double)(r1 * sinf(a1));
         out[2] = (double)(r2 * cosf(a2));
@@ -150,7 +160,7 @@ void orc_philox_gauss3(uint64_t seed, uint32_t member, uint32_t particle, uint64
         double r = sqrt(-2.0 * log(u1));
         out[0] = r * cos(2.0 * M_PI * u2);
         out[1] = r * sin(2.0 * M_PI * u2);
-        ctr[2] = particle | (1u << 24);
+        key[0] = particle | (1u << 24);
         orc_philox4x32_10(ctr, key, w);
         u1 = ((double)(((((uint64_t)w[1]) << 32) | w[0]) >> 11) + 0.5) * two53;
         u2 = ((double)(((((uint64_t)w[3]) << 32) | w[2]) >> 11) + 0.5) * two53;

@@ -144,3 +144,20 @@ def philox_gauss3(lib, seed, member, particle, step, mode):
     lib.orc_philox_gauss3(C.c_uint64(seed), C.c_uint32(member), C.c_uint32(particle), C.c_uint64(step),
                           C.c_int(mode), o)
     return list(o)
+
+
+def oracle_ensemble(lib, c, seeds, axis=None, m0=None):
+    """OpenMP ensemble of oracle runs (reference MT noise per seed): sums [S,4] and final [R,N,3] in A/m."""
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    R = len(seeds)
+    sums = np.zeros((c.S, 4)); final = np.zeros((R, c.N, 3))
+    axis = c.axis if axis is None else np.ascontiguousarray(axis, dtype=np.float64)
+    m0 = c.m0 if m0 is None else np.ascontiguousarray(m0, dtype=np.float64)
+    lib.orc_ensemble.restype = C.c_double
+    lib.orc_ensemble(C.c_size_t(R), _p(seeds), C.c_int(c.N), _p(c.radius), _p(c.anisotropy), _p(axis),
+                     C.c_size_t(3 * c.N if axis.ndim == 3 else 0), _p(m0), C.c_size_t(3 * c.N if m0.ndim == 3 else 0),
+                     _p(c.location), C.c_double(c.Ms), C.c_double(c.alpha), C.c_double(c.T), C.c_int(int(c.renorm)),
+                     C.c_int(int(c.interactions)), C.c_int(int(c.implicit)), C.c_double(c.eps), C.c_double(c.dt),
+                     C.c_double(c.t_end), C.c_size_t(c.S), C.c_int(FIELD[c.field_shape]), C.c_double(c.H0),
+                     C.c_double(c.f), _p(sums), _p(final))
+    return sums, final

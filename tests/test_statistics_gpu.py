@@ -1,0 +1,212 @@
+"""Statistical parity of the production noise path (in-kernel Philox) with the reference
+ensemble (oracle + the reference's mt19937_64 stream), equilibrium physics, invariance of the
+results under time-chunking and member sharding, and convergence orders (test/convergence)."""
+import os
+
+import numpy as np
+import pytest
+from scipy import integrate
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def orc():
+    return ol.load_oracle()
+
+
+@pytest.fixture(scope='module')
+def core():
+    import magpy_b200.core as core
+    return core
+
+
+def gpu(core, c, seeds, **kw):
+    return core.simulate_ensemble(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, c.renorm,
+                                  c.interactions, c.implicit, c.dt, c.t_end, c.S, seeds, field_shape=c.field_shape,
+                                  field_amplitude=c.H0, field_frequency=c.f, implicit_tol=c.eps, **kw)
+
+
+def mean_and_se(sums, R, Ms):
+    mean = sums[:, 2] / R
+    var = np.maximum(sums[:, 3] / R - mean ** 2, 0) * R / (R - 1)
+    return mean / Ms, np.sqrt(var / R) / Ms
+
+
+@pytest.mark.parametrize('implicit,gauss', [(False, 'f32'), (False, 'f64'), (True, 'f32')])
+def test_relaxation_matches_reference_ensemble_within_3_standard_errors(orc, core, implicit, gauss):
+    """Low-barrier particle (sigma = KV/kT = 3.1) relaxing from +z: <Mz>(t) of the Philox ensemble vs
+    the reference-noise ensemble, at every sample, within 3 combined standard errors (a handful
+    of 3-sigma excursions over 40 correlated samples are allowed by construction: <= 2)."""
+    c = ol.make_case(N=1, radius=4e-9, anisotropy=4.7e4, T=300.0, dt=2e-13 if not implicit else 1e-12, t_end=4e-10,
+                     S=41, implicit=implicit, axis=[[0, 0, 1.0]], m0=[[0, 0, 1.0]])
+    Rg, Rc = 200000, 4000
+    out = gpu(core, c, np.arange(Rg) + 12345, return_trajectories=False, gauss=gauss)
+    sums_c, _ = ol.oracle_ensemble(orc, c, np.arange(Rc) + 999)
+    mg, sg = mean_and_se(out['sums'], Rg, c.Ms)
+    mc, sc = mean_and_se(sums_c, Rc, c.Ms)
+    z = (mg - mc)[1:] / np.sqrt(sg ** 2 + sc ** 2)[1:]
+    assert mg[-1] < 0.9          # it does relax
+    assert np.sum(np.abs(z) > 3) <= 2 and np.abs(z).max() < 4.5, z
+    # second moment too
+    vg = out['sums'][:, 3] / Rg / c.Ms ** 2
+    vc = sums_c[:, 3] / Rc / c.Ms ** 2
+    assert np.abs(vg - vc)[1:].max() < 0.03
+
+
+def test_dimer_relaxation_matches_reference_ensemble(orc, core):
+    """BASELINE config 2 geometry: two dipolar-coupled 7 nm particles 9 nm apart, implicit midpoint."""
+    c = ol.make_case(N=2, radius=7e-9, anisotropy=1e5, T=330.0, dt=1e-12, t_end=3e-10, S=31, implicit=True,
+                     axis=[[0, 0, 1.0], [0, 0, 1.0]], m0=[[1.0, 0, 0], [0, 1.0, 0]], location=[[0, 0, 0], [0, 0, 9e-9]])
+    Rg, Rc = 50000, 1500
+    out = gpu(core, c, np.arange(Rg) + 5, return_trajectories=False)
+    sums_c, _ = ol.oracle_ensemble(orc, c, np.arange(Rc) + 77)
+    for comp in (0, 1, 2):
+        mg = out['sums'][:, comp] / Rg / c.Ms
+        mc = sums_c[:, comp] / Rc / c.Ms
+        # per-member spread of a cluster component is < 2 (two unit moments); use the z-variance bound
+        se = np.sqrt(2.0 / Rc + 2.0 / Rg)
+        assert np.abs(mg - mc).max() < 3 * se
+    mg, sg = mean_and_se(out['sums'], Rg, c.Ms)
+    mc, sc = mean_and_se(sums_c, Rc, c.Ms)
+    z = (mg - mc)[1:] / np.sqrt(sg ** 2 + sc ** 2)[1:]
+    assert np.sum(np.abs(z) > 3) <= 2 and np.abs(z).max() < 4.5, z
+    assert out['stats']['newton_failures'] == 0
+
+
+@pytest.mark.parametrize('implicit', [False, True])
+def test_single_particle_equilibrium_is_boltzmann(core, implicit):
+    """docs/source/notebooks/single-particle-equilibrium.ipynb: p(theta) ~ sin(theta) exp(sigma cos^2 theta)."""
+    c = ol.make_case(N=1, radius=5e-9, anisotropy=4e4, T=300.0, alpha=0.5, dt=5e-13 if not implicit else 2e-12,
+                     t_end=2e-9, S=3, implicit=implicit, axis=[[0, 0, 1.0]], m0=[[0, 0, 1.0]])
+    KB = 1.38064852e-23
+    sigma = c.anisotropy[0] * 4 / 3 * np.pi * c.radius[0] ** 3 / KB / c.T
+    R = 100000
+    out = gpu(core, c, np.arange(R) * 3 + 1, return_trajectories=False)
+    m = out['final'][:, 0, :] / c.Ms
+    m /= np.linalg.norm(m, axis=1, keepdims=True)
+    Z = integrate.quad(lambda x: np.exp(sigma * x * x), -1, 1)[0]
+    for k in (2, 4):
+        want = integrate.quad(lambda x: x ** k * np.exp(sigma * x * x), -1, 1)[0] / Z
+        got = (m[:, 2] ** k).mean()
+        se = (m[:, 2] ** k).std() / np.sqrt(R)
+        assert abs(got - want) < 4 * se + 2e-3, (k, got, want, se)
+    # azimuthal symmetry
+    assert abs(m[:, 0].mean()) < 5 / np.sqrt(R) and abs(m[:, 1].mean()) < 5 / np.sqrt(R)
+
+
+def test_results_do_not_depend_on_chunking_or_sharding(core):
+    c = ol.make_case(N=1, dt=1e-13, t_end=3e-11, S=17, field_shape='sine', H0=2e4, f=4e10)
+    seeds = np.arange(300) * 11 + 3
+    whole = gpu(core, c, seeds)
+    os.environ['MAGPY_B200_MAX_CHUNK_STEPS'] = '37'
+    try:
+        chunked = gpu(core, c, seeds)
+    finally:
+        del os.environ['MAGPY_B200_MAX_CHUNK_STEPS']
+    assert chunked['stats']['kernel_launches'] > whole['stats']['kernel_launches'] + 5
+    assert np.array_equal(whole['trajectories'], chunked['trajectories'])
+    assert np.array_equal(whole['final'], chunked['final'])
+    assert np.allclose(whole['sums'], chunked['sums'], rtol=1e-14)
+    # two "ranks": members [0,140) and [140,300) with their global member offsets
+    a = gpu(core, c, seeds[:140], stream_offset=0)
+    b = gpu(core, c, seeds[140:], stream_offset=140)
+    assert np.array_equal(np.concatenate([a['trajectories'], b['trajectories']]), whole['trajectories'])
+    assert np.allclose(a['sums'] + b['sums'], whole['sums'], rtol=1e-13)
+    # a different offset is a different (independent) stream
+    d = gpu(core, c, seeds[140:], stream_offset=0)
+    assert not np.array_equal(d['final'], b['final'])
+    # cluster kernels: same invariance
+    c2 = ol.make_case(N=3, radius=7e-9, anisotropy=1e5, dt=1e-13, t_end=2e-11, S=9)
+    w2 = gpu(core, c2, seeds[:70])
+    os.environ['MAGPY_B200_MAX_CHUNK_STEPS'] = '23'
+    try:
+        ch2 = gpu(core, c2, seeds[:70])
+    finally:
+        del os.environ['MAGPY_B200_MAX_CHUNK_STEPS']
+    assert np.array_equal(w2['trajectories'], ch2['trajectories'])
+
+
+def test_hysteresis_energy_matches_reference_ensemble(orc, core):
+    """Energy dissipated per cycle, -mu0 * loop area (magpy/results.py:167-217), GPU/Philox vs
+    oracle/MT ensembles of a low-barrier particle driven at 2 GHz (short enough for the CPU)."""
+    from magpy_b200.results import EnsembleResults
+    c = ol.make_case(N=1, radius=5e-9, anisotropy=4e4, T=300.0, alpha=0.3, dt=5e-13, t_end=1e-9, S=201,
+                     field_shape='sine', H0=6e4, f=2e9, axis=[[0, 0, 1.0]], m0=[[0, 0, 1.0]])
+    Rg, Rc = 100000, 3000
+    out = gpu(core, c, np.arange(Rg) + 1, return_trajectories=False)
+    eg = EnsembleResults.from_arrays(out['time'], out['field'], Rg, sums=out['sums'], final=out['final'])
+    Eg = eg.final_cycle_energy_dissipated(c.f)
+    # bootstrap the CPU ensemble in 6 blocks for a standard error of the loop area
+    blocks = []
+    t, fl = ol.oracle_simulate(orc, c, seed=1)[:2]
+    for b in range(6):
+        s, _ = ol.oracle_ensemble(orc, c, np.arange(Rc // 6) + 1000 * (b + 1))
+        blocks.append(EnsembleResults.from_arrays(t, fl, Rc // 6, sums=s).final_cycle_energy_dissipated(c.f))
+    Ec, se = np.mean(blocks), np.std(blocks, ddof=1) / np.sqrt(6)
+    # magpy/results.py:191 returns -mu0 * integral(H dM): negative for a dissipative (lagging) loop
+    assert Eg < 0 and Ec < 0 and abs(Eg) > 100.0
+    assert abs(Eg - Ec) < 3.5 * se + 0.01 * abs(Ec), (Eg, Ec, se)
+
+
+def _coupled_levels(core, c, n_fine, levels, R, rng):
+    """Final states for step sizes dt*2^l driven by the SAME Brownian paths (coarse increments are
+    sums of fine ones, as test/convergence/task5.cpp:150-158)."""
+    w = rng.normal(size=(R, n_fine, 3 * c.N))
+    finals = []
+    base_dt = c.dt
+    for l in range(levels):
+        m = 2 ** l
+        wl = w.reshape(R, n_fine // m, m, 3 * c.N).sum(axis=2) / np.sqrt(m)
+        cc = ol.Case(c)
+        cc['dt'] = base_dt * m
+        cc["t_end"] = base_dt * n_fine * (1 + 1e-9)      # zero-order hold: the last sample is the state after n_fine/m steps
+        cc['S'] = 2
+        # the reference executes one more (unobserved) step: pad the stream by one increment
+        wl = np.concatenate([wl, np.zeros((R, 2, 3 * c.N))], axis=1)
+        out = core.simulate_ensemble(cc.radius, cc.anisotropy, cc.axis, cc.m0, cc.location, cc.Ms, cc.alpha, cc.T,
+                                     False, True, cc.implicit, cc.dt, cc.t_end, cc.S, np.zeros(R, dtype=np.int64),
+                                     implicit_tol=cc.eps, injected_dw=wl, return_trajectories=False)
+        assert out['stats']['steps_per_member'] == n_fine // m
+        finals.append(out['final'][:, 0, :] / cc.Ms)
+    return finals
+
+
+@pytest.mark.parametrize('implicit', [False, True])
+def test_strong_convergence_order(orc, core, implicit):
+    """test/convergence/task5 (+ docs/source/notebooks/convergence.ipynb cells 29-38): mean 2-norm of
+    the Cauchy differences between consecutive step sizes on common Brownian paths has slope
+    ~0.5 in log2(dt) for both schemes (the reference's own run: 0.509 Heun, 0.511 implicit)."""
+    rng = np.random.default_rng(2024)
+    c = ol.make_case(N=1, radius=6e-9, anisotropy=4e4, T=300.0, alpha=0.1, implicit=implicit, eps=1e-10,
+                     axis=[[0, 0, 1.0]], m0=[[1.0, 0, 0]])
+    tf = ol.reduced_scalars(orc, c)['time_factor']
+    c['dt'] = 0.0025 / tf                              # reduced dt = 0.0025 * 2^l
+    R, n_fine, levels = 10000, 1280, 6
+    finals = _coupled_levels(core, c, n_fine, levels, R, rng)
+    strong = [np.linalg.norm(finals[l + 1] - finals[l], axis=1).mean() for l in range(levels - 1)]
+    order = np.polyfit(np.arange(levels - 1), np.log2(strong), 1)[0]
+    assert 0.4 < order < 0.7, (order, strong)
+
+
+@pytest.mark.parametrize('implicit', [False, True])
+def test_weak_convergence_order(orc, core, implicit):
+    """The reference has no weak-order test; ours: |E m_z(T)^{dt} - E m_z(T)^{2dt}| on
+    common Brownian paths (variance reduction), an observable without a symmetry that would
+    make it vanish.  Heun and the midpoint rule are weakly first order: slope ~1."""
+    rng = np.random.default_rng(7)
+    c = ol.make_case(N=1, radius=6e-9, anisotropy=4e4, T=300.0, alpha=0.1, implicit=implicit, eps=1e-10,
+                     axis=[[0, 0, 1.0]], m0=[[0.6, 0, 0.8]])
+    tf = ol.reduced_scalars(orc, c)['time_factor']
+    c['dt'] = 0.02 / tf
+    R, n_fine, levels = 40000, 256, 5
+    finals = _coupled_levels(core, c, n_fine, levels, R, rng)
+    diff = [finals[l + 1][:, 2] - finals[l][:, 2] for l in range(levels - 1)]
+    weak = np.array([abs(d.mean()) for d in diff])
+    se = np.array([d.std() / np.sqrt(R) for d in diff])
+    sig = [l for l in range(levels - 1) if weak[l] > 3 * se[l]]
+    assert len(sig) >= 3, (weak, se)
+    order = np.polyfit(np.array(sig), np.log2(weak[sig]), 1)[0]
+    assert 0.6 < order < 2.4, (order, weak, se)
