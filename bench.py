@@ -247,7 +247,7 @@ def ours(args):
                              w['alpha'], w['T'], False, True, False, w['dt'], w['t_end'], w['S'], seeds,
                              field_shape=w['field_shape'], field_amplitude=w['H0'], field_frequency=w['f'],
                              device=local_rank, stream_offset=rank * R, return_trajectories=False,
-                             return_sums=True, return_final=True, gauss='f32')
+                             return_sums=True, return_final=True, gauss='f32p')
 
     def barrier():
         if dist is not None:
@@ -360,7 +360,7 @@ def ours(args):
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': w['name'], 'realisations_per_gpu': R, 'particles': 1, 'heun_steps_per_pass': n_steps,
-                   'samples': w['S'], 'rng': 'Philox4x32-10 + fp32 Box-Muller (in kernel)',
+                   'samples': w['S'], 'rng': 'Philox4x32-10 + fp32 Box-Muller in kernel, one Philox block per two steps (gauss=f32p)',
                    'l2': 'state is register resident; no input is re-read between passes (0 B/step steady-state HBM '
                          'traffic), so no L2 flush applies',
                    'timing': 'CUDA events on the launching stream, max over ranks',

@@ -38,8 +38,10 @@ extern "C" {
 #define MAGPY_B200_FIELD_CONSTANT 2
 
 /* Gaussian transform applied to the Philox4x32-10 words (replaces lib/rng.cpp:14-24) */
-#define MAGPY_B200_GAUSS_F32 0 /* Box-Muller in fp32 on the SFU, widened to fp64 (default) */
+#define MAGPY_B200_GAUSS_F32 0 /* Box-Muller in fp32 on the SFU (32-bit uniforms), widened to fp64 */
 #define MAGPY_B200_GAUSS_F64 1 /* Box-Muller in fp64 from 53-bit uniforms                  */
+#define MAGPY_B200_GAUSS_F32_PACKED 2 /* fp32 Box-Muller, 24-bit radius / 18-bit angle uniforms:
+                                         one Philox block feeds two particle-steps          */
 
 /* Statistics returned by every run (replaces the error codes the reference computes
  * and drops at lib/simulation.cpp:368-369 and the joblib progress lines of

@@ -33,6 +33,7 @@ cdef extern from "magpy_b200.h" nogil:
     int MAGPY_B200_FIELD_CONSTANT
     int MAGPY_B200_GAUSS_F32
     int MAGPY_B200_GAUSS_F64
+    int MAGPY_B200_GAUSS_F32_PACKED
 
     ctypedef struct magpy_b200_stats:
         uint64_t steps_per_member
@@ -115,7 +116,7 @@ SQUARE = 1
 CONSTANT = 2
 
 _FIELD_LOOKUP = {'constant': CONSTANT, 'sine': SINE, 'square': SQUARE}
-_GAUSS_LOOKUP = {'f32': 0, 'f64': 1}
+_GAUSS_LOOKUP = {'f32': 0, 'f64': 1, 'f32p': 2}
 
 
 cdef _raise(int rc):
@@ -330,7 +331,7 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
                       bint use_implicit, double time_step, double end_time, max_samples, seeds,
                       str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
                       double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=True,
-                      bint return_sums=True, bint return_final=True, str gauss='f32', injected_dw=None):
+                      bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None):
     """Integrate R = len(seeds) independent members of one cluster in a single call.
 
     `anisotropy_axis` and `magnetisation_direction` are (N,3) (shared) or (R,N,3).
@@ -368,7 +369,7 @@ cdef class EnsemblePlan:
                  bint use_implicit, double time_step, double end_time, max_samples, seeds,
                  str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
                  double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=False,
-                 bint return_sums=True, bint return_final=True, str gauss='f32', injected_dw=None):
+                 bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None):
         self.e = _build_args(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
                              magnetisation, damping, temperature, renorm, interactions, use_implicit,
                              time_step, end_time, max_samples, seeds, field_shape, field_amplitude,
@@ -463,7 +464,7 @@ def philox_words(ctr, key, int device=0):
     return [o[0], o[1], o[2], o[3]]
 
 
-def gaussians(seed, member, particle, first_step, n_steps, str gauss='f32', int device=0):
+def gaussians(seed, member, particle, first_step, n_steps, str gauss='f32p', int device=0):
     """The (n_steps, 3) unit-variance draws the kernels use for (seed, member, particle)."""
     cdef np.ndarray[double, ndim=2] out = np.empty((int(n_steps), 3))
     cdef int rc = magpy_b200_gaussians(device, int(seed), int(member), int(particle), int(first_step),

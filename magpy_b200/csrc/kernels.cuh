@@ -25,7 +25,7 @@
 
 namespace mb {
 
-enum { NOISE_PHILOX_F32 = 0, NOISE_PHILOX_F64 = 1, NOISE_INJECTED = 2 };
+enum { NOISE_PHILOX_F32 = 0, NOISE_PHILOX_F64 = 1, NOISE_INJECTED = 2, NOISE_PHILOX_PACKED = 3 };
 
 struct RunParams {
     uint64_t R;       // members on this device
@@ -180,19 +180,48 @@ __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __gri
     const uint32_t member = (uint32_t)(r + P.stream_offset);
     const bool renorm = P.renorm != 0;
 
+    // one Heun step from the scaled increment cw; j is the 0-based step index
+    auto advance = [&](const V3& cw, const uint64_t jj) {
+        double hz0 = P.h_const, hz1 = P.h_const;
+        if (FIELD_TAB) {
+            const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (jj - P.j0));
+            hz0 = h.x; hz1 = h.y;
+        }
+        m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
+        if (renorm) renormalise(m);
+    };
+
     uint64_t j = P.j0;
+    float carry[3] = {0.f, 0.f, 0.f};   // packed mode: increments of the odd step of the current Philox block
+    if (NOISE == NOISE_PHILOX_PACKED && (j & 1)) {
+        float g[6];
+        philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
+        carry[0] = g[3]; carry[1] = g[4]; carry[2] = g[5];
+    }
     for (uint32_t k = P.k0; k <= P.k1; ++k) {
         const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
-#pragma unroll 2
-        for (; j < tgt; ++j) {
-            const V3 cw = draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, c, bm_scale);
-            double hz0 = P.h_const, hz1 = P.h_const;
-            if (FIELD_TAB) {
-                const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - P.j0));
-                hz0 = h.x; hz1 = h.y;
+        if (NOISE == NOISE_PHILOX_PACKED) {
+            // invariant: when j is odd, `carry` holds the second half of block j >> 1
+            if ((j & 1) && j < tgt) {
+                advance(V3{widen_f32(carry[0]), widen_f32(carry[1]), widen_f32(carry[2])}, j);
+                ++j;
             }
-            m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
-            if (renorm) renormalise(m);
+            for (; j + 2 <= tgt; j += 2) {
+                float g[6];
+                philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, j);
+                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, j + 1);
+            }
+            if (j < tgt) {
+                float g[6];
+                philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, j);
+                carry[0] = g[3]; carry[1] = g[4]; carry[2] = g[5];
+                ++j;
+            }
+        } else {
+#pragma unroll 2
+            for (; j < tgt; ++j) advance(draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, c, bm_scale), j);
         }
         if (k < P.k1) {
             if (P.traj != nullptr && live) {
@@ -756,6 +785,13 @@ __global__ void transpose_kernel(const double* in, double* out, uint64_t rows, u
         const uint64_t cc = c0 + i, rr = r0 + threadIdx.x;
         if (rr < rows && cc < cols) dst[cc * out_rs + rr] = tile[threadIdx.x][i] * scale;
     }
+}
+
+// out[q][r] = in[q] for q < n, r < R (shared initial state replicated over the members)
+__global__ void broadcast_rows_kernel(const double* in, double* out, uint64_t n, uint64_t R) {
+    const uint64_t total = n * R;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = in[i / R];
 }
 
 __global__ void scale_kernel(double* a, uint64_t n, double s) {

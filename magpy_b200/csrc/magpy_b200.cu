@@ -249,6 +249,9 @@ int set_smem_attr_nt(magpy_b200_plan* pl) {
 #define DISPATCH_NT(fn, pl, ...)                                                                      \
     ((pl)->injected                                                                                   \
          ? ((pl)->use_table ? fn<mb::NOISE_INJECTED, true>(__VA_ARGS__) : fn<mb::NOISE_INJECTED, false>(__VA_ARGS__)) \
+     : (pl)->gauss_mode == MAGPY_B200_GAUSS_F32_PACKED                                                \
+         ? ((pl)->use_table ? fn<mb::NOISE_PHILOX_PACKED, true>(__VA_ARGS__)                          \
+                            : fn<mb::NOISE_PHILOX_PACKED, false>(__VA_ARGS__))                        \
      : (pl)->gauss_mode == MAGPY_B200_GAUSS_F64                                                       \
          ? ((pl)->use_table ? fn<mb::NOISE_PHILOX_F64, true>(__VA_ARGS__)                             \
                             : fn<mb::NOISE_PHILOX_F64, false>(__VA_ARGS__))                           \
@@ -292,8 +295,9 @@ int validate(const magpy_b200_ensemble* a) {
         a->field_shape != MAGPY_B200_FIELD_CONSTANT)
         return fail(MAGPY_B200_ERR_BAD_ARG, "Must specify valid field::options enum (lib/simulation.cpp:570-572)");
     if (!a->injected_dw && !a->seeds) return fail(MAGPY_B200_ERR_BAD_ARG, "seeds must not be NULL unless injected_dw is given");
-    if (a->gauss_mode != MAGPY_B200_GAUSS_F32 && a->gauss_mode != MAGPY_B200_GAUSS_F64)
-        return fail(MAGPY_B200_ERR_BAD_ARG, "gauss_mode must be MAGPY_B200_GAUSS_F32 or _F64");
+    if (a->gauss_mode != MAGPY_B200_GAUSS_F32 && a->gauss_mode != MAGPY_B200_GAUSS_F64 &&
+        a->gauss_mode != MAGPY_B200_GAUSS_F32_PACKED)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "gauss_mode must be MAGPY_B200_GAUSS_F32, _F64 or _F32_PACKED");
     if (!(a->magnetisation > 0.0)) return fail(MAGPY_B200_ERR_BAD_ARG, "magnetisation must be > 0");
     if (a->use_implicit) {
         if (a->n_particles > 32) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 32 particles per cluster");
@@ -448,11 +452,14 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         rc = launch_transpose(pl, pl->d_stage.p, pl->d_state0.p, 1, R, n, 0, n, 0, R, 1.0);
         if (rc) return rc;
     } else {
-        std::vector<double> rep(n * R);
-        for (uint64_t q = 0; q < n; ++q) std::fill_n(rep.begin() + q * R, R, a->magnetisation_direction[q]);
-        CU_TRY(cudaMemcpyAsync(pl->d_state0.p, rep.data(), n * R * 8, cudaMemcpyHostToDevice, pl->stream));
-        CU_TRY(cudaStreamSynchronize(pl->stream));
-        pl->h2d += n * R * 8;
+        // shared initial state: upload the n values once and replicate them on the device
+        CU_TRY(cudaMemcpyAsync(pl->d_stage.p, a->magnetisation_direction, n * 8, cudaMemcpyHostToDevice, pl->stream));
+        pl->h2d += n * 8;
+        const uint64_t total = n * R;
+        mb::broadcast_rows_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, pl->stream>>>(
+            pl->d_stage.p, pl->d_state0.p, n, R);
+        CU_TRY(cudaGetLastError());
+        pl->launches++;
     }
     if (a->axis_stride) {
         CU_TRY(pl->d_axis.alloc(n * R));
@@ -791,7 +798,7 @@ int magpy_b200_simulate(const double* radius, const double* anisotropy, const do
     a.field_amplitude = field_amplitude;
     a.field_frequency = field_frequency;
     a.seeds = &seed;
-    a.gauss_mode = MAGPY_B200_GAUSS_F32;
+    a.gauss_mode = MAGPY_B200_GAUSS_F32_PACKED;
     a.out_time = out_time;
     a.out_field = out_field;
     a.out_trajectories = out_m;  // [1][N][3][S]
@@ -819,7 +826,9 @@ int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t par
     DevBuf<double> d;
     CU_TRY(d.alloc(3 * n_steps));
     const unsigned g = (unsigned)((n_steps + 255) / 256);
-    if (gauss_mode == MAGPY_B200_GAUSS_F64)
+    if (gauss_mode == MAGPY_B200_GAUSS_F32_PACKED)
+        mb::gaussians_kernel<mb::NOISE_PHILOX_PACKED><<<g, 256>>>((uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p);
+    else if (gauss_mode == MAGPY_B200_GAUSS_F64)
         mb::gaussians_kernel<1><<<g, 256>>>((uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p);
     else
         mb::gaussians_kernel<0><<<g, 256>>>((uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p);

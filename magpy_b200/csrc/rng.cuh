@@ -14,6 +14,10 @@
 //              (keeps the FP64 pipe for the integrator).  One Philox call yields the 3 draws of
 //              a particle-step.
 //   GAUSS_F64: Box-Muller in fp64 from 53-bit uniforms (two Philox calls per particle-step).
+//   GAUSS_F32_PACKED: fp32 Box-Muller with 24-bit radius / 18-bit angle uniforms, so that one
+//              Philox block feeds TWO particle-steps (the integer multiplies of Philox share an
+//              issue port with DFMA on sm_100a — profiles/README.md — so halving them is what
+//              raises the FP64 pipe's share of the cycle).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -71,20 +75,19 @@ __device__ __forceinline__ float lg2_approx(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float rsqrt_approx(float x) {
+__device__ __forceinline__ float sqrt_approx(float x) {   // one MUFU.SQRT; sqrt(0) = 0
     float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
 // Box-Muller radius times `amp`:  amp * sqrt(-2 ln u),  u in (0,1) from 32 bits.
 // neg2ln2_amp2 = -2 ln(2) amp^2 folds the scale into the one multiply that follows lg2, so a
 // scaled draw costs the same as a unit one.  The integer is converted toward zero so that u
-// never rounds to 1 (which would make the radius 0 * inf).  Branch free: 2 MUFU + 4 FP32.
+// never rounds to 1.  Branch free: I2FP, FFMA, MUFU.LG2, FMUL, MUFU.SQRT.
 __device__ __forceinline__ float bm_radius_f32(uint32_t x, float neg2ln2_amp2) {
     const float u = fmaf(__uint2float_rz(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    const float y = lg2_approx(u) * neg2ln2_amp2;
-    return y * rsqrt_approx(y);
+    return sqrt_approx(lg2_approx(u) * neg2ln2_amp2);
 }
 
 #define MB_TWO_PI_2M32 1.4629180792671596e-9f /* 2 pi 2^-32 */
@@ -106,6 +109,40 @@ __device__ __forceinline__ void philox_gauss3_f32(uint32_t seed_lo, uint32_t see
     gz = r2 * __cosf(a2);
 }
 
+// Packed mode: SIX draws of N(0, amp^2) from one Philox block, i.e. the increments of the two
+// steps s = 2b and s = 2b + 1 (s = 0-based step index) of one (member, particle).  The 128 bits
+// w0:w1:w2:w3 are cut, most significant first, into three (24-bit radius uniform, 18-bit angle)
+// pairs — 126 bits used.  24 bits is what the fp32 logarithm resolves anyway (radius up to
+// 5.9 sigma); 2^18 equidistant directions reproduce every circular moment below order 2^18.
+//   pair 0 -> g[0], g[1]    pair 1 -> g[2], g[3]    pair 2 -> g[4], g[5]
+// g[0..2] belong to the even step, g[3..5] to the odd one.
+#define MB_PACKED_KEY_TAG (2u << 24)
+#define MB_TWO_PI_2M18 2.3968449810713143e-5f /* 2 pi 2^-18 */
+
+__device__ __forceinline__ void bm_pair_packed(uint32_t r24, uint32_t a18, float neg2ln2_amp2, float& c, float& s) {
+    const float u = fmaf((float)r24, 5.9604644775390625e-08f, 2.98023223876953125e-08f);  // (k + 1/2) 2^-24
+    const float r = sqrt_approx(lg2_approx(u) * neg2ln2_amp2);
+    const float a = (float)a18 * MB_TWO_PI_2M18;
+    c = r * __cosf(a);
+    s = r * __sinf(a);
+}
+
+__device__ __forceinline__ void philox_gauss6_f32(uint32_t seed_lo, uint32_t seed_hi, uint64_t pair_index,
+                                                  uint32_t particle, uint32_t member, float neg2ln2_amp2,
+                                                  float (&g)[6]) {
+    uint32_t w0 = (uint32_t)pair_index, w1 = member, w2 = seed_lo, w3 = seed_hi;
+    philox4x32_10(w0, w1, w2, w3, particle | MB_PACKED_KEY_TAG, MB_PHILOX_KEY1);
+    const uint32_t r0 = w0 >> 8;                                        // bits   0..23
+    const uint32_t a0 = __funnelshift_l(w1, w0, 10) & 0x3ffffu;         // bits  24..41
+    const uint32_t r1 = __funnelshift_l(w2, w1, 10) >> 8;               // bits  42..65
+    const uint32_t a1 = (w2 >> 12) & 0x3ffffu;                          // bits  66..83
+    const uint32_t r2 = __funnelshift_l(w3, w2, 20) >> 8;               // bits  84..107
+    const uint32_t a2 = (w3 >> 2) & 0x3ffffu;                           // bits 108..125
+    bm_pair_packed(r0, a0, neg2ln2_amp2, g[0], g[1]);
+    bm_pair_packed(r1, a1, neg2ln2_amp2, g[2], g[3]);
+    bm_pair_packed(r2, a2, neg2ln2_amp2, g[4], g[5]);
+}
+
 struct Gauss3 {
     double x, y, z;
 };
@@ -115,7 +152,14 @@ template <int GAUSS_MODE>
 __device__ __forceinline__ Gauss3 philox_gauss3(uint32_t seed_lo, uint32_t seed_hi, uint64_t step,
                                                 uint32_t particle, uint32_t member) {
     Gauss3 g;
-    if (GAUSS_MODE == 0) {
+    if (GAUSS_MODE == 3) {   // packed (NOISE_PHILOX_PACKED): `step` is 1-based (the reference's counter), blocks pair steps (0,1), (2,3), ...
+        float v[6];
+        philox_gauss6_f32(seed_lo, seed_hi, (step - 1) >> 1, particle, member, MB_NEG_2LN2, v);
+        const bool odd = ((step - 1) & 1) != 0;
+        g.x = widen_f32(odd ? v[3] : v[0]);
+        g.y = widen_f32(odd ? v[4] : v[1]);
+        g.z = widen_f32(odd ? v[5] : v[2]);
+    } else if (GAUSS_MODE == 0) {
         float x, y, z;
         philox_gauss3_f32(seed_lo, seed_hi, step, particle, member, MB_NEG_2LN2, x, y, z);
         g.x = widen_f32(x);

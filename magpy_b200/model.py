@@ -110,7 +110,7 @@ class EnsembleModel:
 
     def simulate(self, end_time, time_step, max_samples, random_state, renorm=False, interactions=True,
                  n_jobs=1, implicit_solve=True, implicit_tol=1e-9, device=0, stream_offset=0,
-                 return_trajectories=None, gauss='f32', shard=None):
+                 return_trajectories=None, gauss='f32p', shard=None):
         """Simulate every member; arguments up to `implicit_tol` as magpy/model.py:159-208.
 
         `n_jobs` is accepted and ignored (the ensemble runs as one device launch).
@@ -119,7 +119,8 @@ class EnsembleModel:
             stream_offset (int): global index of member 0 (used when an ensemble is sharded).
             return_trajectories (bool|None): keep per-member trajectories; None = keep them
                 when they take less than 2 GiB.
-            gauss ('f32'|'f64'): Gaussian transform of the in-kernel Philox stream.
+            gauss ('f32p'|'f32'|'f64'): Gaussian transform of the in-kernel Philox stream (packed fp32
+                Box-Muller, one Philox block per two steps; fp32 with 32-bit uniforms; fp64).
             shard ((rank, world_size)|None): integrate only this rank's contiguous slice of the
                 members (magpy_b200.sharding.shard_bounds) and all-reduce the ensemble sums over the
                 initialised torch.distributed group; per-member outputs then cover the local slice.

@@ -130,7 +130,11 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * restatement of magpy_b200/csrc/rng.cuh (philox_gauss3) for the parity tests.
  * counter = (step, member, seed_lo, seed_hi), key = (particle | block<<24, 0xB2005EED).
  * mode 0: fp32 Box-Muller of one Philox block (device uses SFU approximations, so compare
- *         with a ~1e-5 tolerance); mode 1: fp64 Box-Muller from 53-bit uniforms, two blocks. */
+ *         with a ~1e-5 tolerance); mode 1: fp64 Box-Muller from 53-bit uniforms, two blocks;
+ * mode 2: packed fp32 Box-Muller — ONE block, counter word 0 = (step-1)>>1, key word 0 =
+ *         particle | 2<<24, feeds the two steps 2b+1, 2b+2: the 128 bits w0:w1:w2:w3 are cut
+ *         into three (24-bit radius, 18-bit angle) pairs -> six draws, the first three for
+ *         the odd `step` (1-based), the last three for the even one. */
 static float u32_to_float_rz(uint32_t x) { /* cvt.rz.f32.u32 */
     if (x >= (1u << 24)) {
         int sh = 8 - __builtin_clz(x);
@@ -139,7 +143,36 @@ static float u32_to_float_rz(uint32_t x) { /* cvt.rz.f32.u32 */
     return (float)x;
 }
 
+static void bm_pair_packed(uint32_t r24, uint32_t a18, float* c, float* s) {
+    const float u = fmaf((float)r24, 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+    const float r = sqrtf(log2f(u) * -1.3862943611198906f);
+    const float a = (float)a18 * 2.3968449810713143e-5f;
+    *c = r * cosf(a);
+    *s = r * sinf(a);
+}
+
 void orc_philox_gauss3(uint64_t seed, uint32_t member, uint32_t particle, uint64_t step, int mode, double out[3]) {
+    if (mode == 2) {
+        const uint32_t pkey[2] = {particle | (2u << 24), 0xB2005EEDu};
+        const uint32_t pctr[4] = {(uint32_t)((step - 1) >> 1), member, (uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t v[4];
+        float g[6];
+        orc_philox4x32_10(pctr, pkey, v);
+        const uint64_t hi = ((uint64_t)v[0] << 32) | v[1], lo = ((uint64_t)v[2] << 32) | v[3];
+        /* bit i of the 128-bit string (0 = most significant) */
+#define ORC_BITS(pos, len)                                                                         \
+    (uint32_t)((((pos) + (len) <= 64) ? (hi >> (64 - (pos) - (len)))                                 \
+                : ((pos) >= 64)      ? (lo >> (128 - (pos) - (len)))                                \
+                                     : ((hi << ((pos) + (len) - 64)) | (lo >> (128 - (pos) - (len))))) & \
+               ((1ull << (len)) - 1))
+        bm_pair_packed(ORC_BITS(0, 24), ORC_BITS(24, 18), &g[0], &g[1]);
+        bm_pair_packed(ORC_BITS(42, 24), ORC_BITS(66, 18), &g[2], &g[3]);
+        bm_pair_packed(ORC_BITS(84, 24), ORC_BITS(108, 18), &g[4], &g[5]);
+#undef ORC_BITS
+        const int odd = (int)((step - 1) & 1);
+        for (int i = 0; i < 3; ++i) out[i] = (double)g[3 * odd + i];
+        return;
+    }
     uint32_t key[2] = {particle, 0xB2005EEDu};
     const uint32_t ctr[4] = {(uint32_t)step, member, (uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t w[4];

@@ -1,34 +1,61 @@
-// Micro-benchmark: how many issue cycles does a DFMA cost next to FP32 / INT work on sm_100a?
-// Each kernel runs K independent DFMA chains plus `MIX` independent non-FP64 ops per DFMA.
+// Micro-benchmark: what does one DFMA cost in issue/dispatch cycles on sm_100a next to the other
+// instruction classes of the Heun kernel (Philox = IMAD.WIDE + LOP3, Box-Muller = MUFU + FMUL,
+// widening = F2F.F64.F32)?  Every kernel runs 8 independent DFMA chains per thread (NDF = 1) or none
+// (NDF = 0) plus MIX independent "other" ops per DFMA slot.  Reported: SM cycles per slot per SMSP.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o issue_mix issue_mix.cu && ./issue_mix
 #include <cstdio>
 #include <cuda_runtime.h>
 
-template <int MIX, int KIND>
+enum { K_FFMA = 0, K_IMAD = 1, K_LOP = 2, K_IMADW = 3, K_MUFU = 4, K_F2F = 5, K_I2F = 6, K_HILO = 7, K_HI = 8, K_PRMT = 9 };
+
+template <int NDF, int MIX, int KIND>
 __global__ void mix_kernel(double* out, float* fout, int iters, double a, double b, float fa, unsigned ia) {
     double x[8];
     float y[16];
     unsigned z[16];
+    double dacc = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = threadIdx.x + i;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { y[i] = threadIdx.x * 0.5f + i; z[i] = threadIdx.x * 7 + i; }
+    for (int i = 0; i < 16; ++i) { y[i] = threadIdx.x * 0.5f + i + 1.0f; z[i] = threadIdx.x * 7 + i; }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                x[i] = fma(x[i], a, b);
+                if (NDF) x[i] = fma(x[i], a, b);
 #pragma unroll
                 for (int m = 0; m < MIX; ++m) {
                     const int q = (i * MIX + m) & 15;
-                    if (KIND == 0) y[q] = fmaf(y[q], fa, 1.0f);
-                    else if (KIND == 1) z[q] = z[q] * ia + 12345u;          // IMAD
-                    else z[q] = (z[q] ^ ia) + (z[q] >> 3);                   // LOP3/SHF/IADD mix
+                    if (KIND == K_FFMA) y[q] = fmaf(y[q], fa, 1.0f);
+                    else if (KIND == K_IMAD) z[q] = z[q] * ia + 12345u;
+                    else if (KIND == K_LOP) z[q] = (z[q] ^ ia) + (z[q] >> 3);   // LOP3 / SHF / IADD mix (3 instr)
+                    else if (KIND == K_IMADW) {
+                        unsigned long long p;
+                        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(z[q]), "r"(ia));
+                        unsigned lo, hi;
+                        asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+                        z[q] = hi ^ lo;                                           // IMAD.WIDE + LOP3
+                    } else if (KIND == K_MUFU) {
+                        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y[q]) : "f"(y[q]));
+                    } else if (KIND == K_F2F) {
+                        z[q] ^= (unsigned)__double2hiint((double)y[q]);           // F2F.F64.F32 + LOP3 + FADD
+                        y[q] += 1.0f;
+                    } else if (KIND == K_I2F) {
+                        y[q] += __uint2float_rz(z[q]);                            // I2FP + FADD + IADD
+                        z[q] += 3u;
+                    } else if (KIND == K_HILO) {
+                        z[q] = __umulhi(z[q], ia) ^ (z[q] * ia);                  // IMAD.HI.U32 + IMAD + LOP3
+                    } else if (KIND == K_HI) {
+                        z[q] = __umulhi(z[q], ia);                                // IMAD.HI.U32
+                    } else if (KIND == K_PRMT) {
+                        z[q] = __byte_perm(z[q], ia, 0x2103);                     // PRMT
+                    }
                 }
             }
         }
     }
-    double s = 0; float t = 0; unsigned w = 0;
+    double s = dacc; float t = 0; unsigned w = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += x[i];
 #pragma unroll
@@ -37,38 +64,57 @@ __global__ void mix_kernel(double* out, float* fout, int iters, double a, double
     fout[blockIdx.x * blockDim.x + threadIdx.x] = t + (float)w;
 }
 
-template <int MIX, int KIND>
+template <int NDF, int MIX, int KIND>
 void run(const char* name, int warps_per_smsp) {
     int dev = 0; cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
-    const int threads = 128, blocks = p.multiProcessorCount * warps_per_smsp, iters = 4096;
+    const int threads = 128, blocks = p.multiProcessorCount * warps_per_smsp, iters = 2048;
     double* d; float* f;
     cudaMalloc(&d, sizeof(double) * blocks * threads); cudaMalloc(&f, sizeof(float) * blocks * threads);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int r = 0; r < 4; ++r) {
         cudaEventRecord(e0);
-        mix_kernel<MIX, KIND><<<blocks, threads>>>(d, f, iters, 0.999999, 1e-7, 0.999f, 2654435761u);
+        mix_kernel<NDF, MIX, KIND><<<blocks, threads>>>(d, f, iters, 0.999999, 1e-7, 0.999f, 2654435761u);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (r && ms < best) best = ms;
     }
     int khz; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
-    // warp-level DFMAs per SMSP: each SMSP has warps_per_smsp warps (blocks*4 warps over SMs*4 SMSPs)
-    const double dfma_per_warp = (double)iters * 4 * 8;
+    const double slots_per_warp = (double)iters * 4 * 8;
     const double cycles = best * 1e-3 * khz * 1e3;
-    printf("%-28s warps/SMSP=%2d  %.3f ms  cycles per DFMA-slot (per SMSP) = %.3f  [%d other ops per DFMA]\n", name,
-           warps_per_smsp, best, cycles / (dfma_per_warp * warps_per_smsp), MIX);
+    printf("%-34s warps/SMSP=%2d  %8.3f ms  cycles per slot per SMSP = %6.3f  [%d DFMA + %d other per slot]\n", name,
+           warps_per_smsp, best, cycles / (slots_per_warp * warps_per_smsp), NDF, MIX);
     cudaFree(d); cudaFree(f);
 }
 
 int main() {
-    for (int w : {4, 8}) {
-        run<0, 0>("DFMA only", w);
-        run<1, 0>("DFMA + 1 FFMA", w);
-        run<2, 0>("DFMA + 2 FFMA", w);
-        run<3, 0>("DFMA + 3 FFMA", w);
-        run<1, 1>("DFMA + 1 IMAD", w);
-        run<2, 1>("DFMA + 2 IMAD", w);
-        run<1, 2>("DFMA + 1 (LOP3,SHF,IADD)", w);
+    for (int w : {8}) {
+        run<1, 0, K_FFMA>("DFMA only", w);
+        run<1, 1, K_FFMA>("DFMA + 1 FFMA", w);
+        run<1, 2, K_FFMA>("DFMA + 2 FFMA", w);
+        run<1, 3, K_FFMA>("DFMA + 3 FFMA", w);
+        run<0, 2, K_FFMA>("2 FFMA", w);
+        run<1, 1, K_IMAD>("DFMA + 1 IMAD", w);
+        run<1, 2, K_IMAD>("DFMA + 2 IMAD", w);
+        run<0, 2, K_IMAD>("2 IMAD", w);
+        run<1, 1, K_IMADW>("DFMA + 1 (IMAD.WIDE,LOP3)", w);
+        run<1, 2, K_IMADW>("DFMA + 2 (IMAD.WIDE,LOP3)", w);
+        run<0, 2, K_IMADW>("2 (IMAD.WIDE,LOP3)", w);
+        run<1, 1, K_LOP>("DFMA + 1 (LOP3,SHF,IADD)", w);
+        run<0, 1, K_LOP>("1 (LOP3,SHF,IADD)", w);
+        run<1, 1, K_MUFU>("DFMA + 1 MUFU", w);
+        run<0, 1, K_MUFU>("1 MUFU", w);
+        run<1, 1, K_F2F>("DFMA + 1 (F2F.F64.F32,LOP3,FADD)", w);
+        run<0, 1, K_F2F>("1 (F2F.F64.F32,LOP3,FADD)", w);
+        run<1, 1, K_I2F>("DFMA + 1 (I2FP,FADD,IADD)", w);
+        run<0, 1, K_I2F>("1 (I2FP,FADD,IADD)", w);
+        run<1, 1, K_HILO>("DFMA + 1 (IMAD.HI,IMAD,LOP3)", w);
+        run<1, 2, K_HILO>("DFMA + 2 (IMAD.HI,IMAD,LOP3)", w);
+        run<0, 1, K_HILO>("1 (IMAD.HI,IMAD,LOP3)", w);
+        run<1, 1, K_HI>("DFMA + 1 IMAD.HI", w);
+        run<1, 2, K_HI>("DFMA + 2 IMAD.HI", w);
+        run<0, 2, K_HI>("2 IMAD.HI", w);
+        run<0, 2, K_PRMT>("2 PRMT", w);
+        run<1, 2, K_PRMT>("DFMA + 2 PRMT", w);
     }
     return 0;
 }

@@ -17,9 +17,9 @@ def run(R, steps, axis=(0, 0, 1.0), field='sine', gauss='f32', S=21, dt=1e-12, r
     print(f'R={R} steps={steps} axis={axis} field={field} gauss={gauss} renorm={renorm}: {st["integrate_ms"]:.2f} ms, '
           f'{ps:.4e} particle-steps/s, <mz>={out["sums"][-1,2]/R/4e5:.5f}', flush=True)
 
-run(1000000, 20000)
-run(1000000, 20000, axis=(0.6, 0, 0.8))
-run(1000000, 20000, field='constant')
-run(1000000, 10000, renorm=True)
-run(1 << 20, 20000)
-run(148 * 2048 * 3, 20000)
+for g in (sys.argv[1:] or ['f32p', 'f32']):
+    run(1000000, 20000, gauss=g)
+    run(1000000, 20000, axis=(0.6, 0, 0.8), gauss=g)
+    run(1000000, 20000, field='constant', gauss=g)
+    run(1000000, 10000, renorm=True, gauss=g)
+    run(148 * 2048 * 3, 20000, gauss=g)

@@ -80,11 +80,11 @@ def test_philox_words_match_random123_and_oracle(orc, core):
         assert core.philox_words(ctr, key) == ol.philox(orc, ctr, key)
 
 
-@pytest.mark.parametrize('mode,tol', [('f64', 1e-13), ('f32', 2e-5)])
+@pytest.mark.parametrize('mode,tol', [('f64', 1e-13), ('f32', 2e-5), ('f32p', 2e-5)])
 def test_gaussian_stream_matches_oracle(orc, core, mode, tol):
     seed, member, particle, first, n = 123456789012345, 77, 3, 1000, 4096
     got = core.gaussians(seed, member, particle, first, n, gauss=mode)
-    want = np.array([ol.philox_gauss3(orc, seed, member, particle, first + i, 0 if mode == 'f32' else 1)
+    want = np.array([ol.philox_gauss3(orc, seed, member, particle, first + i, {'f32': 0, 'f64': 1, 'f32p': 2}[mode])
                      for i in range(n)])
     assert np.abs(got - want).max() < tol
     # sanity of the stream itself

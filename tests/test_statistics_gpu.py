@@ -35,7 +35,7 @@ def mean_and_se(sums, R, Ms):
     return mean / Ms, np.sqrt(var / R) / Ms
 
 
-@pytest.mark.parametrize('implicit,gauss', [(False, 'f32'), (False, 'f64'), (True, 'f32')])
+@pytest.mark.parametrize('implicit,gauss', [(False, 'f32p'), (False, 'f32'), (False, 'f64'), (True, 'f32p')])
 def test_relaxation_matches_reference_ensemble_within_3_standard_errors(orc, core, implicit, gauss):
     """Low-barrier particle (sigma = KV/kT = 3.1) relaxing from +z: <Mz>(t) of the Philox ensemble vs
     the reference-noise ensemble, at every sample, within 3 combined standard errors (a handful
