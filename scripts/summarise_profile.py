@@ -1,0 +1,73 @@
+"""Condense an .ncu-rep (read with `ncu -i`) into the counters DESIGN.md / bench.py cite.
+
+    python scripts/summarise_profile.py gpurun_out/heun_single.ncu-rep profiles/r01_heun_single
+
+writes <out>.json (all selected counters, per launch) and prints a markdown table."""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+KEYS = [
+    'gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+    'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor',
+    'sm__warps_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second',
+    'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+    'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+    'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+    'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+    'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
+    'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum',
+    'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed',
+    'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed',
+    'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed',
+    'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+    'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+    'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
+    'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    launches = []
+    for vals in rows[2:]:
+        d = {}
+        for h, u, v in zip(hdr, units, vals):
+            if h == 'Kernel Name':
+                d['kernel'] = v
+            if h in KEYS:
+                try:
+                    d[h] = {'value': float(v.replace(',', '')), 'unit': u}
+                except ValueError:
+                    d[h] = {'value': v, 'unit': u}
+        launches.append(d)
+    json.dump(launches, open(out + '.json', 'w'), indent=1)
+    for d in launches:
+        print('### ' + d.get('kernel', '?')[:150])
+        print('| counter | value | unit |\n|---|---|---|')
+        for k in KEYS:
+            if k in d:
+                v = d[k]['value']
+                print('| `%s` | %s | %s |' % (k, ('%.6g' % v) if isinstance(v, float) else v, d[k]['unit']))
+        print()
+
+
+if __name__ == '__main__':
+    main()
