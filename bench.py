@@ -122,8 +122,8 @@ def load_cpu_reference():
     if os.path.exists(ref):
         lib = C.CDLL(ref)
         lib.ref_ensemble.restype = C.c_double
-        lib.ref_num_threads.restype = C.c_int
-        cores = lib.ref_num_threads()
+        # all host cores this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+        cores = _host_cores()
 
         def run(seeds):
             seeds = np.ascontiguousarray(seeds, dtype=np.int64)
@@ -133,16 +133,17 @@ def load_cpu_reference():
                 P(arr['axis']), C.c_size_t(0), P(arr['m0']), C.c_size_t(0), P(arr['location']),
                 C.c_double(w['Ms']), C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0),
                 C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']),
-                C.c_int(field_code), C.c_double(w['H0']), C.c_double(w['f']), C.c_int(0), P(sums), None)
+                C.c_int(field_code), C.c_double(w['H0']), C.c_double(w['f']), C.c_int(cores), P(sums), None)
             if el < 0:
                 raise RuntimeError('reference ensemble failed')
             return el
         return 'reference', cores, run
     if not os.path.exists(orc):
         subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')])
+    cores = _host_cores()
+    os.environ['OMP_NUM_THREADS'] = str(cores)   # read by libgomp when the oracle is loaded
     lib = C.CDLL(orc)
     lib.orc_ensemble.restype = C.c_double
-    cores = os.cpu_count() or 1
 
     def run(seeds):
         seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
@@ -156,6 +157,13 @@ def load_cpu_reference():
             C.c_double(w['H0']), C.c_double(w['f']), P(sums), None)
         return time.perf_counter() - t0
     return 'port', cores, run
+
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def steps_per_member():
@@ -303,7 +311,7 @@ def ours(args):
         int_ms = t_int / args.steps
     value = world * ps_per_pass / (ms_per_step * 1e-3)
     out = plan.fetch()
-    mean_mz = float(out['sums'][-1, 2] / R / w['Ms'])
+    mean_mz = float(out['sums'][-1, 2] / (R * world) / w['Ms'])   # the plan's sums were all-reduced in place
     del plan
 
     # end to end through the public API with host buffers (H2D + D2H inside the timed region)
@@ -348,6 +356,8 @@ def ours(args):
             traffic = None
     cpu = None
     try:
+        if world > 1:
+            raise RuntimeError('timed at N=1 only (see the N=1 line and --impl reference)')
         kind, cores, run = load_cpu_reference()
         v, n, el = cpu_sample(run, cores, n_steps + 1, 12.0)
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind,

@@ -109,6 +109,9 @@ typedef struct magpy_b200_plan magpy_b200_plan; /* opaque: device-resident ensem
 int magpy_b200_abi_version(void);
 const char* magpy_b200_last_error(void);
 int magpy_b200_device_count(int* count);
+/* Device buffers of finished calls stay cached in the device's stream-ordered memory pool so
+ * that repeated calls do not pay cudaMalloc/cudaFree again; this returns them to the driver. */
+int magpy_b200_release_cached_memory(int device);
 
 /* physical constants exactly as include/constants.hpp:10-12 (replaces
  * core.get_KB / get_mu0 / get_gamma, magpy/core.pyx:29-34) */

@@ -89,6 +89,7 @@ cdef extern from "magpy_b200.h" nogil:
     int magpy_b200_abi_version()
     const char* magpy_b200_last_error()
     int magpy_b200_device_count(int* count)
+    int magpy_b200_release_cached_memory(int device)
     double magpy_b200_get_KB()
     double magpy_b200_get_mu0()
     double magpy_b200_get_gamma()
@@ -159,6 +160,13 @@ cpdef int device_count():
     cdef int n = 0
     magpy_b200_device_count(&n)
     return n
+
+
+def release_cached_memory(int device=0):
+    """Return the device buffers cached from earlier calls to the CUDA driver."""
+    cdef int rc = magpy_b200_release_cached_memory(device)
+    if rc != 0:
+        _raise(rc)
 
 
 cpdef simulate(

@@ -127,18 +127,37 @@ int build_schedule(double dt, double T, size_t S, std::vector<uint64_t>& cum) {
 }
 
 // ---- device buffers -------------------------------------------------------------------
+// Device allocations of a plan come from the device's stream-ordered memory pool with the
+// release threshold lifted, so the second and later calls of a process reuse the blocks of the
+// first instead of paying cudaMalloc/cudaFree (tens of ms per ensemble call) again.
+int enable_pool(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return MAGPY_B200_OK;
+    cudaMemPool_t pool;
+    CU_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CU_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done[device] = true;
+    return MAGPY_B200_OK;
+}
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    cudaError_t alloc(size_t count) {
+    cudaStream_t pool_stream = nullptr;   // non-null: stream-ordered pool allocation
+    cudaError_t alloc(size_t count, cudaStream_t stream = nullptr) {
         release();
         n = count;
+        pool_stream = stream;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc(&p, count * sizeof(T));
+        return stream ? cudaMallocAsync(&p, count * sizeof(T), stream) : cudaMalloc(&p, count * sizeof(T));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pool_stream) cudaFreeAsync(p, pool_stream);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
@@ -185,6 +204,10 @@ struct magpy_b200_plan {
 
     ~magpy_b200_plan() {
         cudaSetDevice(device);
+        d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
+        d_traj.release(); d_sums.release(); d_partial.release(); d_tab.release(); d_dW.release(); d_stage.release();
+        d_seeds.release(); d_target.release(); d_newton.release();
+        if (stream) cudaStreamSynchronize(stream);
         for (auto e : ev_k) cudaEventDestroy(e);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
@@ -404,9 +427,19 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
                          2.0 * pl->max_chunk_steps + (double)N * N * 4);
     if (pl->want_traj) need += 8.0 * 2.0 * (double)pl->S * n * R;
     if (pl->injected) need += 8.0 * 2.0 * (double)pl->total_steps * n * R;
+    if (need > 0.9 * (double)free_b) {   // blocks cached by the pool count as used: give them back and look again
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, pl->device) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    }
     if (need > 0.9 * (double)free_b)
         return fail(MAGPY_B200_ERR_NOMEM, "request needs %.1f GB of device memory, %.1f GB free", need / 1e9, free_b / 1e9);
 
+    rc = enable_pool(pl->device);
+    if (rc) return rc;
     CU_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&pl->ev_begin));
     CU_TRY(cudaEventCreate(&pl->ev_end));
@@ -414,16 +447,16 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     for (auto& e : pl->ev_k) CU_TRY(cudaEventCreate(&e));
 
     // uploads
-    CU_TRY(pl->d_state0.alloc(n * R));
-    CU_TRY(pl->d_state.alloc(n * R));
-    CU_TRY(pl->d_kred.alloc(N));
-    CU_TRY(pl->d_sig.alloc(N));
-    CU_TRY(pl->d_seeds.alloc(R));
-    CU_TRY(pl->d_target.alloc(pl->S));
-    CU_TRY(pl->d_sums.alloc(pl->S * 4));
-    CU_TRY(pl->d_partial.alloc((size_t)4 * pl->max_chunk_samples * pl->grid));
-    CU_TRY(pl->d_newton.alloc(3));
-    if (pl->use_table) CU_TRY(pl->d_tab.alloc(2 * std::max<uint64_t>(1, pl->max_chunk_steps)));
+    CU_TRY(pl->d_state0.alloc(n * R, pl->stream));
+    CU_TRY(pl->d_state.alloc(n * R, pl->stream));
+    CU_TRY(pl->d_kred.alloc(N, pl->stream));
+    CU_TRY(pl->d_sig.alloc(N, pl->stream));
+    CU_TRY(pl->d_seeds.alloc(R, pl->stream));
+    CU_TRY(pl->d_target.alloc(pl->S, pl->stream));
+    CU_TRY(pl->d_sums.alloc(pl->S * 4, pl->stream));
+    CU_TRY(pl->d_partial.alloc((size_t)4 * pl->max_chunk_samples * pl->grid, pl->stream));
+    CU_TRY(pl->d_newton.alloc(3, pl->stream));
+    if (pl->use_table) CU_TRY(pl->d_tab.alloc(2 * std::max<uint64_t>(1, pl->max_chunk_steps), pl->stream));
     CU_TRY(cudaMemcpyAsync(pl->d_kred.p, rd.k_red.data(), N * 8, cudaMemcpyHostToDevice, pl->stream));
     CU_TRY(cudaMemcpyAsync(pl->d_sig.p, rd.sigma.data(), N * 8, cudaMemcpyHostToDevice, pl->stream));
     CU_TRY(cudaMemcpyAsync(pl->d_target.p, pl->target.data(), pl->S * 8, cudaMemcpyHostToDevice, pl->stream));
@@ -444,7 +477,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         size_t stage = n * R;
         if (pl->injected) stage = std::max<size_t>(stage, (size_t)pl->total_steps * n * R);
         if (pl->want_traj) stage = std::max<size_t>(stage, (size_t)pl->S * n * R);
-        CU_TRY(pl->d_stage.alloc(stage));
+        CU_TRY(pl->d_stage.alloc(stage, pl->stream));
     }
     if (a->m0_stride) {
         CU_TRY(cudaMemcpyAsync(pl->d_stage.p, a->magnetisation_direction, n * R * 8, cudaMemcpyHostToDevice, pl->stream));
@@ -462,20 +495,20 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         pl->launches++;
     }
     if (a->axis_stride) {
-        CU_TRY(pl->d_axis.alloc(n * R));
+        CU_TRY(pl->d_axis.alloc(n * R, pl->stream));
         CU_TRY(cudaMemcpyAsync(pl->d_stage.p, a->anisotropy_axis, n * R * 8, cudaMemcpyHostToDevice, pl->stream));
         pl->h2d += n * R * 8;
         rc = launch_transpose(pl, pl->d_stage.p, pl->d_axis.p, 1, R, n, 0, n, 0, R, 1.0);
         if (rc) return rc;
     } else {
-        CU_TRY(pl->d_axis.alloc(n));
+        CU_TRY(pl->d_axis.alloc(n, pl->stream));
         CU_TRY(cudaMemcpyAsync(pl->d_axis.p, a->anisotropy_axis, n * 8, cudaMemcpyHostToDevice, pl->stream));
         pl->h2d += n * 8;
     }
     if (pl->injected) {
         // host [R][steps][n] -> device [steps][n][R]
         const uint64_t T = pl->total_steps;
-        CU_TRY(pl->d_dW.alloc(std::max<uint64_t>(1, T * n * R)));
+        CU_TRY(pl->d_dW.alloc(std::max<uint64_t>(1, T * n * R), pl->stream));
         if (T > 0) {
             if (a->injected_steps == T) {
                 CU_TRY(cudaMemcpyAsync(pl->d_stage.p, a->injected_dw, T * n * R * 8, cudaMemcpyHostToDevice, pl->stream));
@@ -503,12 +536,12 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
                 t[0] = d[0] / mag; t[1] = d[1] / mag; t[2] = d[2] / mag;
                 t[3] = rd.dip_pre * (rd.v_red[jx] / cube);
             }
-        CU_TRY(pl->d_dip.alloc(tab.size()));
+        CU_TRY(pl->d_dip.alloc(tab.size(), pl->stream));
         CU_TRY(cudaMemcpyAsync(pl->d_dip.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, pl->stream));
         CU_TRY(cudaStreamSynchronize(pl->stream));
         pl->h2d += tab.size() * 8;
     }
-    if (pl->want_traj) CU_TRY(pl->d_traj.alloc((size_t)pl->S * n * R));
+    if (pl->want_traj) CU_TRY(pl->d_traj.alloc((size_t)pl->S * n * R, pl->stream));
     CU_TRY(cudaStreamSynchronize(pl->stream));
 
     rc = DISPATCH_NT(set_smem_attr_nt, pl, pl);
@@ -697,6 +730,16 @@ int magpy_b200_schedule(double dt_red, double t_end_red, size_t S, uint64_t* cum
     std::vector<uint64_t> c;
     if (build_schedule(dt_red, t_end_red, S, c)) return fail(MAGPY_B200_ERR_BAD_ARG, "step count exceeds 32 bits");
     std::copy(c.begin(), c.end(), cum);
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_release_cached_memory(int device) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    cudaMemPool_t pool;
+    CU_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemPoolTrimTo(pool, 0));
     return MAGPY_B200_OK;
 }
 

@@ -150,8 +150,11 @@ class EnsembleModel:
             groups = [np.arange(lo, hi)]
 
         S = int(max_samples)
-        traj = np.empty((hi - lo, N, 3, S)) if return_trajectories else None
-        final = np.empty((hi - lo, N, 3))
+        single = len(groups) == 1     # the usual case: one device call, its output arrays are the result
+        traj = final = None
+        if not single:
+            traj = np.empty((hi - lo, N, 3, S)) if return_trajectories else None
+            final = np.empty((hi - lo, N, 3))
         sums = np.zeros((S, 4))
         time = field = None
         stats = []
@@ -169,16 +172,19 @@ class EnsembleModel:
                 params['radius'], params['anisotropy'], member_array('anisotropy_axis'),
                 member_array('magnetisation_direction'), params['location'], params['magnetisation'],
                 params['damping'], params['temperature'], renorm, interactions, implicit_solve, time_step,
-                end_time, S, seeds[idx], params['field_shape'], params['field_amplitude'],
-                params['field_frequency'], implicit_tol, device=device,
+                end_time, S, seeds[lo:hi] if single else seeds[idx], params['field_shape'],
+                params['field_amplitude'], params['field_frequency'], implicit_tol, device=device,
                 stream_offset=int(stream_offset) + first, return_trajectories=return_trajectories,
                 return_sums=True, return_final=True, gauss=gauss)
             if time is None:
                 time, field = out['time'], out['field']
-            if return_trajectories:
-                traj[idx - lo] = out['trajectories']
-            final[idx - lo] = out['final']
-            sums += out['sums']
+            if single:
+                traj, final, sums = out['trajectories'], out['final'], out['sums']
+            else:
+                if return_trajectories:
+                    traj[idx - lo] = out['trajectories']
+                final[idx - lo] = out['final']
+                sums += out['sums']
             stats.append(out['stats'])
         if shard is not None:
             from .sharding import allreduce_sums
