@@ -1,0 +1,146 @@
+// common.cuh — shared declarations of the sm_100a kernels of the ensemble sLLG integrator
+// (kernels: heun_single.cu, imid_single.cu, small.cu, cluster.cu, service.cu; launchers: launch.h).
+//
+// Data layout in HBM (R = members on this device, N = particles per cluster, n = 3N):
+//   state     [n][R]        fp64, member index fastest -> every load/store is coalesced
+//   axis      [n][R] or [n] anisotropy axes (per member or shared)
+//   traj      [S][n][R]     sampled trajectory points (optional)
+//   partial   [Sc][grid][4] per-CTA partial ensemble sums of one chunk of samples
+//   sums      [S][4]        ensemble sums {Mx, My, Mz, Mz^2} (cluster-summed, reduced units)
+//   field_tab [steps][2]    applied field at the two evaluation times of every step
+//   dW        [steps][n][R] injected unit-variance increments (parity mode only)
+//
+// K1 heun_single      one thread per member, N = 1, state in fp64 registers
+// K3 imid_single      same mapping, implicit midpoint with the reference's quasi-Newton
+// K2 heun_cluster     one warp-wide CTA row per particle slot: lanes = 32 members,
+//                     threadIdx.y = particle slot; moments staged in shared memory for
+//                     the all-pairs dipolar sum
+// K4 imid_cluster     same mapping; block-diagonal quasi-Newton, CTA-wide convergence
+// K5 ensemble sums    fused into K1-K4 (warp shuffle -> smem -> per-CTA partial) +
+//                     reduce_partials (fixed-order, deterministic)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "llg_math.cuh"
+#include "rng.cuh"
+
+namespace mb {
+
+enum { NOISE_PHILOX_F32 = 0, NOISE_PHILOX_F64 = 1, NOISE_INJECTED = 2, NOISE_PHILOX_PACKED = 3 };
+
+struct RunParams {
+    uint64_t R;       // members on this device
+    uint32_t N;       // particles per cluster
+    int renorm;       // divide each moment by its 2-norm after every step
+    int interactions; // all-pairs dipolar field
+    double alpha, dt, sqrt_dt;
+    double eps, clampA;  // implicit: tolerance, Ah = sqrt(2*1000*|ln dt|)
+    double h_const;      // applied field when no table is used (reduced units)
+    const double* k_red; // [N]
+    const double* sig;   // [N] thermal field strength sigma_i
+    const double* dip;   // [N][N][4] {sqrt(3) r_hat_ij (3), c_dip * v_j / cube_ij}; diagonal zero
+    const double* axis;  // see layout
+    uint64_t axis_cs, axis_rs;  // component stride, member stride
+    const int64_t* seeds;       // [R]
+    uint64_t stream_offset;
+    double* state;              // [n][R]
+    const uint64_t* target;     // [S] state index stored by sample k
+    uint64_t j0, j1;            // advance the state from index j0 to j1
+    uint32_t k0, k1;            // samples recorded by this launch
+    const double* field_tab;    // [(j1-j0)][2] or nullptr
+    const double* dW;           // injected noise or nullptr
+    uint64_t dW_j0;             // step index of dW row 0
+    double* traj;               // nullptr or [S][n][R]
+    double* partial;            // nullptr or [(k1-k0)][gridDim.x][4]
+    unsigned long long* newton; // [3] total / max / failures
+};
+
+// ---------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// unit-variance draws (implicit kernels clamp them before scaling, lib/integrators.cpp:598-602)
+template <int NOISE>
+__device__ __forceinline__ V3 draw_noise(const RunParams& P, uint32_t k0, uint32_t k1, uint64_t j, uint32_t particle,
+                                         uint32_t member, uint64_t r) {
+    if (NOISE == NOISE_INJECTED) {
+        const uint64_t n = 3ull * P.N;
+        const double* row = P.dW + ((j - P.dW_j0) * n + 3ull * particle) * P.R + r;
+        return V3{row[0], row[P.R], row[2 * P.R]};
+    } else {
+        const Gauss3 g = philox_gauss3<NOISE>(k0, k1, j + 1, particle, member);
+        return V3{g.x, g.y, g.z};
+    }
+}
+
+// Heun kernels: the scaled increment c*w with c = sigma*sqrt(dt).  In the fp32 Gaussian mode the
+// scale is folded into the Box-Muller radius (neg2ln2_c2 = -2 ln2 c^2), so no fp64 multiply is
+// spent on the noise; the injected and fp64 modes multiply in fp64.
+template <int NOISE>
+__device__ __forceinline__ V3 draw_scaled(const RunParams& P, uint32_t k0, uint32_t k1, uint64_t j, uint32_t particle,
+                                          uint32_t member, uint64_t r, double c, float neg2ln2_c2) {
+    if (NOISE == NOISE_PHILOX_F32) {
+        float x, y, z;
+        philox_gauss3_f32(k0, k1, j + 1, particle, member, neg2ln2_c2, x, y, z);
+        return V3{widen_f32(x), widen_f32(y), widen_f32(z)};
+    } else {
+        const V3 w = draw_noise<NOISE>(P, k0, k1, j, particle, member, r);
+        return V3{c * w.x, c * w.y, c * w.z};
+    }
+}
+
+__device__ __forceinline__ float scale_to_bm(double c) { return (float)(-1.3862943611198906 * c * c); }
+
+// CTA-level sum of 4 values per thread over a 1-D block of NW warps into partial[slot][4]
+template <int NW>
+__device__ __forceinline__ void cta_partial_sums(double v0, double v1, double v2, double v3, double* smem /*NW*4*/,
+                                                 double* out4) {
+    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        smem[warp * 4 + 0] = v0; smem[warp * 4 + 1] = v1; smem[warp * 4 + 2] = v2; smem[warp * 4 + 3] = v3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += smem[w * 4 + threadIdx.x];
+        out4[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+constexpr int SINGLE_THREADS = 128;
+constexpr int CL_LANES = 32;
+
+__device__ __forceinline__ void renormalise(V3& m) {
+    const double inv = 1.0 / sqrt(dot(m, m));
+    m.x *= inv; m.y *= inv; m.z *= inv;
+}
+
+struct NewtonCount {
+    unsigned long long total, worst, fails;
+};
+
+__device__ __forceinline__ void newton_flush(const RunParams& P, const NewtonCount& nc, bool live) {
+    unsigned long long t = live ? nc.total : 0ull, w = live ? nc.worst : 0ull, f = live ? nc.fails : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+        f += __shfl_xor_sync(0xffffffffu, f, o);
+        const unsigned long long ow = __shfl_xor_sync(0xffffffffu, w, o);
+        w = ow > w ? ow : w;
+    }
+    if ((threadIdx.x & 31) == 0 && P.newton != nullptr) {
+        atomicAdd(P.newton + 0, t);
+        atomicMax(P.newton + 1, w);
+        atomicAdd(P.newton + 2, f);
+    }
+}
+
+}  // namespace mb

@@ -1,0 +1,148 @@
+#include "common.cuh"
+#include "launch.h"
+
+namespace mb {
+
+// ---------------------------------------------------------------------------------
+// K1: explicit Heun, single particle (lib/integrators.cpp:372-405 over the LLG SDE of
+// lib/llg.cpp:332-348 with the field of lib/simulation.cpp:271-290, N = 1)
+// ---------------------------------------------------------------------------------
+
+// One Heun step of a single macrospin in 40 fp64 instructions (47 with a general easy axis).
+// With u = g + alpha (m x g) the LLG increment is f(m,g) = -m x u, so the predictor
+// x~ = m + f(m,g) and the corrector m' = (m + x~)/2 + f(x~,g~)/2 are accumulated directly in the
+// FMAs of the second cross product (no separate adds, and f1 is never materialised).
+template <bool AXIS_Z>
+__device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V3& edt, const double alpha,
+                                               const double dt, const V3& cw, const double hz0, const double hz1) {
+    // stage 1: g = h(m,t) dt + sigma sqrt(dt) w
+    V3 g;
+    if (AXIS_Z) {  // easy axis = z: h = (k m_z + h_app) z, two fp64 ops instead of seven
+        g = V3{cw.x, cw.y, fma(m.z, edt.z, fma(hz0, dt, cw.z))};
+    } else {
+        const double s = dot(m, e);
+        g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz0, dt, cw.z))};
+    }
+    V3 p = cross(m, g);
+    V3 u{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
+    const V3 mt{fma(-m.y, u.z, fma(m.z, u.y, m.x)), fma(-m.z, u.x, fma(m.x, u.z, m.y)),
+                fma(-m.x, u.y, fma(m.y, u.x, m.z))};
+    // stage 2 at (x~, t+dt), same Wiener increment
+    if (AXIS_Z) {
+        g = V3{cw.x, cw.y, fma(mt.z, edt.z, fma(hz1, dt, cw.z))};
+    } else {
+        const double s = dot(mt, e);
+        g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz1, dt, cw.z))};
+    }
+    p = cross(mt, g);
+    u = V3{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
+    const V3 hm{0.5 * mt.x, 0.5 * mt.y, 0.5 * mt.z};
+    const V3 h{fma(0.5, m.x, hm.x), fma(0.5, m.y, hm.y), fma(0.5, m.z, hm.z)};
+    return V3{fma(-hm.y, u.z, fma(hm.z, u.y, h.x)), fma(-hm.z, u.x, fma(hm.x, u.z, h.y)),
+              fma(-hm.x, u.y, fma(hm.y, u.x, h.z))};
+}
+
+template <int NOISE, bool FIELD_TAB, bool AXIS_Z>
+__global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __grid_constant__ RunParams P) {
+    __shared__ double red[(SINGLE_THREADS / 32) * 4];
+    const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
+    const bool live = r_raw < P.R;
+    const uint64_t r = live ? r_raw : P.R - 1;
+
+    V3 m{P.state[r], P.state[P.R + r], P.state[2 * P.R + r]};
+    V3 e{0.0, 0.0, 1.0};
+    if (!AXIS_Z)
+        e = V3{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
+    const double alpha = P.alpha, dt = P.dt;
+    const double kdt = P.k_red[0] * dt;
+    const V3 edt{e.x * kdt, e.y * kdt, e.z * kdt};
+    const double c = P.sig[0] * P.sqrt_dt;
+    const float bm_scale = scale_to_bm(c);
+    const uint64_t seed = (uint64_t)P.seeds[r];
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const bool renorm = P.renorm != 0;
+
+    // one Heun step from the scaled increment cw; j is the 0-based step index
+    auto advance = [&](const V3& cw, const uint64_t jj) {
+        double hz0 = P.h_const, hz1 = P.h_const;
+        if (FIELD_TAB) {
+            const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (jj - P.j0));
+            hz0 = h.x; hz1 = h.y;
+        }
+        m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
+        if (renorm) renormalise(m);
+    };
+
+    uint64_t j = P.j0;
+    float carry[3] = {0.f, 0.f, 0.f};   // packed mode: increments of the odd step of the current Philox block
+    if (NOISE == NOISE_PHILOX_PACKED && (j & 1)) {
+        float g[6];
+        philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
+        carry[0] = g[3]; carry[1] = g[4]; carry[2] = g[5];
+    }
+    for (uint32_t k = P.k0; k <= P.k1; ++k) {
+        const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+        if (NOISE == NOISE_PHILOX_PACKED) {
+            // invariant: when j is odd, `carry` holds the second half of block j >> 1
+            if ((j & 1) && j < tgt) {
+                advance(V3{widen_f32(carry[0]), widen_f32(carry[1]), widen_f32(carry[2])}, j);
+                ++j;
+            }
+            for (; j + 2 <= tgt; j += 2) {
+                float g[6];
+                philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, j);
+                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, j + 1);
+            }
+            if (j < tgt) {
+                float g[6];
+                philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, j);
+                carry[0] = g[3]; carry[1] = g[4]; carry[2] = g[5];
+                ++j;
+            }
+        } else {
+#pragma unroll 2
+            for (; j < tgt; ++j) advance(draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, c, bm_scale), j);
+        }
+        if (k < P.k1) {
+            if (P.traj != nullptr && live) {
+                double* t = P.traj + (uint64_t)k * 3 * P.R + r;
+                t[0] = m.x; t[P.R] = m.y; t[2 * P.R] = m.z;
+            }
+            if (P.partial != nullptr) {
+                const double z = live ? m.z : 0.0;
+                cta_partial_sums<SINGLE_THREADS / 32>(live ? m.x : 0.0, live ? m.y : 0.0, z, z * z, red,
+                                                      P.partial + ((uint64_t)(k - P.k0) * gridDim.x + blockIdx.x) * 4);
+            }
+        }
+    }
+    if (live) {
+        P.state[r] = m.x; P.state[P.R + r] = m.y; P.state[2 * P.R + r] = m.z;
+    }
+}
+
+template <int NOISE>
+static void launch_hs(bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
+    const dim3 g(grid), b(SINGLE_THREADS);
+    if (tab) {
+        if (axis_z) heun_single_kernel<NOISE, true, true><<<g, b, 0, s>>>(P);
+        else heun_single_kernel<NOISE, true, false><<<g, b, 0, s>>>(P);
+    } else {
+        if (axis_z) heun_single_kernel<NOISE, false, true><<<g, b, 0, s>>>(P);
+        else heun_single_kernel<NOISE, false, false><<<g, b, 0, s>>>(P);
+    }
+}
+
+cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
+    switch (noise) {
+        case NOISE_PHILOX_F32: launch_hs<NOISE_PHILOX_F32>(tab, axis_z, grid, s, P); break;
+        case NOISE_PHILOX_F64: launch_hs<NOISE_PHILOX_F64>(tab, axis_z, grid, s, P); break;
+        case NOISE_INJECTED: launch_hs<NOISE_INJECTED>(tab, axis_z, grid, s, P); break;
+        default: launch_hs<NOISE_PHILOX_PACKED>(tab, axis_z, grid, s, P); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mb

@@ -1,0 +1,133 @@
+#include "common.cuh"
+#include "launch.h"
+
+namespace mb {
+
+// ---------------------------------------------------------------------------------
+// K3: implicit midpoint, single particle (lib/integrators.cpp:576-651 +
+// lib/optimisation.cpp:81-149).  The quasi-Newton iteration is reproduced as the
+// reference runs it: clamped increments, Euler-midpoint initial guess, Jacobian
+// J = I - a'/2 - (B'.w)/2 with no dt on a', tolerance eps*||guess|| fixed before the
+// loop, stop on ||delta||_2 <= tol or after 1000 iterations.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const double kred, const double alpha,
+                                               const double sr, const double dt, const double clampA,
+                                               const double sqrt_dt, const double eps, const V3& w,
+                                               const double hz_t, const double hz_mid, const double hj[9],
+                                               NewtonCount& nc) {
+    const V3 wm{fmax(-clampA, fmin(clampA, w.x)) * sqrt_dt, fmax(-clampA, fmin(clampA, w.y)) * sqrt_dt,
+                fmax(-clampA, fmin(clampA, w.z)) * sqrt_dt};
+    const V3 sw{sr * wm.x, sr * wm.y, sr * wm.z};
+    // Euler half step as the initial guess of (x0 + x1)/2
+    V3 X;
+    {
+        const double s = kred * dot(x0, e);
+        const V3 g{fma(s * e.x, dt, sw.x), fma(s * e.y, dt, sw.y), fma(fma(s, e.z, hz_t), dt, sw.z)};
+        const V3 f = llg_f(x0, g, alpha);
+        X = V3{(f.x + x0.x) / 2, (f.y + x0.y) / 2, (f.z + x0.z) / 2};
+    }
+    const double tol = eps * sqrt(dot(X, X));
+    double err = 2 * tol;
+    int iter = 1000;
+    unsigned long long done = 0;
+    bool singular = false;
+    while ((err > tol) && (iter-- > 0)) {
+        const double s = kred * dot(X, e);
+        const V3 h{s * e.x, s * e.y, fma(s, e.z, hz_mid)};
+        const V3 g{fma(h.x, dt, sw.x), fma(h.y, dt, sw.y), fma(h.z, dt, sw.z)};
+        const V3 f = llg_f(X, g, alpha);
+        double b[3] = {-(X.x - x0.x - 0.5 * f.x), -(X.y - x0.y - 0.5 * f.y), -(X.z - x0.z - 0.5 * f.z)};
+        double A[9], D[9], d[3];
+        drift_jacobian(A, X, alpha, h, hj);
+        diffusion_jacobian_dot(D, X, sr, alpha, wm);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * A[i] - 0.5 * D[i];
+        ++done;
+        if (!solve3(A, b, d)) {
+            // dgesv info > 0: the reference returns with x_root = -F (lib/optimisation.cpp:136-137)
+            X = V3{b[0], b[1], b[2]};
+            singular = true;
+            break;
+        }
+        err = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        X.x += d[0]; X.y += d[1]; X.z += d[2];
+    }
+    nc.total += done;
+    nc.worst = done > nc.worst ? done : nc.worst;
+    nc.fails += (singular || iter == -1) ? 1ull : 0ull;
+    return V3{2 * X.x - x0.x, 2 * X.y - x0.y, 2 * X.z - x0.z};
+}
+
+template <int NOISE, bool FIELD_TAB>
+__global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __grid_constant__ RunParams P) {
+    __shared__ double red[(SINGLE_THREADS / 32) * 4];
+    const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
+    const bool live = r_raw < P.R;
+    const uint64_t r = live ? r_raw : P.R - 1;
+
+    V3 m{P.state[r], P.state[P.R + r], P.state[2 * P.R + r]};
+    const V3 e{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
+    const double kred = P.k_red[0], sr = P.sig[0];
+    double hj[9];
+    {
+        const double ev[3] = {e.x, e.y, e.z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jx = 0; jx < 3; ++jx) hj[3 * i + jx] = kred * ev[i] * ev[jx];  // lib/field.cpp:159-174
+    }
+    const uint64_t seed = (uint64_t)P.seeds[r];
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const bool renorm = P.renorm != 0;
+    NewtonCount nc{0ull, 0ull, 0ull};
+
+    uint64_t j = P.j0;
+    for (uint32_t k = P.k0; k <= P.k1; ++k) {
+        const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+        for (; j < tgt; ++j) {
+            const V3 w = draw_noise<NOISE>(P, key0, key1, j, 0u, member, r);
+            double hz0 = P.h_const, hz1 = P.h_const;
+            if (FIELD_TAB) {
+                const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - P.j0));
+                hz0 = h.x; hz1 = h.y;
+            }
+            m = imid_single_step(m, e, kred, P.alpha, sr, P.dt, P.clampA, P.sqrt_dt, P.eps, w, hz0, hz1, hj, nc);
+            if (renorm) renormalise(m);
+        }
+        if (k < P.k1) {
+            if (P.traj != nullptr && live) {
+                double* t = P.traj + (uint64_t)k * 3 * P.R + r;
+                t[0] = m.x; t[P.R] = m.y; t[2 * P.R] = m.z;
+            }
+            if (P.partial != nullptr) {
+                const double z = live ? m.z : 0.0;
+                cta_partial_sums<SINGLE_THREADS / 32>(live ? m.x : 0.0, live ? m.y : 0.0, z, z * z, red,
+                                                      P.partial + ((uint64_t)(k - P.k0) * gridDim.x + blockIdx.x) * 4);
+            }
+        }
+    }
+    if (live) {
+        P.state[r] = m.x; P.state[P.R + r] = m.y; P.state[2 * P.R + r] = m.z;
+    }
+    newton_flush(P, nc, live);
+}
+
+template <int NOISE>
+static void launch_is(bool tab, unsigned grid, cudaStream_t s, const RunParams& P) {
+    const dim3 g(grid), b(SINGLE_THREADS);
+    if (tab) imid_single_kernel<NOISE, true><<<g, b, 0, s>>>(P);
+    else imid_single_kernel<NOISE, false><<<g, b, 0, s>>>(P);
+}
+
+cudaError_t launch_imid_single(int noise, bool tab, unsigned grid, cudaStream_t s, const RunParams& P) {
+    switch (noise) {
+        case NOISE_PHILOX_F32: launch_is<NOISE_PHILOX_F32>(tab, grid, s, P); break;
+        case NOISE_PHILOX_F64: launch_is<NOISE_PHILOX_F64>(tab, grid, s, P); break;
+        case NOISE_INJECTED: launch_is<NOISE_INJECTED>(tab, grid, s, P); break;
+        default: launch_is<NOISE_PHILOX_PACKED>(tab, grid, s, P); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mb

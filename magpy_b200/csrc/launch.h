@@ -1,0 +1,34 @@
+// launch.h — host-callable launchers of the sm_100a kernels (one translation unit per kernel family,
+// compiled in parallel; the host side in magpy_b200.cu sees only these functions).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mb {
+
+struct RunParams;
+
+// noise: NOISE_PHILOX_F32 | NOISE_PHILOX_F64 | NOISE_INJECTED | NOISE_PHILOX_PACKED; tab: applied field from field_tab
+cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P);
+cudaError_t launch_imid_single(int noise, bool tab, unsigned grid, cudaStream_t s, const RunParams& P);
+cudaError_t launch_heun_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
+cudaError_t launch_imid_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
+// layout: 0 = pair table in global memory, 1 = table in shared memory, 2 = table in shared memory + one moment buffer
+cudaError_t launch_heun_cluster(int noise, bool tab, int np, int layout, dim3 grid, dim3 block, size_t smem,
+                                cudaStream_t s, const RunParams& P);
+cudaError_t launch_imid_cluster(int noise, bool tab, int np, dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                const RunParams& P);
+
+cudaError_t launch_field_table(double* tab, uint64_t j0, uint64_t n_steps, double dt, double second_offset, int shape,
+                               double h0, double f_red, cudaStream_t s);
+cudaError_t launch_reduce_partials(const double* partial, double* sums, uint32_t k0, uint32_t n_samples, uint32_t n_cta,
+                                   cudaStream_t s);
+cudaError_t launch_transpose(const double* in, double* out, uint64_t rows, uint64_t cols, uint64_t batches, uint64_t in_bs,
+                             uint64_t in_rs, uint64_t out_bs, uint64_t out_rs, double scale, cudaStream_t s);
+cudaError_t launch_broadcast_rows(const double* in, double* out, uint64_t n, uint64_t R, cudaStream_t s);
+cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t s);
+cudaError_t launch_philox_words(const uint32_t ctr[4], const uint32_t key[2], uint32_t* out);
+cudaError_t launch_gaussians(int noise, uint64_t seed, uint32_t member, uint32_t particle, uint64_t first_step,
+                             uint64_t n_steps, double* out);
+
+}  // namespace mb

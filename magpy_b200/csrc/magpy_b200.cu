@@ -16,7 +16,8 @@
 #include <vector>
 
 #include "../../include/magpy_b200.h"
-#include "kernels.cuh"
+#include "common.cuh"
+#include "launch.h"
 
 namespace {
 
@@ -188,8 +189,10 @@ struct magpy_b200_plan {
     dim3 block{1, 1, 1};
     size_t smem = 0;
     int np = 1;
+    int layout = 0;        // Heun cluster kernel: see cluster.cu
     bool use_table = false;
     bool axis_z = false;   // N = 1 and one shared easy axis exactly along +z: specialised Heun kernel
+    bool small = false;    // 2 <= N <= 4: one thread per cluster, all moments in registers
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
@@ -217,84 +220,48 @@ struct magpy_b200_plan {
 
 namespace {
 
-int launch_transpose(magpy_b200_plan* pl, const double* in, double* out, uint64_t batches, uint64_t rows,
-                     uint64_t cols, uint64_t in_bs, uint64_t in_rs, uint64_t out_bs, uint64_t out_rs, double scale);
+#define LAUNCH_TRY(expr)                                                                             \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(MAGPY_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        pl->launches++;                                                                              \
+    } while (0)
+
+int plan_noise(const magpy_b200_plan* pl) {
+    if (pl->injected) return mb::NOISE_INJECTED;
+    if (pl->gauss_mode == MAGPY_B200_GAUSS_F64) return mb::NOISE_PHILOX_F64;
+    if (pl->gauss_mode == MAGPY_B200_GAUSS_F32) return mb::NOISE_PHILOX_F32;
+    return mb::NOISE_PHILOX_PACKED;
+}
 
 // ---- kernel dispatch ------------------------------------------------------------------
-template <int NOISE, bool TAB>
-int launch_integrate_nt(magpy_b200_plan* pl, const mb::RunParams& P) {
-    const dim3 g(pl->grid), b = pl->block;
+int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
+    const int noise = plan_noise(pl);
+    const bool tab = pl->use_table;
     if (pl->N == 1) {
-        if (pl->implicit) mb::imid_single_kernel<NOISE, TAB><<<g, b, 0, pl->stream>>>(P);
-        else if (pl->axis_z) mb::heun_single_kernel<NOISE, TAB, true><<<g, b, 0, pl->stream>>>(P);
-        else mb::heun_single_kernel<NOISE, TAB, false><<<g, b, 0, pl->stream>>>(P);
+        if (pl->implicit) LAUNCH_TRY(mb::launch_imid_single(noise, tab, pl->grid, pl->stream, P));
+        else LAUNCH_TRY(mb::launch_heun_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
+    } else if (pl->small) {
+        if (pl->implicit) LAUNCH_TRY(mb::launch_imid_small(noise, tab, pl->N, pl->grid, pl->stream, P));
+        else LAUNCH_TRY(mb::launch_heun_small(noise, tab, pl->N, pl->grid, pl->stream, P));
     } else if (pl->implicit) {
-        switch (pl->np) {
-            case 1: mb::imid_cluster_kernel<NOISE, TAB, 1><<<g, b, pl->smem, pl->stream>>>(P); break;
-            case 2: mb::imid_cluster_kernel<NOISE, TAB, 2><<<g, b, pl->smem, pl->stream>>>(P); break;
-            default: mb::imid_cluster_kernel<NOISE, TAB, 4><<<g, b, pl->smem, pl->stream>>>(P); break;
-        }
+        LAUNCH_TRY(mb::launch_imid_cluster(noise, tab, pl->np, dim3(pl->grid), pl->block, pl->smem, pl->stream, P));
     } else {
-        switch (pl->np) {
-            case 1: mb::heun_cluster_kernel<NOISE, TAB, 1><<<g, b, pl->smem, pl->stream>>>(P); break;
-            case 2: mb::heun_cluster_kernel<NOISE, TAB, 2><<<g, b, pl->smem, pl->stream>>>(P); break;
-            case 4: mb::heun_cluster_kernel<NOISE, TAB, 4><<<g, b, pl->smem, pl->stream>>>(P); break;
-            default: mb::heun_cluster_kernel<NOISE, TAB, 8><<<g, b, pl->smem, pl->stream>>>(P); break;
-        }
-    }
-    CU_TRY(cudaGetLastError());
-    pl->launches++;
-    return MAGPY_B200_OK;
-}
-
-template <int NOISE, bool TAB>
-int set_smem_attr_nt(magpy_b200_plan* pl) {
-    if (pl->N == 1 || pl->smem <= 48 * 1024) return MAGPY_B200_OK;
-    const int bytes = (int)pl->smem;
-    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if (pl->implicit) {
-        switch (pl->np) {
-            case 1: CU_TRY(cudaFuncSetAttribute(mb::imid_cluster_kernel<NOISE, TAB, 1>, attr, bytes)); break;
-            case 2: CU_TRY(cudaFuncSetAttribute(mb::imid_cluster_kernel<NOISE, TAB, 2>, attr, bytes)); break;
-            default: CU_TRY(cudaFuncSetAttribute(mb::imid_cluster_kernel<NOISE, TAB, 4>, attr, bytes)); break;
-        }
-    } else {
-        switch (pl->np) {
-            case 1: CU_TRY(cudaFuncSetAttribute(mb::heun_cluster_kernel<NOISE, TAB, 1>, attr, bytes)); break;
-            case 2: CU_TRY(cudaFuncSetAttribute(mb::heun_cluster_kernel<NOISE, TAB, 2>, attr, bytes)); break;
-            case 4: CU_TRY(cudaFuncSetAttribute(mb::heun_cluster_kernel<NOISE, TAB, 4>, attr, bytes)); break;
-            default: CU_TRY(cudaFuncSetAttribute(mb::heun_cluster_kernel<NOISE, TAB, 8>, attr, bytes)); break;
-        }
+        LAUNCH_TRY(mb::launch_heun_cluster(noise, tab, pl->np, pl->layout, dim3(pl->grid), pl->block, pl->smem, pl->stream, P));
     }
     return MAGPY_B200_OK;
 }
-
-#define DISPATCH_NT(fn, pl, ...)                                                                      \
-    ((pl)->injected                                                                                   \
-         ? ((pl)->use_table ? fn<mb::NOISE_INJECTED, true>(__VA_ARGS__) : fn<mb::NOISE_INJECTED, false>(__VA_ARGS__)) \
-     : (pl)->gauss_mode == MAGPY_B200_GAUSS_F32_PACKED                                                \
-         ? ((pl)->use_table ? fn<mb::NOISE_PHILOX_PACKED, true>(__VA_ARGS__)                          \
-                            : fn<mb::NOISE_PHILOX_PACKED, false>(__VA_ARGS__))                        \
-     : (pl)->gauss_mode == MAGPY_B200_GAUSS_F64                                                       \
-         ? ((pl)->use_table ? fn<mb::NOISE_PHILOX_F64, true>(__VA_ARGS__)                             \
-                            : fn<mb::NOISE_PHILOX_F64, false>(__VA_ARGS__))                           \
-         : ((pl)->use_table ? fn<mb::NOISE_PHILOX_F32, true>(__VA_ARGS__)                             \
-                            : fn<mb::NOISE_PHILOX_F32, false>(__VA_ARGS__)))
 
 int launch_transpose(magpy_b200_plan* pl, const double* in, double* out, uint64_t batches, uint64_t rows,
                      uint64_t cols, uint64_t in_bs, uint64_t in_rs, uint64_t out_bs, uint64_t out_rs,
                      double scale) {
     // batches go through gridDim.z in slices of 65535
-    const dim3 b(32, 8);
+    if ((rows + 31) / 32 > 65535) return fail(MAGPY_B200_ERR_BAD_ARG, "transpose rows too large");
     for (uint64_t b0 = 0; b0 < batches; b0 += 65535) {
         const uint64_t nb = std::min<uint64_t>(65535, batches - b0);
-        const uint64_t gy = (rows + 31) / 32;
-        if (gy > 65535) return fail(MAGPY_B200_ERR_BAD_ARG, "transpose rows too large");
-        const dim3 g((unsigned)((cols + 31) / 32), (unsigned)gy, (unsigned)nb);
-        mb::transpose_kernel<<<g, b, 0, pl->stream>>>(in + b0 * in_bs, out + b0 * out_bs, rows, cols, in_bs, in_rs,
-                                                     out_bs, out_rs, scale);
-        CU_TRY(cudaGetLastError());
-        pl->launches++;
+        LAUNCH_TRY(mb::launch_transpose(in + b0 * in_bs, out + b0 * out_bs, rows, cols, nb, in_bs, in_rs, out_bs, out_rs,
+                                        scale, pl->stream));
     }
     return MAGPY_B200_OK;
 }
@@ -372,16 +339,38 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         pl->grid = (unsigned)((R + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
         pl->smem = 0;
         pl->np = 1;
+    } else if (N <= 4) {   // one thread per cluster (small.cu)
+        pl->small = true;
+        pl->block = dim3(mb::SINGLE_THREADS);
+        pl->grid = (unsigned)((R + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
+        pl->smem = 0;
+        pl->np = 1;
     } else {
         const uint32_t max_slots = pl->implicit ? 8 : 16;
-        int np = 1;
+        int np = pl->implicit ? 1 : 2;   // Heun: >= 2 own particles per thread reuse every shared-memory moment read
         while ((N + np - 1) / np > max_slots) np *= 2;
         pl->np = np;
         const uint32_t slots = (N + np - 1) / np;
         pl->block = dim3(mb::CL_LANES, slots);
         pl->grid = (unsigned)((R + mb::CL_LANES - 1) / mb::CL_LANES);
-        pl->smem = ((size_t)2 * N * 3 + (size_t)3 * slots) * mb::CL_LANES * sizeof(double);
-        if (pl->smem > 227 * 1024) return fail(MAGPY_B200_ERR_BAD_ARG, "cluster too large for shared memory");
+        const size_t moments = (size_t)N * 3 * mb::CL_LANES * sizeof(double);
+        const size_t red = (size_t)3 * slots * mb::CL_LANES * sizeof(double);
+        const size_t table = (size_t)N * N * 4 * sizeof(double);
+        const size_t cap = 227 * 1024;
+        pl->layout = 0;
+        pl->smem = 2 * moments + red;
+        if (pl->implicit) pl->smem += table;   // N <= 32: the implicit kernel always stages the table
+        if (!pl->implicit) {   // Heun: stage the pair table in shared memory when it fits (cluster.cu)
+            if (2 * moments + red + table <= cap) { pl->layout = 1; pl->smem = 2 * moments + red + table; }
+            else if (np == 4 && moments + red + table <= cap) { pl->layout = 2; pl->smem = moments + red + table; }
+            else if (np == 4) { np = pl->np = 8; }   // only (8, global table) is instantiated beyond that
+            if (pl->layout == 0) {
+                const uint32_t sl = (N + pl->np - 1) / pl->np;
+                pl->block = dim3(mb::CL_LANES, sl);
+                pl->smem = 2 * moments + (size_t)3 * sl * mb::CL_LANES * sizeof(double);
+            }
+        }
+        if (pl->smem > cap) return fail(MAGPY_B200_ERR_BAD_ARG, "cluster too large for shared memory");
     }
     pl->use_table = a->field_shape != MAGPY_B200_FIELD_CONSTANT;
     pl->axis_z = N == 1 && a->axis_stride == 0 && a->anisotropy_axis[0] == 0.0 && a->anisotropy_axis[1] == 0.0 &&
@@ -488,11 +477,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         // shared initial state: upload the n values once and replicate them on the device
         CU_TRY(cudaMemcpyAsync(pl->d_stage.p, a->magnetisation_direction, n * 8, cudaMemcpyHostToDevice, pl->stream));
         pl->h2d += n * 8;
-        const uint64_t total = n * R;
-        mb::broadcast_rows_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, pl->stream>>>(
-            pl->d_stage.p, pl->d_state0.p, n, R);
-        CU_TRY(cudaGetLastError());
-        pl->launches++;
+        LAUNCH_TRY(mb::launch_broadcast_rows(pl->d_stage.p, pl->d_state0.p, n, R, pl->stream));
     }
     if (a->axis_stride) {
         CU_TRY(pl->d_axis.alloc(n * R, pl->stream));
@@ -533,7 +518,9 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
                 const double mag = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
                 const double cube = std::pow(mag / lscale, 3);
                 double* t = &tab[((size_t)i * N + jx) * 4];
-                t[0] = d[0] / mag; t[1] = d[1] / mag; t[2] = d[2] / mag;
+                // sqrt(3) r_hat: (m.t) t = 3 (m.r_hat) r_hat (lib/field.cpp:221-224)
+                const double s3 = 1.7320508075688772;
+                t[0] = s3 * (d[0] / mag); t[1] = s3 * (d[1] / mag); t[2] = s3 * (d[2] / mag);
                 t[3] = rd.dip_pre * (rd.v_red[jx] / cube);
             }
         CU_TRY(pl->d_dip.alloc(tab.size(), pl->stream));
@@ -543,9 +530,6 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     }
     if (pl->want_traj) CU_TRY(pl->d_traj.alloc((size_t)pl->S * n * R, pl->stream));
     CU_TRY(cudaStreamSynchronize(pl->stream));
-
-    rc = DISPATCH_NT(set_smem_attr_nt, pl, pl);
-    if (rc) return rc;
 
     mb::RunParams& P = pl->base;
     P.R = R;
@@ -591,19 +575,15 @@ int plan_run(magpy_b200_plan* pl) {
         P.j0 = c.j0; P.j1 = c.j1; P.k0 = c.k0; P.k1 = c.k1;
         const uint64_t ns = c.j1 - c.j0;
         if (pl->use_table && ns > 0) {
-            mb::field_table_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, pl->stream>>>(
-                pl->d_tab.p, c.j0, ns, pl->red.dt, second, pl->field_shape, pl->red.h0, pl->red.f);
-            CU_TRY(cudaGetLastError());
-            pl->launches++;
+            LAUNCH_TRY(mb::launch_field_table(pl->d_tab.p, c.j0, ns, pl->red.dt, second, pl->field_shape, pl->red.h0,
+                                              pl->red.f, pl->stream));
         }
         CU_TRY(cudaEventRecord(pl->ev_k[2 * ci], pl->stream));
-        int rc = DISPATCH_NT(launch_integrate_nt, pl, pl, P);
+        int rc = launch_integrate(pl, P);
         if (rc) return rc;
         CU_TRY(cudaEventRecord(pl->ev_k[2 * ci + 1], pl->stream));
         if (c.k1 > c.k0) {
-            mb::reduce_partials_kernel<<<c.k1 - c.k0, 256, 0, pl->stream>>>(pl->d_partial.p, pl->d_sums.p, c.k0, pl->grid);
-            CU_TRY(cudaGetLastError());
-            pl->launches++;
+            LAUNCH_TRY(mb::launch_reduce_partials(pl->d_partial.p, pl->d_sums.p, c.k0, c.k1 - c.k0, pl->grid, pl->stream));
         }
         ++ci;
     }
@@ -855,8 +835,7 @@ int magpy_b200_philox_words(int device, const uint32_t ctr[4], const uint32_t ke
     if (rc) return rc;
     DevBuf<uint32_t> d;
     CU_TRY(d.alloc(4));
-    mb::philox_words_kernel<<<1, 1>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], d.p);
-    CU_TRY(cudaGetLastError());
+    CU_TRY(mb::launch_philox_words(ctr, key, d.p));
     CU_TRY(cudaMemcpy(out, d.p, 16, cudaMemcpyDeviceToHost));
     return MAGPY_B200_OK;
 }
@@ -868,14 +847,9 @@ int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t par
     if (!out || n_steps == 0) return fail(MAGPY_B200_ERR_BAD_ARG, "bad arguments");
     DevBuf<double> d;
     CU_TRY(d.alloc(3 * n_steps));
-    const unsigned g = (unsigned)((n_steps + 255) / 256);
-    if (gauss_mode == MAGPY_B200_GAUSS_F32_PACKED)
-        mb::gaussians_kernel<mb::NOISE_PHILOX_PACKED><<<g, 256>>>((uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p);
-    else if (gauss_mode == MAGPY_B200_GAUSS_F64)
-        mb::gaussians_kernel<1><<<g, 256>>>((uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p);
-    else
-        mb::gaussians_kernel<0><<<g, 256>>>((uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p);
-    CU_TRY(cudaGetLastError());
+    const int noise = gauss_mode == MAGPY_B200_GAUSS_F64 ? mb::NOISE_PHILOX_F64
+                      : gauss_mode == MAGPY_B200_GAUSS_F32 ? mb::NOISE_PHILOX_F32 : mb::NOISE_PHILOX_PACKED;
+    CU_TRY(mb::launch_gaussians(noise, (uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p));
     CU_TRY(cudaMemcpy(out, d.p, 3 * n_steps * 8, cudaMemcpyDeviceToHost));
     return MAGPY_B200_OK;
 }
@@ -899,7 +873,7 @@ int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz) {
         CU_TRY(d.alloc((size_t)blocks * threads));
         for (int rep = 0; rep < 4; ++rep) {
             CU_TRY(cudaEventRecord(e0));
-            mb::fp64_peak_kernel<<<blocks, threads>>>(d.p, iters, 0.999999, 1e-7);
+            CU_TRY(mb::launch_fp64_peak(d.p, blocks, threads, iters, nullptr));
             CU_TRY(cudaEventRecord(e1));
             CU_TRY(cudaEventSynchronize(e1));
             float ms = 0.f;

@@ -1,0 +1,157 @@
+#include "common.cuh"
+#include "launch.h"
+
+namespace mb {
+
+// ---------------------------------------------------------------------------------
+// small service kernels
+// ---------------------------------------------------------------------------------
+// applied field at the two evaluation times of each step (lib/field.cpp:37-54,
+// lib/simulation.cpp:350-355): step index s = j+1, t = s*dt; Heun evaluates at t and t+dt
+// (lib/integrators.cpp:386,394), implicit midpoint at t and t+dt/2 (:605,621).
+__global__ void field_table_kernel(double* tab, uint64_t j0, uint64_t n_steps, double dt, double second_offset,
+                                   int shape, double h0, double f_red) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_steps) return;
+    const double t = (double)(unsigned int)(j0 + i + 1) * dt;  // `step` is unsigned int in the reference
+    const double t2 = t + second_offset;
+    double a, b;
+    if (shape == 0) {
+        a = h0 * sin(2 * 3.14159265358979323846 * f_red * t);
+        b = h0 * sin(2 * 3.14159265358979323846 * f_red * t2);
+    } else {
+        a = h0 * (((int)(t * f_red * 2)) % 2 ? -1 : 1);
+        b = h0 * (((int)(t2 * f_red * 2)) % 2 ? -1 : 1);
+    }
+    tab[2 * i] = a;
+    tab[2 * i + 1] = b;
+}
+
+// sums[k0+kk][q] = sum over CTAs of partial[kk][cta][q], fixed order -> deterministic
+__global__ void reduce_partials_kernel(const double* partial, double* sums, uint32_t k0, uint32_t n_cta) {
+    __shared__ double sh[256 * 4];
+    const uint32_t kk = blockIdx.x;
+    const double* p = partial + (uint64_t)kk * n_cta * 4;
+    double a[4] = {0, 0, 0, 0};
+    for (uint32_t c = threadIdx.x; c < n_cta; c += blockDim.x) {
+        const double4 v = *reinterpret_cast<const double4*>(p + (uint64_t)c * 4);
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sh[threadIdx.x * 4 + q] = a[q];
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sh[threadIdx.x * 4 + q] += sh[(threadIdx.x + s) * 4 + q];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) sums[(uint64_t)(k0 + kk) * 4 + threadIdx.x] = sh[threadIdx.x];
+}
+
+// batched strided 2-D transpose: element (b,row,col) at in[b*in_bs + row*in_rs + col] goes to
+// out[b*out_bs + col*out_rs + row], times `scale`.  Both sides are walked along their
+// contiguous index, so loads and stores are coalesced.
+__global__ void transpose_kernel(const double* in, double* out, uint64_t rows, uint64_t cols, uint64_t in_bs,
+                                 uint64_t in_rs, uint64_t out_bs, uint64_t out_rs, double scale) {
+    __shared__ double tile[32][33];
+    const double* src = in + (uint64_t)blockIdx.z * in_bs;
+    double* dst = out + (uint64_t)blockIdx.z * out_bs;
+    const uint64_t c0 = (uint64_t)blockIdx.x * 32, r0 = (uint64_t)blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const uint64_t rr = r0 + i, cc = c0 + threadIdx.x;
+        if (rr < rows && cc < cols) tile[i][threadIdx.x] = src[rr * in_rs + cc];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const uint64_t cc = c0 + i, rr = r0 + threadIdx.x;
+        if (rr < rows && cc < cols) dst[cc * out_rs + rr] = tile[threadIdx.x][i] * scale;
+    }
+}
+
+// out[q][r] = in[q] for q < n, r < R (shared initial state replicated over the members)
+__global__ void broadcast_rows_kernel(const double* in, double* out, uint64_t n, uint64_t R) {
+    const uint64_t total = n * R;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = in[i / R];
+}
+
+__global__ void scale_kernel(double* a, uint64_t n, double s) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] *= s;
+}
+
+// dependent-free DFMA chains: the measured FP64 roofline denominator
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+__global__ void philox_words_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                    uint32_t* out) {
+    philox4x32_10(c0, c1, c2, c3, k0, k1);
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <int GAUSS_MODE>
+__global__ void gaussians_kernel(uint64_t seed, uint32_t member, uint32_t particle, uint64_t first_step,
+                                 uint64_t n_steps, double* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_steps) return;
+    const Gauss3 g = philox_gauss3<GAUSS_MODE>((uint32_t)seed, (uint32_t)(seed >> 32), first_step + i, particle, member);
+    out[3 * i] = g.x; out[3 * i + 1] = g.y; out[3 * i + 2] = g.z;
+}
+
+cudaError_t launch_field_table(double* tab, uint64_t j0, uint64_t n_steps, double dt, double second_offset, int shape,
+                               double h0, double f_red, cudaStream_t s) {
+    field_table_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, s>>>(tab, j0, n_steps, dt, second_offset, shape, h0, f_red);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_partials(const double* partial, double* sums, uint32_t k0, uint32_t n_samples, uint32_t n_cta,
+                                   cudaStream_t s) {
+    reduce_partials_kernel<<<n_samples, 256, 0, s>>>(partial, sums, k0, n_cta);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transpose(const double* in, double* out, uint64_t rows, uint64_t cols, uint64_t batches, uint64_t in_bs,
+                             uint64_t in_rs, uint64_t out_bs, uint64_t out_rs, double scale, cudaStream_t s) {
+    const dim3 g((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batches), b(32, 8);
+    transpose_kernel<<<g, b, 0, s>>>(in, out, rows, cols, in_bs, in_rs, out_bs, out_rs, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_broadcast_rows(const double* in, double* out, uint64_t n, uint64_t R, cudaStream_t s) {
+    const uint64_t total = n * R;
+    const unsigned g = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    broadcast_rows_kernel<<<g, 256, 0, s>>>(in, out, n, R);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t s) {
+    fp64_peak_kernel<<<blocks, threads, 0, s>>>(out, iters, 0.999999, 1e-7);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_philox_words(const uint32_t ctr[4], const uint32_t key[2], uint32_t* out) {
+    philox_words_kernel<<<1, 1>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gaussians(int noise, uint64_t seed, uint32_t member, uint32_t particle, uint64_t first_step,
+                             uint64_t n_steps, double* out) {
+    const unsigned g = (unsigned)((n_steps + 255) / 256);
+    if (noise == NOISE_PHILOX_PACKED) gaussians_kernel<NOISE_PHILOX_PACKED><<<g, 256>>>(seed, member, particle, first_step, n_steps, out);
+    else if (noise == NOISE_PHILOX_F64) gaussians_kernel<NOISE_PHILOX_F64><<<g, 256>>>(seed, member, particle, first_step, n_steps, out);
+    else gaussians_kernel<NOISE_PHILOX_F32><<<g, 256>>>(seed, member, particle, first_step, n_steps, out);
+    return cudaGetLastError();
+}
+
+}  // namespace mb
