@@ -292,7 +292,9 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
 
     Own own[NP];
     V3 m[NP];
-    double hj[NP][9];
+    V3 qu[NP];
+    const V3 e0{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
+    const double k0 = P.k_red[0];
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         const uint32_t p = slot + q * PS;
@@ -308,18 +310,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
             double* d = sm_m + c0 * CL_LANES + lane;
             d[0] = m[q].x; d[CL_LANES] = m[q].y; d[2 * CL_LANES] = m[q].z;
         }
-        // The 9 doubles the reference reads as this particle's field Jacobian: flat offsets
-        // 3p..3p+8 of the dense row-major (3N)^2 anisotropy Jacobian (lib/llg.cpp:387,
-        // lib/field.cpp:159-174) — the true block only for N = 1.
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const uint32_t idx = 3u * own[q].p + i, row = idx / (3u * N), col = idx % (3u * N);
-            double v = 0.0;
-            if (row / 3 == col / 3 && row < 3u * N)
-                v = P.k_red[row / 3] * P.axis[(uint64_t)row * P.axis_cs + r * P.axis_rs] *
-                    P.axis[(uint64_t)col * P.axis_cs + r * P.axis_rs];
-            hj[q][i] = v;
-        }
+        qu[q] = quirk_u(N, own[q].p, e0, k0);   // rank-one field-Jacobian block the reference reads (llg_math.cuh)
     }
     __syncthreads();
 
@@ -374,11 +365,8 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
                     const V3 f = llg_f(X[q], g, alpha);
                     double b[3] = {-(X[q].x - m[q].x - 0.5 * f.x), -(X[q].y - m[q].y - 0.5 * f.y),
                                    -(X[q].z - m[q].z - 0.5 * f.z)};
-                    double A[9], D[9], d[3];
-                    drift_jacobian(A, X[q], alpha, h, hj[q]);
-                    diffusion_jacobian_dot(D, X[q], own[q].sr, alpha, wm[q]);
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) A[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * A[i] - 0.5 * D[i];
+                    double A[9], d[3];
+                    newton_matrix(A, X[q], alpha, h, sw[q], qu[q], e0);
                     if (!solve3(A, b, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                     dl[q] = V3{d[0], d[1], d[2]};
                     part += d[0] * d[0] + d[1] * d[1] + d[2] * d[2];

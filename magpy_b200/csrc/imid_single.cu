@@ -13,11 +13,11 @@ namespace mb {
 __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const double kred, const double alpha,
                                                const double sr, const double dt, const double clampA,
                                                const double sqrt_dt, const double eps, const V3& w,
-                                               const double hz_t, const double hz_mid, const double hj[9],
-                                               NewtonCount& nc) {
+                                               const double hz_t, const double hz_mid, NewtonCount& nc) {
     const V3 wm{fmax(-clampA, fmin(clampA, w.x)) * sqrt_dt, fmax(-clampA, fmin(clampA, w.y)) * sqrt_dt,
                 fmax(-clampA, fmin(clampA, w.z)) * sqrt_dt};
     const V3 sw{sr * wm.x, sr * wm.y, sr * wm.z};
+    const V3 ke{kred * e.x, kred * e.y, kred * e.z};   // field-Jacobian block k e e^T = ke e^T
     // Euler half step as the initial guess of (x0 + x1)/2
     V3 X;
     {
@@ -26,22 +26,20 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
         const V3 f = llg_f(x0, g, alpha);
         X = V3{(f.x + x0.x) / 2, (f.y + x0.y) / 2, (f.z + x0.z) / 2};
     }
-    const double tol = eps * sqrt(dot(X, X));
-    double err = 2 * tol;
+    // err > tol is tested on the squares (no square root inside the loop): tol^2 = eps^2 |X|^2
+    const double tol2 = (eps * eps) * dot(X, X);
+    double err2 = 4 * tol2;
     int iter = 1000;
     unsigned long long done = 0;
     bool singular = false;
-    while ((err > tol) && (iter-- > 0)) {
+    while ((err2 > tol2) && (iter-- > 0)) {
         const double s = kred * dot(X, e);
         const V3 h{s * e.x, s * e.y, fma(s, e.z, hz_mid)};
         const V3 g{fma(h.x, dt, sw.x), fma(h.y, dt, sw.y), fma(h.z, dt, sw.z)};
         const V3 f = llg_f(X, g, alpha);
         double b[3] = {-(X.x - x0.x - 0.5 * f.x), -(X.y - x0.y - 0.5 * f.y), -(X.z - x0.z - 0.5 * f.z)};
-        double A[9], D[9], d[3];
-        drift_jacobian(A, X, alpha, h, hj);
-        diffusion_jacobian_dot(D, X, sr, alpha, wm);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) A[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * A[i] - 0.5 * D[i];
+        double A[9], d[3];
+        newton_matrix(A, X, alpha, h, sw, ke, e);
         ++done;
         if (!solve3(A, b, d)) {
             // dgesv info > 0: the reference returns with x_root = -F (lib/optimisation.cpp:136-137)
@@ -49,7 +47,7 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
             singular = true;
             break;
         }
-        err = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        err2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
         X.x += d[0]; X.y += d[1]; X.z += d[2];
     }
     nc.total += done;
@@ -68,14 +66,6 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
     V3 m{P.state[r], P.state[P.R + r], P.state[2 * P.R + r]};
     const V3 e{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
     const double kred = P.k_red[0], sr = P.sig[0];
-    double hj[9];
-    {
-        const double ev[3] = {e.x, e.y, e.z};
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int jx = 0; jx < 3; ++jx) hj[3 * i + jx] = kred * ev[i] * ev[jx];  // lib/field.cpp:159-174
-    }
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t member = (uint32_t)(r + P.stream_offset);
@@ -92,7 +82,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
                 const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - P.j0));
                 hz0 = h.x; hz1 = h.y;
             }
-            m = imid_single_step(m, e, kred, P.alpha, sr, P.dt, P.clampA, P.sqrt_dt, P.eps, w, hz0, hz1, hj, nc);
+            m = imid_single_step(m, e, kred, P.alpha, sr, P.dt, P.clampA, P.sqrt_dt, P.eps, w, hz0, hz1, nc);
             if (renorm) renormalise(m);
         }
         if (k < P.k1) {

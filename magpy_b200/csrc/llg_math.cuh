@@ -7,7 +7,7 @@
 // so one Heun stage is a single f(m, h dt + sigma sqrt(dt) w).  The implicit scheme
 // additionally needs the reference's Jacobian tables *as tabulated* (lib/llg.cpp:68-81,
 // 118-158), including the two entries of the diffusion Jacobian that are not the
-// analytic derivative — the quasi-Newton iterate sequence depends on them.
+// analytic derivative — the quasi-Newton iterate sequence depends on them (newton_matrix).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -29,52 +29,13 @@ __device__ __forceinline__ V3 llg_f(const V3& m, const V3& g, const double alpha
     return V3{-fma(alpha, q.x, p.x), -fma(alpha, q.y, p.y), -fma(alpha, q.z, p.z)};
 }
 
-// d a_i / d m_j as the reference tabulates it (lib/llg.cpp:68-81); hj = 3x3 row-major
-// "field Jacobian" block handed in by the caller (which reproduces the block the
-// reference actually reads, lib/llg.cpp:387).
-__device__ __forceinline__ void drift_jacobian(double J[9], const V3& m, const double a, const V3& h,
-                                               const double hj[9]) {
-    const double m0 = m.x, m1 = m.y, m2 = m.z, h0 = h.x, h1 = h.y, h2 = h.z;
-    const double s12 = m1 * m1 + m2 * m2, s02 = m0 * m0 + m2 * m2, s01 = m0 * m0 + m1 * m1;
-    J[0] = m2 * hj[3] - m1 * hj[6] + a * (-m1 * h1 - m2 * h2 + s12 * hj[0] - m0 * (m1 * hj[3] + m2 * hj[6]));
-    J[1] = -h2 + m2 * hj[4] - m1 * hj[7] + a * (2 * m1 * h0 + s12 * hj[1] - m0 * (h1 + m1 * hj[4] + m2 * hj[7]));
-    J[2] = h1 + m2 * hj[5] - m1 * hj[8] + a * (2 * m2 * h0 + s12 * hj[2] - m0 * (h2 + m1 * hj[5] + m2 * hj[8]));
-    J[3] = h2 - m2 * hj[0] + m0 * hj[6] + a * (2 * m0 * h1 + s02 * hj[3] - m1 * (h0 + m0 * hj[0] + m2 * hj[6]));
-    J[4] = -m2 * hj[1] + m0 * hj[7] + a * (-m0 * h0 - m2 * h2 + s02 * hj[4] - m1 * (m0 * hj[1] + m2 * hj[7]));
-    J[5] = -h0 - m2 * hj[2] + m0 * hj[8] + a * (2 * m2 * h1 + s02 * hj[5] - m1 * (h2 + m0 * hj[2] + m2 * hj[8]));
-    J[6] = -h1 + m1 * hj[0] - m0 * hj[3] + a * (2 * m0 * h2 + s01 * hj[6] - m2 * (h0 + m0 * hj[0] + m1 * hj[3]));
-    J[7] = h0 + m1 * hj[1] - m0 * hj[4] + a * (2 * m1 * h2 + s01 * hj[7] - m2 * (h1 + m0 * hj[1] + m1 * hj[4]));
-    J[8] = m1 * hj[2] - m0 * hj[5] + a * (-m0 * h0 - m1 * h1 + s01 * hj[8] - m2 * (m0 * hj[2] + m1 * hj[5]));
-}
-
-// Contribution of the diffusion Jacobian to the quasi-Newton matrix:
-//   D[3i+j] = sum_k T[i][k][j] * w_k   with T = lib/llg.cpp:118-158 (index [x][y][z] = 9x+3y+z).
-// Entries T[0][1][1] and T[2][2][1] use m2 where the analytic derivative has m0 / m1;
-// they are kept as the reference has them.
-__device__ __forceinline__ void diffusion_jacobian_dot(double D[9], const V3& m, const double sr,
-                                                       const double alpha, const V3& w) {
-    const double as = alpha * sr;
-    const double m0 = m.x, m1 = m.y, m2 = m.z, w0 = w.x, w1 = w.y, w2 = w.z;
-    // i = 0 : T[0][k][j]
-    D[0] = /*k0*/ 0.0 + /*k1*/ (-as * m1) * w1 + /*k2*/ (-as * m2) * w2;
-    D[1] = (2 * as * m1) * w0 + (-as * m2) * w1 + (-sr) * w2;
-    D[2] = (2 * as * m2) * w0 + (sr)*w1 + (-as * m0) * w2;
-    // i = 1 : T[1][k][j]
-    D[3] = (-as * m1) * w0 + (2 * as * m0) * w1 + (sr)*w2;
-    D[4] = (-as * m0) * w0 + 0.0 + (-as * m2) * w2;
-    D[5] = (-sr) * w0 + (2 * as * m2) * w1 + (-as * m1) * w2;
-    // i = 2 : T[2][k][j]
-    D[6] = (-as * m2) * w0 + (-sr) * w1 + (2 * as * m0) * w2;
-    D[7] = (sr)*w0 + (-as * m2) * w1 + (2 * as * m2) * w2;
-    D[8] = (-as * m0) * w0 + (-as * m1) * w1 + 0.0;
-}
-
 // Solve the 3x3 system A d = b in registers: Gaussian elimination with row partial
 // pivoting (first largest |entry| in the column), i.e. what dgesv does to the 3x3
 // diagonal block the reference's block-diagonal J reduces to (lib/optimisation.cpp:134).
 // Returns false when a pivot is exactly zero (dgesv info > 0).
 __device__ __forceinline__ bool solve3(double A[9], double b[3], double d[3]) {
     // column 0
+    double inv0;
     {
         const double a0 = fabs(A[0]), a1 = fabs(A[3]), a2 = fabs(A[6]);
         int p = 0;
@@ -95,12 +56,13 @@ __device__ __forceinline__ bool solve3(double A[9], double b[3], double d[3]) {
             t = b[0]; b[0] = b[2]; b[2] = t;
         }
         if (A[0] == 0.0) return false;
-        const double inv = 1.0 / A[0];
-        const double l1 = A[3] * inv, l2 = A[6] * inv;
+        inv0 = 1.0 / A[0];
+        const double l1 = A[3] * inv0, l2 = A[6] * inv0;
         A[4] -= l1 * A[1]; A[5] -= l1 * A[2]; b[1] -= l1 * b[0];
         A[7] -= l2 * A[1]; A[8] -= l2 * A[2]; b[2] -= l2 * b[0];
     }
     // column 1
+    double inv1;
     {
         if (fabs(A[7]) > fabs(A[4])) {
             double t;
@@ -109,15 +71,67 @@ __device__ __forceinline__ bool solve3(double A[9], double b[3], double d[3]) {
             t = b[1]; b[1] = b[2]; b[2] = t;
         }
         if (A[4] == 0.0) return false;
-        const double l = A[7] * (1.0 / A[4]);
+        inv1 = 1.0 / A[4];
+        const double l = A[7] * inv1;
         A[8] -= l * A[5];
         b[2] -= l * b[1];
     }
     if (A[8] == 0.0) return false;
-    d[2] = b[2] / A[8];
-    d[1] = (b[1] - A[5] * d[2]) / A[4];
-    d[0] = (b[0] - A[1] * d[1] - A[2] * d[2]) / A[0];
+    // back substitution with the three pivot reciprocals (one fp64 division each)
+    d[2] = b[2] * (1.0 / A[8]);
+    d[1] = (b[1] - A[5] * d[2]) * inv1;
+    d[0] = (b[0] - A[1] * d[1] - A[2] * d[2]) * inv0;
     return true;
+}
+
+// Quasi-Newton matrix of one particle:   A = I - (a' + B'.w)/2   with the reference's tables
+// (lib/llg.cpp:68-81, 118-158, lib/integrators.cpp:630-636), built from their structure instead of entry
+// by entry.  Both tables are the same linear map of a "field" v,
+//     L(v) = [v]x - alpha ((m.v) I + m v^T - 2 v m^T),
+// a' = L(h) + G HJ with G = da/dh and HJ the 3x3 "field Jacobian" block the reference reads, and
+// B'.w = L(sigma w) + C, where C holds the two entries in which the reference's diffusion table differs
+// from the analytic derivative (T[0][1][1] and T[2][2][1] use m2).  HJ is always rank one, HJ = u eb^T
+// (see quirk_u), and G u = f(m,u), so
+//     A = I + L(-(h + sigma w)/2) - f(m,u) eb^T / 2 - C/2          59 fp64 operations instead of 164.
+// N = 1: u = k e, eb = e (the true anisotropy block k e e^T).
+__device__ __forceinline__ void newton_matrix(double A[9], const V3& m, const double alpha, const V3& h,
+                                              const V3& sw /* sigma * w */, const V3& u, const V3& e) {
+    const V3 vh{-0.5 * (h.x + sw.x), -0.5 * (h.y + sw.y), -0.5 * (h.z + sw.z)};
+    const V3 am{alpha * m.x, alpha * m.y, alpha * m.z};
+    const V3 tv{2.0 * vh.x, 2.0 * vh.y, 2.0 * vh.z};
+    const double base = fma(-alpha, dot(m, vh), 1.0);
+    const V3 f = llg_f(m, u, alpha);
+    const V3 fh{-0.5 * f.x, -0.5 * f.y, -0.5 * f.z};
+    A[0] = fma(fh.x, e.x, fma(am.x, vh.x, base));
+    A[4] = fma(fh.y, e.y, fma(am.y, vh.y, base));
+    A[8] = fma(fh.z, e.z, fma(am.z, vh.z, base));
+    A[1] = fma(fh.x, e.y, fma(-am.x, vh.y, fma(tv.x, am.y, -vh.z)));
+    A[2] = fma(fh.x, e.z, fma(-am.x, vh.z, fma(tv.x, am.z, vh.y)));
+    A[3] = fma(fh.y, e.x, fma(-am.y, vh.x, fma(tv.y, am.x, vh.z)));
+    A[5] = fma(fh.y, e.z, fma(-am.y, vh.z, fma(tv.y, am.z, -vh.x)));
+    A[6] = fma(fh.z, e.x, fma(-am.z, vh.x, fma(tv.z, am.x, -vh.y)));
+    A[7] = fma(fh.z, e.y, fma(-am.z, vh.y, fma(tv.z, am.y, vh.x)));
+    // the reference's two non-analytic diffusion-table entries
+    A[1] = fma(0.5 * (m.z - m.x), alpha * sw.y, A[1]);
+    A[7] = fma(-(m.z - m.y), alpha * sw.z, A[7]);
+}
+
+// The 3x3 block the reference hands to llg::drift_jacobian for particle p of an N-particle cluster is
+// the 9 doubles at flat offsets 3p..3p+8 of the dense row-major (3N)^2 anisotropy Jacobian
+// (lib/llg.cpp:387 reads hj+(3*n); lib/field.cpp:159-174 fills the diagonal blocks with k e e^T) — the
+// true block only for N = 1.  Its row i is the 3-column segment number g = p + i of the dense matrix:
+// dense row r = g / N, block column g % N, non-zero only on the block diagonal (g % N == r / 3), where
+// it equals k_b e_b[r % 3] e_b^T with b = r / 3.  For N >= 2, g <= N + 1 means r <= 1 and b = 0: every
+// block is u e_0^T with u_i = k_0 e_0[r] when g is 0 or N, else 0.  (N = 1: g = i, u = k_0 e_0.)
+__device__ __forceinline__ V3 quirk_u(const unsigned N, const unsigned p, const V3& e0, const double k0) {
+    double u[3];
+#pragma unroll
+    for (unsigned i = 0; i < 3; ++i) {
+        const unsigned g = p + i, r = g / N;
+        const double comp = (r % 3 == 0) ? e0.x : (r % 3 == 1) ? e0.y : e0.z;
+        u[i] = (g % N == r / 3) ? k0 * comp : 0.0;
+    }
+    return V3{u[0], u[1], u[2]};
 }
 
 }  // namespace mb

@@ -206,27 +206,6 @@ __global__ void __launch_bounds__(SMALL_THREADS) heun_small_kernel(const __grid_
 // ---------------------------------------------------------------------------------
 // implicit midpoint
 // ---------------------------------------------------------------------------------
-// The 9 doubles the reference reads as particle p's field Jacobian: flat offsets 3p..3p+8 of the
-// dense row-major (3N)^2 anisotropy Jacobian (lib/llg.cpp:387 reads hj+(3*n); lib/field.cpp:159-174
-// fills the diagonal blocks with k e e^T) — the true block only for N = 1.  With N and p known at
-// compile time the index arithmetic folds and only the non-zero products remain.
-template <int N>
-__device__ __forceinline__ void quirk_field_jacobian(double (&hj)[9], const int p, const V3 (&e)[N],
-                                                     const double (&kred)[N]) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        const int idx = 3 * p + i, row = idx / (3 * N), col = idx % (3 * N);
-        double v = 0.0;
-        if (row / 3 == col / 3) {
-            const V3& er = e[row / 3];
-            const double a = (row % 3 == 0) ? er.x : (row % 3 == 1) ? er.y : er.z;
-            const double b = (col % 3 == 0) ? er.x : (col % 3 == 1) ? er.y : er.z;
-            v = kred[row / 3] * a * b;
-        }
-        hj[i] = v;
-    }
-}
-
 template <int NOISE, bool FIELD_TAB, int N>
 __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SMALL_THREADS / 32) * 4];
@@ -299,12 +278,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
                     double bb[3] = {-(X[i].x - m[i].x - 0.5 * f.x), -(X[i].y - m[i].y - 0.5 * f.y),
                                     -(X[i].z - m[i].z - 0.5 * f.z)};
                     b[i] = V3{bb[0], bb[1], bb[2]};
-                    double A[9], D[9], d[3], hj[9];
-                    quirk_field_jacobian<N>(hj, i, e, kred);
-                    drift_jacobian(A, X[i], alpha, h[i], hj);
-                    diffusion_jacobian_dot(D, X[i], sr[i], alpha, wm[i]);
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) A[q] = ((q % 4 == 0) ? 1.0 : 0.0) - 0.5 * A[q] - 0.5 * D[q];
+                    double A[9], d[3];
+                    newton_matrix(A, X[i], alpha, h[i], sw[i], quirk_u(N, i, e[0], kred[0]), e[0]);
                     if (!solve3(A, bb, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                     dl[i] = V3{d[0], d[1], d[2]};
                     e2 += d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
