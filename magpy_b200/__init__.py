@@ -9,9 +9,10 @@ hand-written sm_100a CUDA kernels behind a C ABI (include/magpy_b200.h).  Import
 from . import core
 from . import results
 from . import sharding
+from . import geometry
 from .core import simulate, simulate_ensemble, get_KB, get_mu0, get_gamma
 from .model import Model, EnsembleModel
 from .results import Results, EnsembleResults
 
-__all__ = ['core', 'results', 'sharding', 'simulate', 'simulate_ensemble', 'get_KB', 'get_mu0', 'get_gamma',
+__all__ = ['core', 'results', 'sharding', 'geometry', 'simulate', 'simulate_ensemble', 'get_KB', 'get_mu0', 'get_gamma',
            'Model', 'EnsembleModel', 'Results', 'EnsembleResults']

@@ -668,6 +668,23 @@ long orc_simulate(int N, const double* radius, const double* anisotropy, const d
     return fails;
 }
 
+/* ------------------------------------------------------------------------- *
+ * Discrete-orientation (thermal activation) comparator, lib/dom.cpp:33-59:   *
+ * the 2x2 Neel-Brown transition matrix of a uniaxial particle in a reduced   *
+ * field h (|h| < 1) along its axis.  Valid for sigma (1-h)^2 >> 1 only       *
+ * (lib/dom.cpp:20-22).  Pinned by test/tests.cpp:609-620.                    *
+ * ------------------------------------------------------------------------- */
+void orc_dom_transition_matrix(double* W, double k, double v, double T, double h, double ms, double alpha) {
+    const double sigma = k * v / ORC_KB / T;
+    const double taun = v * ms * (1 + alpha * alpha) / 2.0 / ORC_GYROMAG / alpha / ORC_KB / T;
+    const double e1 = sigma * (1 - h) * (1 - h), e2 = sigma * (1 + h) * (1 + h);
+    const double prefactor = taun * sqrt(M_PI) / pow(sigma, 1.5) / (1 - h * h);
+    const double rate1 = 1.0 / prefactor * (1 - h) * exp(-e1);
+    const double rate2 = 1.0 / prefactor * (1 + h) * exp(-e2);
+    W[0] = -rate2; W[1] = rate1;
+    W[2] = rate2;  W[3] = -rate1;
+}
+
 /* Number of N(0,1) draws orc_simulate consumes: 3N * (steps executed). */
 uint64_t orc_steps_executed(double dt_red, double T_red, size_t S) {
     uint64_t* cum = (uint64_t*)malloc(sizeof(uint64_t) * S);

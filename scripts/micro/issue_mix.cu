@@ -6,7 +6,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-enum { K_FFMA = 0, K_IMAD = 1, K_LOP = 2, K_IMADW = 3, K_MUFU = 4, K_F2F = 5, K_I2F = 6, K_HILO = 7, K_HI = 8, K_PRMT = 9 };
+enum { K_FFMA = 0, K_IMAD = 1, K_LOP = 2, K_IMADW = 3, K_MUFU = 4, K_F2F = 5, K_I2F = 6, K_HILO = 7, K_HI = 8, K_PRMT = 9, K_HILO_SPLIT = 10 };
 
 template <int NDF, int MIX, int KIND>
 __global__ void mix_kernel(double* out, float* fout, int iters, double a, double b, float fa, unsigned ia) {
@@ -46,6 +46,11 @@ __global__ void mix_kernel(double* out, float* fout, int iters, double a, double
                         z[q] += 3u;
                     } else if (KIND == K_HILO) {
                         z[q] = __umulhi(z[q], ia) ^ (z[q] * ia);                  // IMAD.HI.U32 + IMAD + LOP3
+                    } else if (KIND == K_HILO_SPLIT) {
+                        // high word against the immediate, low word against the same value held in a register:
+                        // ptxas cannot prove the multipliers equal, so it cannot fuse the two into one IMAD.WIDE
+                        const unsigned hi = __umulhi(z[q], 2654435761u);
+                        z[q] = hi ^ (z[q] * ia);
                     } else if (KIND == K_HI) {
                         z[q] = __umulhi(z[q], ia);                                // IMAD.HI.U32
                     } else if (KIND == K_PRMT) {
@@ -110,6 +115,9 @@ int main() {
         run<1, 1, K_HILO>("DFMA + 1 (IMAD.HI,IMAD,LOP3)", w);
         run<1, 2, K_HILO>("DFMA + 2 (IMAD.HI,IMAD,LOP3)", w);
         run<0, 1, K_HILO>("1 (IMAD.HI,IMAD,LOP3)", w);
+        run<1, 1, K_HILO_SPLIT>("DFMA + 1 (IMAD.HI imm,IMAD reg,LOP3)", w);
+        run<1, 2, K_HILO_SPLIT>("DFMA + 2 (IMAD.HI imm,IMAD reg,LOP3)", w);
+        run<0, 1, K_HILO_SPLIT>("1 (IMAD.HI imm,IMAD reg,LOP3)", w);
         run<1, 1, K_HI>("DFMA + 1 IMAD.HI", w);
         run<1, 2, K_HI>("DFMA + 2 IMAD.HI", w);
         run<0, 2, K_HI>("2 IMAD.HI", w);

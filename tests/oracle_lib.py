@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, 'oracle', 'libsllg_oracle.so')
 REF_SO = os.path.join(ROOT, 'oracle', '_ref', 'libmagpy_ref.so')
 
+KB = 1.38064852e-23   # include/constants.hpp:10
 FIELD = {'sine': 0, 'square': 1, 'constant': 2}
 
 
@@ -161,3 +162,11 @@ def oracle_ensemble(lib, c, seeds, axis=None, m0=None):
                      C.c_double(c.t_end), C.c_size_t(c.S), C.c_int(FIELD[c.field_shape]), C.c_double(c.H0),
                      C.c_double(c.f), _p(sums), _p(final))
     return sums, final
+
+
+def dom_transition_matrix(lib, k, v, T, h, ms, alpha):
+    """2x2 Neel-Brown transition matrix (lib/dom.cpp:33-59), row-major [W00, W01, W10, W11]."""
+    W = (C.c_double * 4)()
+    lib.orc_dom_transition_matrix(W, C.c_double(k), C.c_double(v), C.c_double(T), C.c_double(h), C.c_double(ms),
+                                  C.c_double(alpha))
+    return list(W)

@@ -192,6 +192,28 @@ def test_ensemble_model_seeds_and_grouping(monkeypatch):
         mp.EnsembleModel(3, base, no_such_parameter=[1, 2, 3])
 
 
+def test_geometry_helpers():
+    from magpy_b200 import geometry as g
+    # the two examples of the reference's docstring (magpy/geometry/coordinates.py:80-87)
+    assert np.allclose(g.chain_coordinates(3, 2.5, direction=[1, 0, 0]), [[0, 0, 0], [2.5, 0, 0], [5, 0, 0]])
+    assert np.allclose(g.chain_coordinates(2, 3.0, direction=[3, 4, 0]), [[0, 0, 0], [1.8, 2.4, 0]])
+    # same two draws and formula as magpy/initial_conditions.py:4-16 from the global legacy generator
+    np.random.seed(11)
+    theta, u = 2.0 * np.pi * np.random.rand(), np.random.rand()
+    phi = np.arccos(1 - 2.0 * u)
+    np.random.seed(11)
+    ax = g.uniform_random_axes(5)
+    assert np.allclose(ax[0], [np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta), np.cos(phi)])
+    assert np.allclose(np.linalg.norm(ax, axis=1), 1.0)
+    # BASELINE config 4 shape: 64 non-overlapping particles, reproducible from a seed
+    pts = g.random_cluster_coordinates(64, 2.4e-8, rng=5)
+    d = np.linalg.norm(pts[:, None] - pts[None], axis=-1) + np.eye(64)
+    assert pts.shape == (64, 3) and d.min() >= 2.4e-8 and np.allclose(pts.mean(axis=0), 0, atol=1e-20)
+    assert np.array_equal(pts, g.random_cluster_coordinates(64, 2.4e-8, rng=5))
+    with pytest.raises(ValueError):
+        g.random_cluster_coordinates(8, 1e-8, packing=0.6)
+
+
 def test_shard_bounds():
     from magpy_b200.sharding import shard_bounds
     for R, G in ((10, 3), (8, 8), (1000000, 8), (5, 8), (7, 2)):

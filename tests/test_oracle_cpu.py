@@ -288,6 +288,12 @@ def test_oracle_matches_compiled_reference_live(orc):
     assert np.array_equal(a, b)
 
 
+def test_dom_transition_matrix_known_answer(orc):
+    k = KAT['dom_transition_matrix']
+    W = ol.dom_transition_matrix(orc, k['k'], k['v'], k['T'], k['h'], k['ms'], k['alpha'])
+    assert np.allclose(W, k['expect'], rtol=4e-15, atol=0)   # EXPECT_DOUBLE_EQ = 4 ulp
+
+
 def test_philox_random123_known_answers(orc):
     kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),

@@ -210,3 +210,32 @@ def test_weak_convergence_order(orc, core, implicit):
     assert len(sig) >= 3, (weak, se)
     order = np.polyfit(np.array(sig), np.log2(weak[sig]), 1)[0]
     assert 0.6 < order < 2.4, (order, weak, se)
+
+
+def test_neel_relaxation_time_against_master_equation(orc, core):
+    """Single 6 nm particle (sigma = KV/kT = 8.7) relaxing from +z over 1 microsecond: the decay rate of the
+    ensemble <Mz>(t) against the reference's discrete-orientation master equation (lib/dom.cpp:33-59), whose
+    two-state solution at zero field is exp(-2 W t).  The master equation uses the Neel-Brown high-barrier
+    asymptote (valid for sigma >> 1, lib/dom.cpp:20-22; its leading correction is the factor 1 - 1/sigma,
+    i.e. 11 % here), so the bar is 20 % on the rate, not a number of standard errors."""
+    # renorm=True as in the reference's long Heun runs: without it |m| random-walks away from 1 over 5e5 steps
+    # (lib/simulation.cpp:379-387), in the reference exactly as here
+    c = ol.make_case(N=1, radius=6e-9, anisotropy=4e4, Ms=4e5, alpha=0.1, T=300.0, dt=2e-12, t_end=1e-6, S=201,
+                     axis=[[0, 0, 1.0]], m0=[[0, 0, 1.0]], renorm=True)
+    R = 32768
+    out = gpu(core, c, np.arange(R) + 777, return_trajectories=False)
+    mz, se = mean_and_se(out['sums'], R, c.Ms)
+    V = 4.0 / 3.0 * np.pi * 6e-9 ** 3
+    W = ol.dom_transition_matrix(orc, 4e4, V, 300.0, 0.0, 4e5, 0.1)
+    rate_dom = 2 * W[1]                                    # p0 - p1 decays with W01 + W10
+    t = out['time']
+    sel = (t > 0.1e-6) & (mz > 10 * se)                    # past the intra-well transient, above the noise floor
+    slope, intercept = np.polyfit(t[sel], np.log(mz[sel]), 1)
+    rate_sllg = -slope
+    assert sel.sum() > 50
+    assert 0.8 < rate_sllg / rate_dom < 1.2, (rate_sllg, rate_dom)
+    # the corrected asymptote (1 - 1/sigma) is closer still
+    sigma = 4e4 * V / (ol.KB * 300.0)
+    assert abs(rate_sllg / (rate_dom * (1 - 1 / sigma)) - 1) < 0.1, (rate_sllg, rate_dom, sigma)
+    # the fast intra-well relaxation leaves <Mz> near the well average <cos theta> = 1 - 1/(2 sigma) + ...
+    assert abs(np.exp(intercept) - (1 - 1 / (2 * sigma))) < 0.03
