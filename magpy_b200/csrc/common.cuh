@@ -118,8 +118,10 @@ __device__ __forceinline__ void cta_partial_sums(double v0, double v1, double v2
 constexpr int SINGLE_THREADS = 128;
 constexpr int CL_LANES = 32;
 
+// m / |m| (lib/simulation.cpp:379-387).  rsqrt() is MUFU.RSQ64H plus Newton steps, branch free and
+// accurate to 1 ulp; the literal 1/sqrt() costs a DSQRT and a DDIV with their slow-path calls.
 __device__ __forceinline__ void renormalise(V3& m) {
-    const double inv = 1.0 / sqrt(dot(m, m));
+    const double inv = rsqrt(dot(m, m));
     m.x *= inv; m.y *= inv; m.z *= inv;
 }
 

@@ -42,7 +42,7 @@ __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V
               fma(-hm.x, u.y, fma(hm.y, u.x, h.z))};
 }
 
-template <int NOISE, bool FIELD_TAB, bool AXIS_Z>
+template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool RENORM>
 __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
@@ -61,20 +61,22 @@ __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __gri
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t member = (uint32_t)(r + P.stream_offset);
-    const bool renorm = P.renorm != 0;
 
-    // one Heun step from the scaled increment cw; j is the 0-based step index
-    auto advance = [&](const V3& cw, const uint64_t jj) {
+    // one Heun step from the scaled increment cw; `tp` = this step's entry of the field table
+    auto advance = [&](const V3& cw, const double2* tp) {
         double hz0 = P.h_const, hz1 = P.h_const;
         if (FIELD_TAB) {
-            const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (jj - P.j0));
+            const double2 h = __ldg(tp);
             hz0 = h.x; hz1 = h.y;
         }
         m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
-        if (renorm) renormalise(m);
+        if (RENORM) renormalise(m);
     };
 
+    // All loop state of the inner loops is 32-bit (a launch covers at most 2^32 steps and the Philox
+    // counter word is the low 32 bits of the step / step-pair index anyway) plus one table pointer.
     uint64_t j = P.j0;
+    const double2* tab = reinterpret_cast<const double2*>(P.field_tab);
     float carry[3] = {0.f, 0.f, 0.f};   // packed mode: increments of the odd step of the current Philox block
     if (NOISE == NOISE_PHILOX_PACKED && (j & 1)) {
         float g[6];
@@ -86,25 +88,30 @@ __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __gri
         if (NOISE == NOISE_PHILOX_PACKED) {
             // invariant: when j is odd, `carry` holds the second half of block j >> 1
             if ((j & 1) && j < tgt) {
-                advance(V3{widen_f32(carry[0]), widen_f32(carry[1]), widen_f32(carry[2])}, j);
+                advance(V3{widen_f32(carry[0]), widen_f32(carry[1]), widen_f32(carry[2])}, tab + (j - P.j0));
                 ++j;
             }
-            for (; j + 2 <= tgt; j += 2) {
+            const uint32_t pairs = (uint32_t)((tgt - j) >> 1);
+            uint32_t blk = (uint32_t)(j >> 1);
+            const double2* tp = tab + (j - P.j0);
+            for (uint32_t i = pairs; i != 0; --i, ++blk, tp += 2) {
                 float g[6];
-                philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
-                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, j);
-                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, j + 1);
+                philox_gauss6_f32(key0, key1, blk, 0u, member, bm_scale, g);
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tp);
+                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tp + 1);
             }
+            j += 2ull * pairs;
             if (j < tgt) {
                 float g[6];
                 philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
-                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, j);
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tab + (j - P.j0));
                 carry[0] = g[3]; carry[1] = g[4]; carry[2] = g[5];
                 ++j;
             }
         } else {
+            const double2* tp = tab + (j - P.j0);
 #pragma unroll 2
-            for (; j < tgt; ++j) advance(draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, c, bm_scale), j);
+            for (; j < tgt; ++j, ++tp) advance(draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, c, bm_scale), tp);
         }
         if (k < P.k1) {
             if (P.traj != nullptr && live) {
@@ -123,15 +130,22 @@ __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __gri
     }
 }
 
+template <int NOISE, bool TAB, bool AXIS_Z>
+static void launch_hs2(bool renorm, dim3 g, dim3 b, cudaStream_t s, const RunParams& P) {
+    if (renorm) heun_single_kernel<NOISE, TAB, AXIS_Z, true><<<g, b, 0, s>>>(P);
+    else heun_single_kernel<NOISE, TAB, AXIS_Z, false><<<g, b, 0, s>>>(P);
+}
+
 template <int NOISE>
 static void launch_hs(bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
     const dim3 g(grid), b(SINGLE_THREADS);
+    const bool renorm = P.renorm != 0;
     if (tab) {
-        if (axis_z) heun_single_kernel<NOISE, true, true><<<g, b, 0, s>>>(P);
-        else heun_single_kernel<NOISE, true, false><<<g, b, 0, s>>>(P);
+        if (axis_z) launch_hs2<NOISE, true, true>(renorm, g, b, s, P);
+        else launch_hs2<NOISE, true, false>(renorm, g, b, s, P);
     } else {
-        if (axis_z) heun_single_kernel<NOISE, false, true><<<g, b, 0, s>>>(P);
-        else heun_single_kernel<NOISE, false, false><<<g, b, 0, s>>>(P);
+        if (axis_z) launch_hs2<NOISE, false, true>(renorm, g, b, s, P);
+        else launch_hs2<NOISE, false, false>(renorm, g, b, s, P);
     }
 }
 

@@ -111,18 +111,22 @@ __device__ __forceinline__ void philox_gauss3_f32(uint32_t seed_lo, uint32_t see
 
 // Packed mode: SIX draws of N(0, amp^2) from one Philox block, i.e. the increments of the two
 // steps s = 2b and s = 2b + 1 (s = 0-based step index) of one (member, particle).  The 128 bits
-// w0:w1:w2:w3 are cut, most significant first, into three (24-bit radius uniform, 18-bit angle)
-// pairs — 126 bits used.  24 bits is what the fp32 logarithm resolves anyway (radius up to
-// 5.9 sigma); 2^18 equidistant directions reproduce every circular moment below order 2^18.
+// w0:w1:w2:w3 are cut, most significant first, into three (24-bit radius field, 18-bit angle) pairs;
+// the top 23 bits of each radius field are used (what an fp32 mantissa holds; radius up to 5.6 sigma);
+// 2^18 equidistant directions reproduce every circular moment below order 2^18.
 //   pair 0 -> g[0], g[1]    pair 1 -> g[2], g[3]    pair 2 -> g[4], g[5]
 // g[0..2] belong to the even step, g[3..5] to the odd one.
 #define MB_PACKED_KEY_TAG (2u << 24)
-#define MB_TWO_PI_2M18 2.3968449810713143e-5f /* 2 pi 2^-18 */
 
-__device__ __forceinline__ void bm_pair_packed(uint32_t r24, uint32_t a18, float neg2ln2_amp2, float& c, float& s) {
-    const float u = fmaf((float)r24, 5.9604644775390625e-08f, 2.98023223876953125e-08f);  // (k + 1/2) 2^-24
+// Both uniforms are turned into floats in [1, 2) by OR-ing the bits into the mantissa (one LOP3, no
+// integer-to-float conversion): the radius uniform is u = 2 - f in (0, 1] and the angle needs no offset
+// at all because sin/cos have period one revolution.
+__device__ __forceinline__ void bm_pair_packed(uint32_t r23_bits /* 23 bits, already in mantissa position */,
+                                               uint32_t a18_bits /* 18 bits, in the top of the mantissa */,
+                                               float neg2ln2_amp2, float& c, float& s) {
+    const float u = 2.0f - __uint_as_float(r23_bits | 0x3f800000u);          // (0, 1], steps of 2^-23
     const float r = sqrt_approx(lg2_approx(u) * neg2ln2_amp2);
-    const float a = (float)a18 * MB_TWO_PI_2M18;
+    const float a = __uint_as_float(a18_bits | 0x3f800000u) * 6.283185307179586f;   // 2 pi (1 + k 2^-18)
     c = r * __cosf(a);
     s = r * __sinf(a);
 }
@@ -132,12 +136,13 @@ __device__ __forceinline__ void philox_gauss6_f32(uint32_t seed_lo, uint32_t see
                                                   float (&g)[6]) {
     uint32_t w0 = (uint32_t)pair_index, w1 = member, w2 = seed_lo, w3 = seed_hi;
     philox4x32_10(w0, w1, w2, w3, particle | MB_PACKED_KEY_TAG, MB_PHILOX_KEY1);
-    const uint32_t r0 = w0 >> 8;                                        // bits   0..23
-    const uint32_t a0 = __funnelshift_l(w1, w0, 10) & 0x3ffffu;         // bits  24..41
-    const uint32_t r1 = __funnelshift_l(w2, w1, 10) >> 8;               // bits  42..65
-    const uint32_t a1 = (w2 >> 12) & 0x3ffffu;                          // bits  66..83
-    const uint32_t r2 = __funnelshift_l(w3, w2, 20) >> 8;               // bits  84..107
-    const uint32_t a2 = (w3 >> 2) & 0x3ffffu;                           // bits 108..125
+    // 23-bit radius fields land in mantissa bits 22..0, 18-bit angle fields in mantissa bits 22..5
+    const uint32_t r0 = w0 >> 9;                                              // string bits   0..22  (bit 23 unused)
+    const uint32_t a0 = (__funnelshift_l(w1, w0, 15)) & 0x007fffe0u;          // string bits  24..41
+    const uint32_t r1 = __funnelshift_l(w2, w1, 10) >> 9;                     // string bits  42..64  (bit 65 unused)
+    const uint32_t a1 = (w2 >> 7) & 0x007fffe0u;                              // string bits  66..83
+    const uint32_t r2 = __funnelshift_l(w3, w2, 20) >> 9;                     // string bits  84..106 (bit 107 unused)
+    const uint32_t a2 = (w3 << 3) & 0x007fffe0u;                              // string bits 108..125
     bm_pair_packed(r0, a0, neg2ln2_amp2, g[0], g[1]);
     bm_pair_packed(r1, a1, neg2ln2_amp2, g[2], g[3]);
     bm_pair_packed(r2, a2, neg2ln2_amp2, g[4], g[5]);

@@ -133,8 +133,9 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  *         with a ~1e-5 tolerance); mode 1: fp64 Box-Muller from 53-bit uniforms, two blocks;
  * mode 2: packed fp32 Box-Muller — ONE block, counter word 0 = (step-1)>>1, key word 0 =
  *         particle | 2<<24, feeds the two steps 2b+1, 2b+2: the 128 bits w0:w1:w2:w3 are cut
- *         into three (24-bit radius, 18-bit angle) pairs -> six draws, the first three for
- *         the odd `step` (1-based), the last three for the even one. */
+ *         into three (24-bit radius field of which the top 23 bits are used, 18-bit angle)
+ *         pairs -> six draws, the first three for the odd `step` (1-based), the last three
+ *         for the even one. */
 static float u32_to_float_rz(uint32_t x) { /* cvt.rz.f32.u32 */
     if (x >= (1u << 24)) {
         int sh = 8 - __builtin_clz(x);
@@ -143,10 +144,10 @@ static float u32_to_float_rz(uint32_t x) { /* cvt.rz.f32.u32 */
     return (float)x;
 }
 
-static void bm_pair_packed(uint32_t r24, uint32_t a18, float* c, float* s) {
-    const float u = fmaf((float)r24, 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+static void bm_pair_packed(uint32_t r23, uint32_t a18, float* c, float* s) {
+    const float u = 2.0f - (1.0f + (float)r23 * 1.1920928955078125e-07f);       /* 1 - k 2^-23, in (0, 1] */
     const float r = sqrtf(log2f(u) * -1.3862943611198906f);
-    const float a = (float)a18 * 2.3968449810713143e-5f;
+    const float a = (1.0f + (float)a18 * 3.814697265625e-06f) * 6.283185307179586f; /* 2 pi (1 + k 2^-18) */
     *c = r * cosf(a);
     *s = r * sinf(a);
 }
@@ -165,9 +166,9 @@ void orc_philox_gauss3(uint64_t seed, uint32_t member, uint32_t particle, uint64
                 : ((pos) >= 64)      ? (lo >> (128 - (pos) - (len)))                                \
                                      : ((hi << ((pos) + (len) - 64)) | (lo >> (128 - (pos) - (len))))) & \
                ((1ull << (len)) - 1))
-        bm_pair_packed(ORC_BITS(0, 24), ORC_BITS(24, 18), &g[0], &g[1]);
-        bm_pair_packed(ORC_BITS(42, 24), ORC_BITS(66, 18), &g[2], &g[3]);
-        bm_pair_packed(ORC_BITS(84, 24), ORC_BITS(108, 18), &g[4], &g[5]);
+        bm_pair_packed(ORC_BITS(0, 23), ORC_BITS(24, 18), &g[0], &g[1]);
+        bm_pair_packed(ORC_BITS(42, 23), ORC_BITS(66, 18), &g[2], &g[3]);
+        bm_pair_packed(ORC_BITS(84, 23), ORC_BITS(108, 18), &g[4], &g[5]);
 #undef ORC_BITS
         const int odd = (int)((step - 1) & 1);
         for (int i = 0; i < 3; ++i) out[i] = (double)g[3 * odd + i];

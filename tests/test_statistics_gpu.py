@@ -79,7 +79,9 @@ def test_dimer_relaxation_matches_reference_ensemble(orc, core):
 @pytest.mark.parametrize('implicit', [False, True])
 def test_single_particle_equilibrium_is_boltzmann(core, implicit):
     """docs/source/notebooks/single-particle-equilibrium.ipynb: p(theta) ~ sin(theta) exp(sigma cos^2 theta)."""
-    c = ol.make_case(N=1, radius=5e-9, anisotropy=4e4, T=300.0, alpha=0.5, dt=5e-13 if not implicit else 2e-12,
+    # Heun's weak bias on <cos^2 theta> is first order in dt (+4.3e-3 at 5e-13 s, +1.1e-3 at 1e-13 s, measured with all
+    # three Gaussian transforms), so the explicit scheme runs at 1e-13 s to stay inside the 2e-3 allowance below
+    c = ol.make_case(N=1, radius=5e-9, anisotropy=4e4, T=300.0, alpha=0.5, dt=1e-13 if not implicit else 2e-12,
                      t_end=2e-9, S=3, implicit=implicit, axis=[[0, 0, 1.0]], m0=[[0, 0, 1.0]])
     KB = 1.38064852e-23
     sigma = c.anisotropy[0] * 4 / 3 * np.pi * c.radius[0] ** 3 / KB / c.T
