@@ -136,6 +136,15 @@ int magpy_b200_simulate(const double* radius, const double* anisotropy, const do
 /* Host buffers in, host buffers out (upload, integrate, reduce, download). */
 int magpy_b200_simulate_ensemble(const magpy_b200_ensemble* args, magpy_b200_stats* stats);
 
+/* The same over several GPUs of one box from ONE host thread: the members are cut into contiguous ranges of
+ * ceil(R / n_devices) (member i keeps its seed and its Philox index whatever the device count, so results do not
+ * depend on it), every device integrates its range concurrently on its own stream, per-member outputs land in the
+ * caller's arrays at the member's global position and the [S][4] ensemble sums of the devices are added on the host
+ * in device-list order (n_devices x 3 KB: no collective is needed inside one process).  `args->device` is ignored.
+ * Replaces the `n_jobs` process pool of magpy/model.py:204-207. */
+int magpy_b200_simulate_ensemble_multi(const magpy_b200_ensemble* args, const int* devices, int n_devices,
+                                       magpy_b200_stats* stats);
+
 /* Device-resident variant: create uploads inputs and allocates outputs once; run
  * re-integrates from the initial state (asynchronously on the plan's stream);
  * fetch copies the requested outputs into the host pointers of `args`. */

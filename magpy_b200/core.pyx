@@ -97,6 +97,7 @@ cdef extern from "magpy_b200.h" nogil:
                             double, double, double, int, int, int, double, double, double, size_t, int64_t, int,
                             double, double, double*, double*, double*, magpy_b200_stats*)
     int magpy_b200_simulate_ensemble(const magpy_b200_ensemble*, magpy_b200_stats*)
+    int magpy_b200_simulate_ensemble_multi(const magpy_b200_ensemble*, const int*, int, magpy_b200_stats*)
     int magpy_b200_plan_create(const magpy_b200_ensemble*, magpy_b200_plan**)
     int magpy_b200_plan_run(magpy_b200_plan*)
     int magpy_b200_plan_sync(magpy_b200_plan*, magpy_b200_stats*)
@@ -339,8 +340,11 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
                       bint use_implicit, double time_step, double end_time, max_samples, seeds,
                       str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
                       double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=True,
-                      bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None):
+                      bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None, devices=None):
     """Integrate R = len(seeds) independent members of one cluster in a single call.
+
+    `devices` (list of CUDA ordinals, or 'all') shards the members over several GPUs of this box from this one
+    process (magpy_b200_simulate_ensemble_multi); `device` is then ignored.
 
     `anisotropy_axis` and `magnetisation_direction` are (N,3) (shared) or (R,N,3).
     Returns a dict with 'time' [S], 'field' [S], 'trajectories' [R,N,3,S] | None,
@@ -354,8 +358,24 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
                                        return_sums, return_final, gauss, injected_dw)
     cdef magpy_b200_stats st
     cdef int rc
-    with nogil:
-        rc = magpy_b200_simulate_ensemble(&e.a, &st)
+    cdef np.ndarray[int, ndim=1, mode='c'] c_dev
+    cdef int n_dev
+    if devices is None:
+        with nogil:
+            rc = magpy_b200_simulate_ensemble(&e.a, &st)
+    else:
+        if isinstance(devices, str):
+            if devices != 'all':
+                raise ValueError("devices must be a list of CUDA device ordinals or 'all'")
+            devices = list(range(device_count()))
+            if not devices:
+                raise RuntimeError('no CUDA device available; magpy_b200 has no CPU fallback')
+        c_dev = np.ascontiguousarray(devices, dtype=np.intc).reshape(-1)
+        n_dev = c_dev.shape[0]
+        if n_dev == 0:
+            raise ValueError('devices must list at least one CUDA device')
+        with nogil:
+            rc = magpy_b200_simulate_ensemble_multi(&e.a, <const int*> &c_dev[0], n_dev, &st)
     if rc != 0:
         _raise(rc)
     return {'N': e.N, 'R': e.R, 'time': e.time, 'field': e.field, 'trajectories': e.trajectories,

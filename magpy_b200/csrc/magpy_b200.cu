@@ -790,6 +790,79 @@ int magpy_b200_simulate_ensemble(const magpy_b200_ensemble* args, magpy_b200_sta
     return rc;
 }
 
+int magpy_b200_simulate_ensemble_multi(const magpy_b200_ensemble* args, const int* devices, int n_devices,
+                                       magpy_b200_stats* stats) {
+    if (!args) return fail(MAGPY_B200_ERR_BAD_ARG, "args is NULL");
+    if (!devices || n_devices < 1) return fail(MAGPY_B200_ERR_BAD_ARG, "devices must list at least one CUDA device");
+    if (n_devices == 1) {
+        magpy_b200_ensemble one = *args;
+        one.device = devices[0];
+        return magpy_b200_simulate_ensemble(&one, stats);
+    }
+    const uint64_t R = args->n_members, n = 3ull * args->n_particles, S = args->max_samples;
+    const uint64_t per = (R + n_devices - 1) / n_devices;   // same split as magpy_b200/sharding.py
+    std::vector<magpy_b200_plan*> plans;
+    std::vector<magpy_b200_ensemble> shard;
+    std::vector<std::vector<double>> part;
+    int rc = MAGPY_B200_OK;
+    try {
+        for (int g = 0; g < n_devices && !rc; ++g) {
+            const uint64_t lo = std::min<uint64_t>((uint64_t)g * per, R), hi = std::min<uint64_t>(lo + per, R);
+            if (hi == lo) break;   // more devices than members
+            magpy_b200_ensemble a = *args;
+            a.device = devices[g];
+            a.n_members = hi - lo;
+            a.stream_offset = args->stream_offset + lo;
+            if (a.seeds) a.seeds += lo;
+            if (a.axis_stride) a.anisotropy_axis += lo * a.axis_stride;
+            if (a.m0_stride) a.magnetisation_direction += lo * a.m0_stride;
+            if (a.injected_dw) a.injected_dw += lo * a.injected_steps * n;
+            if (a.out_trajectories) a.out_trajectories += lo * n * S;
+            if (a.out_final) a.out_final += lo * n;
+            part.emplace_back(a.out_sums ? S * 4 : 0);
+            if (g > 0) a.out_time = a.out_field = nullptr;
+            shard.push_back(a);
+            magpy_b200_plan* pl = nullptr;
+            rc = magpy_b200_plan_create(&shard.back(), &pl);
+            if (!rc) plans.push_back(pl);
+        }
+        // all shards integrate concurrently: plan_run only enqueues work on the plan's own stream
+        for (size_t g = 0; g < plans.size() && !rc; ++g) rc = plan_run(plans[g]);
+        magpy_b200_stats total;
+        std::memset(&total, 0, sizeof total);
+        for (size_t g = 0; g < plans.size() && !rc; ++g) {
+            const magpy_b200_ensemble& a = shard[g];
+            rc = plan_sync(plans[g], nullptr);
+            if (!rc)
+                rc = plan_fetch(plans[g], a.out_time, a.out_field, a.out_trajectories,
+                                a.out_sums ? part[g].data() : nullptr, a.out_final);
+            magpy_b200_stats st;
+            if (!rc) rc = plan_sync(plans[g], &st);
+            if (rc) break;
+            total.steps_per_member = st.steps_per_member;
+            total.particle_steps += st.particle_steps;
+            total.newton_iterations += st.newton_iterations;
+            total.newton_max_iterations = std::max(total.newton_max_iterations, st.newton_max_iterations);
+            total.newton_failures += st.newton_failures;
+            total.kernel_launches += st.kernel_launches;
+            total.device_ms = std::max(total.device_ms, st.device_ms);
+            total.integrate_ms = std::max(total.integrate_ms, st.integrate_ms);
+            total.h2d_bytes += st.h2d_bytes;
+            total.d2h_bytes += st.d2h_bytes;
+        }
+        if (!rc && args->out_sums) {   // fixed device order: deterministic for a given device list
+            std::fill_n(args->out_sums, S * 4, 0.0);
+            for (size_t g = 0; g < plans.size(); ++g)
+                for (uint64_t q = 0; q < S * 4; ++q) args->out_sums[q] += part[g][q];
+        }
+        if (!rc && stats) *stats = total;
+    } catch (const std::exception& e) {
+        rc = fail(MAGPY_B200_ERR_NOMEM, "%s", e.what());
+    }
+    for (magpy_b200_plan* pl : plans) delete pl;
+    return rc;
+}
+
 int magpy_b200_simulate(const double* radius, const double* anisotropy, const double* anisotropy_axis,
                         const double* magnetisation_direction, const double* location, size_t n_particles,
                         double magnetisation, double damping, double temperature, int renorm, int interactions,

@@ -93,6 +93,12 @@ def test_argument_errors_do_not_need_a_device(core):
     with pytest.raises(KeyError):
         core.simulate_ensemble(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False,
                                True, False, c.dt, c.t_end, 10, [1, 2, 3], gauss='f16')
+    with pytest.raises(ValueError):          # single-process multi-GPU entry: an empty device list
+        core.simulate_ensemble(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False,
+                               True, False, c.dt, c.t_end, 10, [1, 2, 3], devices=[])
+    with pytest.raises(ValueError):
+        core.simulate_ensemble(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False,
+                               True, False, c.dt, c.t_end, 10, [1, 2, 3], devices='some')
 
 
 def test_no_cpu_fallback(core):
@@ -104,6 +110,9 @@ def test_no_cpu_fallback(core):
                       c.t_end, 10, 1)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         core.fp64_peak()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        core.simulate_ensemble(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True,
+                               False, c.dt, c.t_end, 10, [1, 2, 3], devices=[0, 1])
 
 
 def test_product_never_touches_the_oracle():

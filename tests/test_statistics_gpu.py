@@ -131,6 +131,30 @@ def test_results_do_not_depend_on_chunking_or_sharding(core):
     assert np.array_equal(w2['trajectories'], ch2['trajectories'])
 
 
+def test_single_process_multi_gpu_matches_one_gpu(core):
+    """magpy_b200_simulate_ensemble_multi: members sharded over the GPUs of the box from one process give the
+    per-member outputs of a one-GPU run bit for bit and the same ensemble sums up to fp64 summation order."""
+    n_dev = core.device_count()
+    c = ol.make_case(N=3, dt=1e-13, t_end=2e-11, S=9, field_shape='sine', H0=1e4, f=1e10, rng=np.random.default_rng(3))
+    seeds = np.arange(1, 1001) * 17
+    rng = np.random.default_rng(4)
+    m0 = rng.normal(size=(len(seeds), c.N, 3)); m0 /= np.linalg.norm(m0, axis=-1, keepdims=True)
+    one = gpu(core, ol.Case(dict(c, m0=m0)), seeds)
+    # more devices than exist must fail loudly
+    with pytest.raises(RuntimeError):
+        gpu(core, ol.Case(dict(c, m0=m0)), seeds, devices=[0, n_dev])
+    devs = list(range(n_dev)) if n_dev > 1 else [0, 0]      # one GPU: two shards on the same device
+    many = gpu(core, ol.Case(dict(c, m0=m0)), seeds, devices=devs)
+    assert np.array_equal(one['trajectories'], many['trajectories'])
+    assert np.array_equal(one['final'], many['final'])
+    assert np.array_equal(one['time'], many['time']) and np.array_equal(one['field'], many['field'])
+    assert np.allclose(one['sums'], many['sums'], rtol=1e-12, atol=1e-9 * c.Ms)
+    assert many['stats']['particle_steps'] == one['stats']['particle_steps']
+    # 'all' and a ragged split (3 shards of 334, 334, 332)
+    rag = gpu(core, ol.Case(dict(c, m0=m0)), seeds, devices=[0] * 3, return_trajectories=False)
+    assert np.array_equal(one['final'], rag['final'])
+
+
 def test_hysteresis_energy_matches_reference_ensemble(orc, core):
     """Energy dissipated per cycle, -mu0 * loop area (magpy/results.py:167-217), GPU/Philox vs
     oracle/MT ensembles of a low-barrier particle driven at 2 GHz (short enough for the CPU)."""
