@@ -3,7 +3,7 @@
 //   lib/simulation.cpp  (SI->reduced conversion :498-549, schedule :171-174/:342-405,
 //                        rescale :610-621)
 //   magpy/model.py:202-207 (per-member fan-out)
-// and drives the kernels in kernels.cuh.  No CPU integration path exists here: without a
+// and drives the kernels through the launchers of launch.h.  No CPU integration path exists here: without a
 // CUDA device every compute entry point fails with MAGPY_B200_ERR_NO_DEVICE.
 #include <algorithm>
 #include <cmath>
