@@ -77,35 +77,46 @@ __global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __gri
     // counter word is the low 32 bits of the step / step-pair index anyway) plus one table pointer.
     uint64_t j = P.j0;
     const double2* tab = reinterpret_cast<const double2*>(P.field_tab);
-    float carry[3] = {0.f, 0.f, 0.f};   // packed mode: increments of the odd step of the current Philox block
-    if (NOISE == NOISE_PHILOX_PACKED && (j & 1)) {
-        float g[6];
-        philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
-        carry[0] = g[3]; carry[1] = g[4]; carry[2] = g[5];
-    }
+    // Packed noise: `g` holds the six increments of Philox block `gblk` (steps 2 gblk and 2 gblk + 1) while
+    // `have` is set.  The pair loop is software pipelined — the block of the NEXT step pair is generated inside
+    // the loop body that integrates the CURRENT pair, so that the generator's IMAD.WIDE / MUFU / F2F instructions
+    // are interleaved with the integrator's DFMA chain in program order — and the prefetched block is carried
+    // across sample boundaries, so nothing is generated twice or thrown away (except once per launch).
+    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t gblk = 0;
+    bool have = false;
+    auto need = [&](const uint32_t blk) {
+        if (!have || gblk != blk) {
+            philox_gauss6_f32(key0, key1, blk, 0u, member, bm_scale, g);
+            gblk = blk;
+            have = true;
+        }
+    };
     for (uint32_t k = P.k0; k <= P.k1; ++k) {
         const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
         if (NOISE == NOISE_PHILOX_PACKED) {
-            // invariant: when j is odd, `carry` holds the second half of block j >> 1
-            if ((j & 1) && j < tgt) {
-                advance(V3{widen_f32(carry[0]), widen_f32(carry[1]), widen_f32(carry[2])}, tab + (j - P.j0));
+            if ((j & 1) && j < tgt) {          // odd step: second half of its block
+                need((uint32_t)(j >> 1));
+                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tab + (j - P.j0));
                 ++j;
             }
             const uint32_t pairs = (uint32_t)((tgt - j) >> 1);
             uint32_t blk = (uint32_t)(j >> 1);
             const double2* tp = tab + (j - P.j0);
-            for (uint32_t i = pairs; i != 0; --i, ++blk, tp += 2) {
-                float g[6];
-                philox_gauss6_f32(key0, key1, blk, 0u, member, bm_scale, g);
+            if (pairs != 0) need(blk);
+            for (uint32_t i = pairs; i != 0; --i, tp += 2) {
+                float gn[6];
+                philox_gauss6_f32(key0, key1, ++blk, 0u, member, bm_scale, gn);
                 advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tp);
                 advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tp + 1);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) g[q] = gn[q];
+                gblk = blk;
             }
             j += 2ull * pairs;
-            if (j < tgt) {
-                float g[6];
-                philox_gauss6_f32(key0, key1, j >> 1, 0u, member, bm_scale, g);
+            if (j < tgt) {                     // one more (even) step before the sample: first half of its block
+                need((uint32_t)(j >> 1));
                 advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tab + (j - P.j0));
-                carry[0] = g[3]; carry[1] = g[4]; carry[2] = g[5];
                 ++j;
             }
         } else {

@@ -56,13 +56,15 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
     }
 }
 
-// float -> double widening.  Measured on B200 (profiles/README.md): one F2F.F64.F32 on the XU
-// pipe beats the 5-instruction integer re-biasing of exponent and mantissa by 5 % end to end,
-// because the kernel is bound by issue slots, not by the XU pipe.
+// float -> double widening of a Gaussian increment.  Measured on B200 (profiles/README.md): in the
+// issue-mix micro-benchmark one F2F.F64.F32 takes ~3.5 cycles of the FP64 pipe away from a DFMA stream,
+// but assembling the double from the float's bits (LOP3, LEA.HI, LOP3, SHF: exponent re-biased by 896,
+// mantissa shifted by 3) makes the Heun kernel 9 % slower end to end (2.22e11 vs 2.44e11 particle-steps/s):
+// the kernel has no issue slots to spare for 24 more instructions per step pair.  F2F stays.
 __device__ __forceinline__ double widen_f32(float f) {
 #ifdef MB_WIDEN_INT
     const uint32_t b = __float_as_uint(f);
-    const uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);
+    const uint32_t hi = (((b & 0x7fffffffu) >> 3) + 0x38000000u) | (b & 0x80000000u);
     const uint32_t lo = b << 29;
     return __hiloint2double((int)hi, (int)lo);
 #else

@@ -6,7 +6,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-enum { K_FFMA = 0, K_IMAD = 1, K_LOP = 2, K_IMADW = 3, K_MUFU = 4, K_F2F = 5, K_I2F = 6, K_HILO = 7, K_HI = 8, K_PRMT = 9, K_HILO_SPLIT = 10 };
+enum { K_FFMA = 0, K_IMAD = 1, K_LOP = 2, K_IMADW = 3, K_MUFU = 4, K_F2F = 5, K_I2F = 6, K_HILO = 7, K_HI = 8, K_PRMT = 9, K_HILO_SPLIT = 10, K_WIDEN_INT = 11, K_I2F_F64 = 12 };
 
 template <int NDF, int MIX, int KIND>
 __global__ void mix_kernel(double* out, float* fout, int iters, double a, double b, float fa, unsigned ia) {
@@ -23,7 +23,8 @@ __global__ void mix_kernel(double* out, float* fout, int iters, double a, double
         for (int u = 0; u < 4; ++u) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (NDF) x[i] = fma(x[i], a, b);
+#pragma unroll
+                for (int d = 0; d < NDF; ++d) x[i] = fma(x[i], a, b + d);
 #pragma unroll
                 for (int m = 0; m < MIX; ++m) {
                     const int q = (i * MIX + m) & 15;
@@ -51,6 +52,13 @@ __global__ void mix_kernel(double* out, float* fout, int iters, double a, double
                         // ptxas cannot prove the multipliers equal, so it cannot fuse the two into one IMAD.WIDE
                         const unsigned hi = __umulhi(z[q], 2654435761u);
                         z[q] = hi ^ (z[q] * ia);
+                    } else if (KIND == K_WIDEN_INT) {
+                        // float -> double by integer re-biasing (5 ALU instructions, no XU)
+                        const unsigned bits = __float_as_uint(y[q]);
+                        const unsigned hi = (bits & 0x80000000u) | (((bits & 0x7fffffffu) >> 3) + 0x38000000u);
+                        const unsigned lo = bits << 29;
+                        z[q] ^= hi ^ lo;
+                        y[q] += 1.0f;
                     } else if (KIND == K_HI) {
                         z[q] = __umulhi(z[q], ia);                                // IMAD.HI.U32
                     } else if (KIND == K_PRMT) {
@@ -118,6 +126,22 @@ int main() {
         run<1, 1, K_HILO_SPLIT>("DFMA + 1 (IMAD.HI imm,IMAD reg,LOP3)", w);
         run<1, 2, K_HILO_SPLIT>("DFMA + 2 (IMAD.HI imm,IMAD reg,LOP3)", w);
         run<0, 1, K_HILO_SPLIT>("1 (IMAD.HI imm,IMAD reg,LOP3)", w);
+        run<4, 1, K_IMADW>("4 DFMA + 1 (IMAD.WIDE,LOP3)", w);
+        run<4, 1, K_HILO_SPLIT>("4 DFMA + 1 (IMAD.HI imm,IMAD reg,LOP3)", w);
+        run<4, 0, K_FFMA>("4 DFMA", w);
+        run<4, 1, K_F2F>("4 DFMA + 1 (F2F.F64.F32,LOP3,FADD)", w);
+        run<8, 1, K_F2F>("8 DFMA + 1 (F2F.F64.F32,LOP3,FADD)", w);
+        run<4, 1, K_WIDEN_INT>("4 DFMA + 1 (int widen ~6 ALU,FADD)", w);
+        run<8, 1, K_WIDEN_INT>("8 DFMA + 1 (int widen ~6 ALU,FADD)", w);
+        run<8, 0, K_FFMA>("8 DFMA", w);
+        run<8, 1, K_MUFU>("8 DFMA + 1 MUFU", w);
+        run<8, 2, K_MUFU>("8 DFMA + 2 MUFU", w);
+        run<8, 1, K_I2F>("8 DFMA + 1 (I2FP,FADD,IADD)", w);
+        run<4, 1, K_MUFU>("4 DFMA + 1 MUFU", w);
+        run<4, 2, K_FFMA>("4 DFMA + 2 FFMA", w);
+        run<4, 4, K_FFMA>("4 DFMA + 4 FFMA", w);
+        run<4, 2, K_PRMT>("4 DFMA + 2 PRMT", w);
+        run<4, 4, K_PRMT>("4 DFMA + 4 PRMT", w);
         run<1, 1, K_HI>("DFMA + 1 IMAD.HI", w);
         run<1, 2, K_HI>("DFMA + 2 IMAD.HI", w);
         run<0, 2, K_HI>("2 IMAD.HI", w);
