@@ -9,8 +9,20 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+def _ensure_built():
+    """The binaries are git-ignored: on a fresh checkout build them once (nvcc cross-compiles without a GPU)."""
+    import glob
+    have = (os.path.exists(os.path.join(ROOT, 'magpy_b200', 'libmagpy_b200.so'))
+            and glob.glob(os.path.join(ROOT, 'magpy_b200', 'core.*.so'))
+            and os.path.exists(os.path.join(ROOT, 'oracle', 'libsllg_oracle.so')))
+    if not have:
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    _ensure_built()
 
 
 def _cuda_devices():
