@@ -176,3 +176,14 @@ class EnsembleResults:
         """Energy dissipated during the last field period (magpy/results.py:193-217)."""
         T = 1. / field_frequency
         return self.energy_dissipated(start_time=self.time[-1] - T)
+
+    def specific_absorption_rate(self, field_frequency, density=5180.0):
+        """Specific absorption rate in W/kg of particle material: the energy dissipated per field cycle and
+        unit volume (:meth:`final_cycle_energy_dissipated`, J/m^3) times the field frequency, divided by the
+        mass density (default: magnetite, 5180 kg/m^3).  The reference stops at the energy per cycle
+        (magpy/results.py:193-217); the conversion is the textbook SAR = |E| f / rho.  The magnitude is
+        taken because the reference's `-mu0 * trapz(field, M)` is negative for a magnetisation that lags
+        the field (its sign convention is kept unchanged in :meth:`energy_dissipated`).  For a cluster the
+        ensemble magnetisation is the sum over its particles, so divide by the particle count for a
+        per-particle figure."""
+        return abs(self.final_cycle_energy_dissipated(field_frequency)) * field_frequency / density

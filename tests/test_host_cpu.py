@@ -165,6 +165,21 @@ def test_results_api_matches_reference_semantics():
     assert np.allclose(se, traj[:, :, 2].sum(1).std(axis=0, ddof=1) / np.sqrt(R))
 
 
+def test_sar_is_cycle_energy_times_frequency_over_density():
+    from magpy_b200.results import EnsembleResults
+    from magpy_b200.core import get_mu0
+    f, H0, Ms, S = 3e5, 2e4, 4e5, 4001
+    t = np.linspace(0, 2 / f, S)
+    H = H0 * np.sin(2 * np.pi * f * t)
+    M = 0.8 * Ms * np.sin(2 * np.pi * f * t - 0.3)            # lagging response: elliptical loop
+    sums = np.zeros((S, 4)); sums[:, 2] = 10 * M
+    res = EnsembleResults.from_arrays(t, H, 10, sums=sums)
+    area = np.pi * H0 * 0.8 * Ms * np.sin(0.3) * get_mu0()   # mu0 * pi * H0 * M0 * sin(phase lag) per cycle
+    # the reference's sign convention (magpy/results.py:191): -mu0 * trapz(field, M) is negative for a lagging M
+    assert abs(res.final_cycle_energy_dissipated(f) / -area - 1) < 1e-3
+    assert abs(res.specific_absorption_rate(f) / (area * f / 5180.0) - 1) < 1e-3
+
+
 def test_ensemble_model_seeds_and_grouping(monkeypatch):
     import magpy_b200 as mp
     from magpy_b200 import model as model_mod
