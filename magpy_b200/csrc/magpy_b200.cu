@@ -460,8 +460,6 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     pl->h2d += R * 8;
 
     // per-member arrays arrive [R][n]; the device wants [n][R]
-    const bool need_stage = a->m0_stride || a->axis_stride || pl->injected || true;
-    (void)need_stage;
     {
         size_t stage = n * R;
         if (pl->injected) stage = std::max<size_t>(stage, (size_t)pl->total_steps * n * R);

@@ -76,11 +76,6 @@ __global__ void broadcast_rows_kernel(const double* in, double* out, uint64_t n,
         out[i] = in[i / R];
 }
 
-__global__ void scale_kernel(double* a, uint64_t n, double s) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] *= s;
-}
-
 // dependent-free DFMA chains: the measured FP64 roofline denominator
 __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
