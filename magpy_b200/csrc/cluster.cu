@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
                                    -(X[q].z - m[q].z - 0.5 * f.z)};
                     double A[9], d[3];
                     newton_matrix(A, X[q], alpha, h, sw[q], qu[q], e0);
-                    if (!solve3(A, b, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
+                    if (!solve3_adjugate(A, b, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                     dl[q] = V3{d[0], d[1], d[2]};
                     part += d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
                 }

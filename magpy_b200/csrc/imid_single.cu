@@ -41,7 +41,7 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
         double A[9], d[3];
         newton_matrix(A, X, alpha, h, sw, ke, e);
         ++done;
-        if (!solve3(A, b, d)) {
+        if (!solve3_adjugate(A, b, d)) {
             // dgesv info > 0: the reference returns with x_root = -F (lib/optimisation.cpp:136-137)
             X = V3{b[0], b[1], b[2]};
             singular = true;

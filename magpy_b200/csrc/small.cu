@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
                     b[i] = V3{bb[0], bb[1], bb[2]};
                     double A[9], d[3];
                     newton_matrix(A, X[i], alpha, h[i], sw[i], quirk_u(N, i, e[0], kred[0]), e[0]);
-                    if (!solve3(A, bb, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
+                    if (!solve3_adjugate(A, bb, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                     dl[i] = V3{d[0], d[1], d[2]};
                     e2 += d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
                 }
