@@ -265,3 +265,40 @@ def test_neel_relaxation_time_against_master_equation(orc, core):
     assert abs(rate_sllg / (rate_dom * (1 - 1 / sigma)) - 1) < 0.1, (rate_sllg, rate_dom, sigma)
     # the fast intra-well relaxation leaves <Mz> near the well average <cos theta> = 1 - 1/(2 sigma) + ...
     assert abs(np.exp(intercept) - (1 - 1 / (2 * sigma))) < 0.03
+
+
+def test_full_size_ensembles_checksum_properties(core):
+    """BASELINE configs 3 and 4 at their full member counts (1,000,000 single particles under the 300 kHz / 20 kA/m
+    sine field; 100,000 clusters of 64 dipolar-coupled particles), shortened in time: size-independent properties
+    instead of an oracle — the fused ensemble sums are the sums of the per-member final states (a checksum of
+    checksums), halves of the ensemble add up to the whole whatever the member range / Philox offset, and
+    renormalised moments have unit length."""
+    from magpy_b200 import geometry
+    # config 3
+    R = 1_000_000
+    c = ol.make_case(N=1, dt=1e-12, t_end=2e-8, S=5, field_shape='sine', H0=2e4, f=3e5, axis=[[0, 0, 1.0]],
+                     m0=[[0, 0, 1.0]], renorm=True)
+    seeds = np.random.default_rng(1).integers(0, 2 ** 31 - 1, R)
+    whole = gpu(core, c, seeds, return_trajectories=False)
+    f = whole['final'][:, 0, :] / c.Ms
+    assert np.abs(np.linalg.norm(f, axis=1) - 1).max() < 1e-12
+    assert abs(whole['sums'][-1, 2] / c.Ms - f[:, 2].sum()) < 1e-6 * R
+    assert abs(whole['sums'][-1, 3] / c.Ms ** 2 - (f[:, 2] ** 2).sum()) < 1e-6 * R
+    lo = gpu(core, c, seeds[:R // 2], return_trajectories=False)
+    hi = gpu(core, c, seeds[R // 2:], return_trajectories=False, stream_offset=R // 2)
+    assert np.array_equal(np.concatenate([lo['final'], hi['final']]), whole['final'])
+    assert np.allclose(lo['sums'] + hi['sums'], whole['sums'], rtol=1e-12, atol=1e-6 * c.Ms)
+    assert whole['stats']['particle_steps'] == R * whole['stats']['steps_per_member']
+    # config 4
+    N, R4 = 64, 100_000
+    axes = geometry.uniform_random_axes(N, rng=4)
+    c4 = ol.make_case(N=N, radius=12e-9, anisotropy=4e4, axis=axes, m0=axes, dt=1e-14, t_end=1e-12, S=3,
+                      location=geometry.random_cluster_coordinates(N, 3e-8, rng=4), renorm=True)
+    out = gpu(core, c4, np.arange(R4), return_trajectories=False)
+    f4 = out['final'] / c4.Ms                                           # [R, N, 3]
+    assert np.abs(np.linalg.norm(f4, axis=2) - 1).max() < 1e-12
+    Mz = f4[:, :, 2].sum(axis=1)
+    assert abs(out['sums'][-1, 2] / c4.Ms - Mz.sum()) < 1e-6 * R4 * N
+    assert abs(out['sums'][-1, 3] / c4.Ms ** 2 - (Mz ** 2).sum()) < 1e-6 * R4 * N * N
+    # after 100 steps of 1e-14 s every moment is still close to its easy axis, which is where it started
+    assert np.abs((f4 * axes[None]).sum(axis=2)).min() > 0.99
