@@ -302,3 +302,26 @@ def test_full_size_ensembles_checksum_properties(core):
     assert abs(out['sums'][-1, 3] / c4.Ms ** 2 - (Mz ** 2).sum()) < 1e-6 * R4 * N * N
     # after 100 steps of 1e-14 s every moment is still close to its easy axis, which is where it started
     assert np.abs((f4 * axes[None]).sum(axis=2)).min() > 0.99
+
+
+@pytest.mark.parametrize('N,implicit', [(1, False), (1, True), (2, False), (6, False), (2, True)])
+def test_zero_temperature_relaxation_closed_form(orc, core, N, implicit):
+    """T = 0 (the in-kernel noise amplitude is exactly zero), no applied field, non-interacting particles with
+    their easy axes along z: tan(theta(t)) = tan(theta0) exp(-alpha t) in reduced time (the closed form the
+    reference's test/convergence/task4 family uses), through the production (Philox) kernels of every family —
+    single, one-thread-per-cluster, shared-memory cluster; Heun and implicit midpoint."""
+    th0 = np.pi / 3
+    c = ol.make_case(N=N, T=0.0, alpha=0.1, S=11, axis=[[0, 0, 1.0]] * N, m0=[[np.sin(th0), 0, np.cos(th0)]] * N,
+                     implicit=implicit, interactions=False)
+    tf = ol.reduced_scalars(orc, c)['time_factor']
+    dt_red = 0.01
+    c['dt'] = dt_red / tf
+    c['t_end'] = 4.0 / tf
+    out = gpu(core, c, np.arange(33))
+    cum = ol.schedule(orc, dt_red, 4.0, c.S)
+    ts = np.maximum(cum.astype(float) - 1, 0) * dt_red
+    exact = 1.0 / np.sqrt(1 + np.tan(th0) ** 2 * np.exp(-2 * 0.1 * ts))
+    mz = out['trajectories'][:, :, 2, :] / c.Ms                 # [R, N, S]
+    assert np.abs(mz - exact).max() < (2e-5 if not implicit else 2e-4)
+    assert np.abs(np.linalg.norm(out['trajectories'], axis=2) / c.Ms - 1).max() < 1e-5
+    assert out['stats']['newton_failures'] == 0
