@@ -10,6 +10,7 @@ namespace mb {
 // J = I - a'/2 - (B'.w)/2 with no dt on a', tolerance eps*||guess|| fixed before the
 // loop, stop on ||delta||_2 <= tol or after 1000 iterations.
 // ---------------------------------------------------------------------------------
+template <bool AXIS_Z>
 __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const double kred, const double alpha,
                                                const double sr, const double dt, const double clampA,
                                                const double sqrt_dt, const double eps, const V3& w,
@@ -18,6 +19,7 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
                 fmax(-clampA, fmin(clampA, w.z)) * sqrt_dt};
     const V3 sw{sr * wm.x, sr * wm.y, sr * wm.z};
     const V3 ke{kred * e.x, kred * e.y, kred * e.z};   // field-Jacobian block k e e^T = ke e^T
+    const V3 nhsw{-0.5 * sw.x, -0.5 * sw.y, -0.5 * sw.z};
     // Euler half step as the initial guess of (x0 + x1)/2
     V3 X;
     {
@@ -33,13 +35,20 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
     unsigned long long done = 0;
     bool singular = false;
     while ((err2 > tol2) && (iter-- > 0)) {
-        const double s = kred * dot(X, e);
-        const V3 h{s * e.x, s * e.y, fma(s, e.z, hz_mid)};
-        const V3 g{fma(h.x, dt, sw.x), fma(h.y, dt, sw.y), fma(h.z, dt, sw.z)};
+        double A[9], d[3];
+        V3 g;
+        if (AXIS_Z) {   // easy axis = z: h = (0, 0, k X_z + h_app)
+            const double hz = fma(kred, X.z, hz_mid);
+            g = V3{sw.x, sw.y, fma(hz, dt, sw.z)};
+            newton_matrix_axis_z(A, X, alpha, hz, sw, nhsw, kred);
+        } else {
+            const double s = kred * dot(X, e);
+            const V3 h{s * e.x, s * e.y, fma(s, e.z, hz_mid)};
+            g = V3{fma(h.x, dt, sw.x), fma(h.y, dt, sw.y), fma(h.z, dt, sw.z)};
+            newton_matrix(A, X, alpha, h, sw, ke, e);
+        }
         const V3 f = llg_f(X, g, alpha);
         double b[3] = {-(X.x - x0.x - 0.5 * f.x), -(X.y - x0.y - 0.5 * f.y), -(X.z - x0.z - 0.5 * f.z)};
-        double A[9], d[3];
-        newton_matrix(A, X, alpha, h, sw, ke, e);
         ++done;
         if (!solve3_adjugate(A, b, d)) {
             // dgesv info > 0: the reference returns with x_root = -F (lib/optimisation.cpp:136-137)
@@ -56,7 +65,7 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
     return V3{2 * X.x - x0.x, 2 * X.y - x0.y, 2 * X.z - x0.z};
 }
 
-template <int NOISE, bool FIELD_TAB>
+template <int NOISE, bool FIELD_TAB, bool AXIS_Z>
 __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
@@ -82,7 +91,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
                 const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - P.j0));
                 hz0 = h.x; hz1 = h.y;
             }
-            m = imid_single_step(m, e, kred, P.alpha, sr, P.dt, P.clampA, P.sqrt_dt, P.eps, w, hz0, hz1, nc);
+            m = imid_single_step<AXIS_Z>(m, e, kred, P.alpha, sr, P.dt, P.clampA, P.sqrt_dt, P.eps, w, hz0, hz1, nc);
             if (renorm) renormalise(m);
         }
         if (k < P.k1) {
@@ -104,18 +113,23 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
 }
 
 template <int NOISE>
-static void launch_is(bool tab, unsigned grid, cudaStream_t s, const RunParams& P) {
+static void launch_is(bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
     const dim3 g(grid), b(SINGLE_THREADS);
-    if (tab) imid_single_kernel<NOISE, true><<<g, b, 0, s>>>(P);
-    else imid_single_kernel<NOISE, false><<<g, b, 0, s>>>(P);
+    if (tab) {
+        if (axis_z) imid_single_kernel<NOISE, true, true><<<g, b, 0, s>>>(P);
+        else imid_single_kernel<NOISE, true, false><<<g, b, 0, s>>>(P);
+    } else {
+        if (axis_z) imid_single_kernel<NOISE, false, true><<<g, b, 0, s>>>(P);
+        else imid_single_kernel<NOISE, false, false><<<g, b, 0, s>>>(P);
+    }
 }
 
-cudaError_t launch_imid_single(int noise, bool tab, unsigned grid, cudaStream_t s, const RunParams& P) {
+cudaError_t launch_imid_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
     switch (noise) {
-        case NOISE_PHILOX_F32: launch_is<NOISE_PHILOX_F32>(tab, grid, s, P); break;
-        case NOISE_PHILOX_F64: launch_is<NOISE_PHILOX_F64>(tab, grid, s, P); break;
-        case NOISE_INJECTED: launch_is<NOISE_INJECTED>(tab, grid, s, P); break;
-        default: launch_is<NOISE_PHILOX_PACKED>(tab, grid, s, P); break;
+        case NOISE_PHILOX_F32: launch_is<NOISE_PHILOX_F32>(tab, axis_z, grid, s, P); break;
+        case NOISE_PHILOX_F64: launch_is<NOISE_PHILOX_F64>(tab, axis_z, grid, s, P); break;
+        case NOISE_INJECTED: launch_is<NOISE_INJECTED>(tab, axis_z, grid, s, P); break;
+        default: launch_is<NOISE_PHILOX_PACKED>(tab, axis_z, grid, s, P); break;
     }
     return cudaGetLastError();
 }

@@ -10,7 +10,7 @@ struct RunParams;
 
 // noise: NOISE_PHILOX_F32 | NOISE_PHILOX_F64 | NOISE_INJECTED | NOISE_PHILOX_PACKED; tab: applied field from field_tab
 cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P);
-cudaError_t launch_imid_single(int noise, bool tab, unsigned grid, cudaStream_t s, const RunParams& P);
+cudaError_t launch_imid_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P);
 cudaError_t launch_heun_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
 cudaError_t launch_imid_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
 // layout: 0 = pair table in global memory, 1 = table in shared memory, 2 = table in shared memory + one moment buffer

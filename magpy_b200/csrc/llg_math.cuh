@@ -84,6 +84,31 @@ __device__ __forceinline__ void newton_matrix(double A[9], const V3& m, const do
     A[7] = fma(-(m.z - m.y), alpha * sw.z, A[7]);
 }
 
+// newton_matrix for a single particle whose easy axis is +z (u = k z, e = z): h = (0, 0, h_z), the rank-one
+// term only touches the third column and f(m, k z) = -k (m_y + alpha m_x m_z, -m_x + alpha m_y m_z,
+// -alpha (m_x^2 + m_y^2)).  `nhsw` = -sigma w / 2 (constant over the iteration).
+__device__ __forceinline__ void newton_matrix_axis_z(double A[9], const V3& m, const double alpha, const double hz,
+                                                     const V3& sw, const V3& nhsw, const double kred) {
+    const V3 vh{nhsw.x, nhsw.y, fma(-0.5, hz, nhsw.z)};
+    const V3 am{alpha * m.x, alpha * m.y, alpha * m.z};
+    const V3 tv{2.0 * vh.x, 2.0 * vh.y, 2.0 * vh.z};
+    const double base = fma(-alpha, dot(m, vh), 1.0);
+    const double kx = kred * m.x, ky = kred * m.y;
+    // -f(m, k z) / 2
+    const V3 fh{0.5 * fma(am.z, kx, ky), 0.5 * fma(am.z, ky, -kx), -0.5 * fma(am.x, kx, am.y * ky)};
+    A[0] = fma(am.x, vh.x, base);
+    A[4] = fma(am.y, vh.y, base);
+    A[8] = fma(am.z, vh.z, base) + fh.z;
+    A[1] = fma(-am.x, vh.y, fma(tv.x, am.y, -vh.z));
+    A[2] = fma(-am.x, vh.z, fma(tv.x, am.z, vh.y)) + fh.x;
+    A[3] = fma(-am.y, vh.x, fma(tv.y, am.x, vh.z));
+    A[5] = fma(-am.y, vh.z, fma(tv.y, am.z, -vh.x)) + fh.y;
+    A[6] = fma(-am.z, vh.x, fma(tv.z, am.x, -vh.y));
+    A[7] = fma(-am.z, vh.y, fma(tv.z, am.y, vh.x));
+    A[1] = fma(0.5 * (m.z - m.x), alpha * sw.y, A[1]);
+    A[7] = fma(-(m.z - m.y), alpha * sw.z, A[7]);
+}
+
 // The 3x3 block the reference hands to llg::drift_jacobian for particle p of an N-particle cluster is
 // the 9 doubles at flat offsets 3p..3p+8 of the dense row-major (3N)^2 anisotropy Jacobian
 // (lib/llg.cpp:387 reads hj+(3*n); lib/field.cpp:159-174 fills the diagonal blocks with k e e^T) — the

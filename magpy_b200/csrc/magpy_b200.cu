@@ -240,7 +240,7 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
     const int noise = plan_noise(pl);
     const bool tab = pl->use_table;
     if (pl->N == 1) {
-        if (pl->implicit) LAUNCH_TRY(mb::launch_imid_single(noise, tab, pl->grid, pl->stream, P));
+        if (pl->implicit) LAUNCH_TRY(mb::launch_imid_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
     } else if (pl->small) {
         if (pl->implicit) LAUNCH_TRY(mb::launch_imid_small(noise, tab, pl->N, pl->grid, pl->stream, P));

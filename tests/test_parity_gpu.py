@@ -120,11 +120,12 @@ def test_heun_single_per_member_axes_and_ragged_block(orc, core):
     assert_traj(ref, out, c)
 
 
+@pytest.mark.parametrize('axis', [[0, 0, 1.0], [0.6, 0, 0.8]])        # easy axis along z: specialised kernel
 @pytest.mark.parametrize('field_shape,H0,f,renorm,eps', [
     ('constant', 0.0, 0.0, False, 1e-9), ('sine', 2e4, 3e9, False, 1e-9), ('constant', 1e4, 0.0, True, 1e-6)])
-def test_implicit_single_injected(orc, core, field_shape, H0, f, renorm, eps):
+def test_implicit_single_injected(orc, core, field_shape, H0, f, renorm, eps, axis):
     c = ol.make_case(N=1, dt=1e-13, t_end=5e-11, S=40, implicit=True, eps=eps, field_shape=field_shape, H0=H0, f=f,
-                     renorm=renorm, axis=[[0, 0, 1.0]], m0=[[1.0, 0, 0]])
+                     renorm=renorm, axis=[axis], m0=[[1.0, 0, 0]])
     seeds = np.array([1001, 5, 77, 123456, 9, 31337])
     t, fl, ref, out, newton = injected_pair(orc, core, c, seeds)
     assert_traj(ref, out, c)
