@@ -30,14 +30,14 @@ import magpy_b200 as mp  # noqa: E402
 from magpy_b200 import geometry  # noqa: E402
 
 
-def run(name, model, R, end_time, time_step, S, implicit, **kw):
+def run(name, model, R, end_time, time_step, S, implicit, traj=False, **kw):
     ens = mp.EnsembleModel(R, model)
     shard = (rank, world) if world > 1 else None
     out = None
     for _ in range(2):   # first pass warms the context / memory pool
         t0 = time.perf_counter()
         out = ens.simulate(end_time, time_step, S, 1001, implicit_solve=implicit, device=local_rank, shard=shard,
-                           return_trajectories=False, **kw)
+                           return_trajectories=traj, **kw)
         wall = time.perf_counter() - t0
     st = out.stats[0]
     ms = st['device_ms']
@@ -56,6 +56,10 @@ def run(name, model, R, end_time, time_step, S, implicit, **kw):
                 'newton_failures': st['newton_failures'], 'mz_first_last': [float(mz[0]), float(mz[-1])]}
         print(json.dumps(line), flush=True)
 
+
+# config 1: 1000 members of the 12 nm particle, Heun dt = 1e-14 s to 1e-9 s, 1000 samples, per-member trajectories kept
+c1 = mp.Model([12e-9], [4e4], [[0, 0, 1.0]], [[1.0, 0, 0]], [[0, 0, 0]], 4e5, 0.1, 300.0)
+run('C1 single Heun 1000 x 1e5 steps, trajectories', c1, 1000, 1e-9, 1e-14, 1000, False, traj=True)
 
 # config 2: two dipolar-coupled 7 nm particles 9 nm apart (two-particle-equilibrium notebook), implicit, 10k members
 dimer = mp.Model([7e-9, 7e-9], [1e5, 1e5], [[0, 0, 1.0]] * 2, [[0, 0, 1.0]] * 2, [[0, 0, 0], [0, 0, 9e-9]], 4e5, 0.1, 330.0)
