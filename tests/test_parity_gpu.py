@@ -122,7 +122,9 @@ def test_heun_single_per_member_axes_and_ragged_block(orc, core):
 
 @pytest.mark.parametrize('axis', [[0, 0, 1.0], [0.6, 0, 0.8]])        # easy axis along z: specialised kernel
 @pytest.mark.parametrize('field_shape,H0,f,renorm,eps', [
-    ('constant', 0.0, 0.0, False, 1e-9), ('sine', 2e4, 3e9, False, 1e-9), ('constant', 1e4, 0.0, True, 1e-6)])
+    ('constant', 0.0, 0.0, False, 1e-9), ('sine', 2e4, 3e9, False, 1e-9), ('constant', 1e4, 0.0, True, 1e-6),
+    # strong field (h = H/H_k = 3.1): the quasi-Newton matrix I - a'/2 - B'.w/2 is far from the identity
+    ('constant', 5e5, 0.0, False, 1e-9)])
 def test_implicit_single_injected(orc, core, field_shape, H0, f, renorm, eps, axis):
     c = ol.make_case(N=1, dt=1e-13, t_end=5e-11, S=40, implicit=True, eps=eps, field_shape=field_shape, H0=H0, f=f,
                      renorm=renorm, axis=[axis], m0=[[1.0, 0, 0]])
