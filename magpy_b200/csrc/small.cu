@@ -79,7 +79,7 @@ __device__ __forceinline__ void sample_outputs(const RunParams& P, const V3 (&m)
 // ---------------------------------------------------------------------------------
 // Heun
 // ---------------------------------------------------------------------------------
-template <int NOISE, bool FIELD_TAB, int N>
+template <int NOISE, bool FIELD_TAB, int N, bool RENORM>
 __global__ void __launch_bounds__(SMALL_THREADS) heun_small_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SMALL_THREADS / 32) * 4];
     __shared__ __align__(32) double sd[N * N * 4];
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) heun_small_kernel(const __grid_
     const uint64_t r_raw = (uint64_t)blockIdx.x * SMALL_THREADS + threadIdx.x;
     const bool live = r_raw < P.R;
     const uint64_t r = live ? r_raw : P.R - 1;
-    const bool inter = P.interactions != 0, renorm = P.renorm != 0;
+    const bool inter = P.interactions != 0;
 
     V3 m[N], e[N];
     double kdt[N], c[N];
@@ -133,54 +133,69 @@ __global__ void __launch_bounds__(SMALL_THREADS) heun_small_kernel(const __grid_
             const V3 h{fma(0.5, m[i].x, hm.x), fma(0.5, m[i].y, hm.y), fma(0.5, m[i].z, hm.z)};
             m[i] = V3{fma(-hm.y, u.z, fma(hm.z, u.y, h.x)), fma(-hm.z, u.x, fma(hm.x, u.z, h.y)),
                       fma(-hm.x, u.y, fma(hm.y, u.x, h.z))};
-            if (renorm) renormalise(m[i]);
+            if (RENORM) renormalise(m[i]);
         }
     };
 
     uint64_t j = P.j0;
-    float carry[N][3];   // packed noise: increments of the odd step of the current Philox blocks
+    // Packed noise: g6[i] holds the six increments of particle i from Philox block `gblk` (steps 2 gblk and
+    // 2 gblk + 1) while `have` is set; it is carried across sample boundaries.  For N <= 2 the pair loop is
+    // software pipelined like K1 (the next block is generated inside the body that integrates the current one).
+    float g6[N][6];
+    uint32_t gblk = 0;
+    bool have = false;
+    auto generate = [&](const uint32_t blk, float (&out)[N][6]) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) carry[i][0] = carry[i][1] = carry[i][2] = 0.f;
-    if (NOISE == NOISE_PHILOX_PACKED && (j & 1)) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            float g6[6];
-            philox_gauss6_f32(key0, key1, j >> 1, (uint32_t)i, member, bm[i], g6);
-            carry[i][0] = g6[3]; carry[i][1] = g6[4]; carry[i][2] = g6[5];
+        for (int i = 0; i < N; ++i) philox_gauss6_f32(key0, key1, blk, (uint32_t)i, member, bm[i], out[i]);
+    };
+    auto need = [&](const uint32_t blk) {
+        if (!have || gblk != blk) {
+            generate(blk, g6);
+            gblk = blk;
+            have = true;
         }
-    }
+    };
+    auto half_step = [&](const int hlf, const uint64_t jj) {
+        V3 cw[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            cw[i] = V3{widen_f32(g6[i][3 * hlf]), widen_f32(g6[i][3 * hlf + 1]), widen_f32(g6[i][3 * hlf + 2])};
+        advance(cw, jj);
+    };
+    constexpr bool PIPELINED = N <= 2;
     for (uint32_t k = P.k0; k <= P.k1; ++k) {
         const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
         if (NOISE == NOISE_PHILOX_PACKED) {
-            V3 cw[N];
             if ((j & 1) && j < tgt) {
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    cw[i] = V3{widen_f32(carry[i][0]), widen_f32(carry[i][1]), widen_f32(carry[i][2])};
-                advance(cw, j);
+                need((uint32_t)(j >> 1));
+                half_step(1, j);
                 ++j;
             }
-            for (; j + 2 <= tgt; j += 2) {
-                float g6[N][6];
+            const uint32_t pairs = (uint32_t)((tgt - j) >> 1);
+            uint32_t blk = (uint32_t)(j >> 1);
+            if (pairs != 0) need(blk);
+            for (uint32_t i = pairs; i != 0; --i, j += 2) {
+                if (PIPELINED) {
+                    float gn[N][6];
+                    generate(++blk, gn);
+                    half_step(0, j);
+                    half_step(1, j + 1);
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    philox_gauss6_f32(key0, key1, j >> 1, (uint32_t)i, member, bm[i], g6[i]);
-                    cw[i] = V3{widen_f32(g6[i][0]), widen_f32(g6[i][1]), widen_f32(g6[i][2])};
+                    for (int p = 0; p < N; ++p)
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) g6[p][q] = gn[p][q];
+                    gblk = blk;
+                } else {
+                    half_step(0, j);
+                    half_step(1, j + 1);
+                    ++blk;
+                    if (i > 1) { generate(blk, g6); gblk = blk; }
+                    else have = false;
                 }
-                advance(cw, j);
-#pragma unroll
-                for (int i = 0; i < N; ++i) cw[i] = V3{widen_f32(g6[i][3]), widen_f32(g6[i][4]), widen_f32(g6[i][5])};
-                advance(cw, j + 1);
             }
             if (j < tgt) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    float g6[6];
-                    philox_gauss6_f32(key0, key1, j >> 1, (uint32_t)i, member, bm[i], g6);
-                    cw[i] = V3{widen_f32(g6[0]), widen_f32(g6[1]), widen_f32(g6[2])};
-                    carry[i][0] = g6[3]; carry[i][1] = g6[4]; carry[i][2] = g6[5];
-                }
-                advance(cw, j);
+                need((uint32_t)(j >> 1));
+                half_step(0, j);
                 ++j;
             }
         } else {
@@ -323,10 +338,20 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
 template <int NOISE, bool TAB>
 static cudaError_t launch_hsm(unsigned N, unsigned grid, cudaStream_t s, const RunParams& P) {
     const dim3 g(grid), b(SMALL_THREADS);
+    const bool renorm = P.renorm != 0;
     switch (N) {
-        case 2: heun_small_kernel<NOISE, TAB, 2><<<g, b, 0, s>>>(P); break;
-        case 3: heun_small_kernel<NOISE, TAB, 3><<<g, b, 0, s>>>(P); break;
-        case 4: heun_small_kernel<NOISE, TAB, 4><<<g, b, 0, s>>>(P); break;
+        case 2:
+            if (renorm) heun_small_kernel<NOISE, TAB, 2, true><<<g, b, 0, s>>>(P);
+            else heun_small_kernel<NOISE, TAB, 2, false><<<g, b, 0, s>>>(P);
+            break;
+        case 3:
+            if (renorm) heun_small_kernel<NOISE, TAB, 3, true><<<g, b, 0, s>>>(P);
+            else heun_small_kernel<NOISE, TAB, 3, false><<<g, b, 0, s>>>(P);
+            break;
+        case 4:
+            if (renorm) heun_small_kernel<NOISE, TAB, 4, true><<<g, b, 0, s>>>(P);
+            else heun_small_kernel<NOISE, TAB, 4, false><<<g, b, 0, s>>>(P);
+            break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
