@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MAGPY_B200_ABI_VERSION 1
+#define MAGPY_B200_ABI_VERSION 2
 
 /* status codes */
 #define MAGPY_B200_OK 0
@@ -101,6 +101,12 @@ typedef struct magpy_b200_ensemble {
     double* out_sums;                /* [S][4]: sum over members of cluster-summed Mx,My,Mz
                                         and of (cluster Mz)^2, A/m                            */
     double* out_final;               /* [R][N][3] state at the last sample, A/m               */
+    /* Coarsened noise for convergence studies on common Brownian paths (test/convergence/task5.cpp:
+     * 150-158: "coarse increments are sums of fine ones"): with L = noise_coarsen_log2 > 0 the unit-variance
+     * increment of step s is 2^(-L/2) times the sum of the 2^L increments the packed Philox stream
+     * (MAGPY_B200_GAUSS_F32_PACKED) assigns to the fine steps s 2^L ... (s+1) 2^L - 1, so runs with
+     * time_step = dt 2^L, L = 0, 1, 2, ... see the same Wiener path.  Single-particle ensembles only. */
+    uint32_t noise_coarsen_log2;
 } magpy_b200_ensemble;
 
 typedef struct magpy_b200_plan magpy_b200_plan; /* opaque: device-resident ensemble */

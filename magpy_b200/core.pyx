@@ -82,6 +82,7 @@ cdef extern from "magpy_b200.h" nogil:
         double* out_trajectories
         double* out_sums
         double* out_final
+        uint32_t noise_coarsen_log2
 
     ctypedef struct magpy_b200_plan:
         pass
@@ -250,7 +251,7 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
                                max_samples, seeds, str field_shape, double field_amplitude,
                                double field_frequency, double implicit_tol, int device, stream_offset,
                                bint return_trajectories, bint return_sums, bint return_final, str gauss,
-                               injected_dw):
+                               injected_dw, int noise_coarsen_log2=0):
     cdef _EnsembleArgs e = _EnsembleArgs()
     cdef np.ndarray[double, ndim=1, mode='c'] c_radius = np.ascontiguousarray(radius, dtype=np.float64).reshape(-1)
     cdef size_t N = c_radius.shape[0]
@@ -303,6 +304,9 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
     e.a.seeds = <const int64_t*> &c_seeds[0]
     e.a.stream_offset = int(stream_offset)
     e.a.gauss_mode = _GAUSS_LOOKUP[gauss]
+    if noise_coarsen_log2 < 0:
+        raise ValueError('noise_coarsen_log2 must be >= 0')
+    e.a.noise_coarsen_log2 = noise_coarsen_log2
     if injected_dw is not None:
         dw = np.ascontiguousarray(injected_dw, dtype=np.float64)
         if dw.ndim != 3 or dw.shape[0] != R or dw.shape[2] != 3 * N:
@@ -340,11 +344,16 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
                       bint use_implicit, double time_step, double end_time, max_samples, seeds,
                       str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
                       double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=True,
-                      bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None, devices=None):
+                      bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None, devices=None,
+                      int noise_coarsen_log2=0):
     """Integrate R = len(seeds) independent members of one cluster in a single call.
 
     `devices` (list of CUDA ordinals, or 'all') shards the members over several GPUs of this box from this one
     process (magpy_b200_simulate_ensemble_multi); `device` is then ignored.
+
+    `noise_coarsen_log2` = L > 0 (single-particle ensembles, gauss='f32p'): the increment of step s is the
+    normalised sum of the 2^L increments the L = 0 stream gives to steps s 2^L ... (s+1) 2^L - 1, so runs with
+    time_step * 2^L see the same Brownian paths (convergence studies, test/convergence/task5.cpp:150-158).
 
     `anisotropy_axis` and `magnetisation_direction` are (N,3) (shared) or (R,N,3).
     Returns a dict with 'time' [S], 'field' [S], 'trajectories' [R,N,3,S] | None,
@@ -355,7 +364,7 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
                                        magnetisation, damping, temperature, renorm, interactions, use_implicit,
                                        time_step, end_time, max_samples, seeds, field_shape, field_amplitude,
                                        field_frequency, implicit_tol, device, stream_offset, return_trajectories,
-                                       return_sums, return_final, gauss, injected_dw)
+                                       return_sums, return_final, gauss, injected_dw, noise_coarsen_log2)
     cdef magpy_b200_stats st
     cdef int rc
     cdef np.ndarray[int, ndim=1, mode='c'] c_dev

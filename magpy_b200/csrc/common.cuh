@@ -26,7 +26,7 @@
 
 namespace mb {
 
-enum { NOISE_PHILOX_F32 = 0, NOISE_PHILOX_F64 = 1, NOISE_INJECTED = 2, NOISE_PHILOX_PACKED = 3 };
+enum { NOISE_PHILOX_F32 = 0, NOISE_PHILOX_F64 = 1, NOISE_INJECTED = 2, NOISE_PHILOX_PACKED = 3, NOISE_PHILOX_COARSE = 4 };
 
 struct RunParams {
     uint64_t R;       // members on this device
@@ -43,6 +43,7 @@ struct RunParams {
     uint64_t axis_cs, axis_rs;  // component stride, member stride
     const int64_t* seeds;       // [R]
     uint64_t stream_offset;
+    uint32_t coarsen_log2;      // NOISE_PHILOX_COARSE: step s sums the packed stream's fine steps s 2^L .. (s+1) 2^L - 1
     double* state;              // [n][R]
     const uint64_t* target;     // [S] state index stored by sample k
     uint64_t j0, j1;            // advance the state from index j0 to j1
@@ -68,7 +69,21 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int NOISE>
 __device__ __forceinline__ V3 draw_noise(const RunParams& P, uint32_t k0, uint32_t k1, uint64_t j, uint32_t particle,
                                          uint32_t member, uint64_t r) {
-    if (NOISE == NOISE_INJECTED) {
+    if (NOISE == NOISE_PHILOX_COARSE) {
+        // L >= 1: the 2^L fine steps of coarse step j are the 2^(L-1) whole blocks j 2^(L-1) ... of the packed stream
+        const uint32_t L = P.coarsen_log2;
+        const uint64_t nb = 1ull << (L - 1), b0 = j << (L - 1);
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (uint64_t b = 0; b < nb; ++b) {
+            float g[6];
+            philox_gauss6_f32(k0, k1, b0 + b, particle, member, MB_NEG_2LN2, g);
+            ax += (double)g[0] + (double)g[3];
+            ay += (double)g[1] + (double)g[4];
+            az += (double)g[2] + (double)g[5];
+        }
+        const double sc = exp2(-0.5 * (double)L);
+        return V3{sc * ax, sc * ay, sc * az};
+    } else if (NOISE == NOISE_INJECTED) {
         const uint64_t n = 3ull * P.N;
         const double* row = P.dW + ((j - P.dW_j0) * n + 3ull * particle) * P.R + r;
         return V3{row[0], row[P.R], row[2 * P.R]};

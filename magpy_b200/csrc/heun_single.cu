@@ -165,6 +165,7 @@ cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, unsigned grid, 
         case NOISE_PHILOX_F32: launch_hs<NOISE_PHILOX_F32>(tab, axis_z, grid, s, P); break;
         case NOISE_PHILOX_F64: launch_hs<NOISE_PHILOX_F64>(tab, axis_z, grid, s, P); break;
         case NOISE_INJECTED: launch_hs<NOISE_INJECTED>(tab, axis_z, grid, s, P); break;
+        case NOISE_PHILOX_COARSE: launch_hs<NOISE_PHILOX_COARSE>(tab, axis_z, grid, s, P); break;
         default: launch_hs<NOISE_PHILOX_PACKED>(tab, axis_z, grid, s, P); break;
     }
     return cudaGetLastError();

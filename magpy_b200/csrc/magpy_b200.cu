@@ -179,6 +179,7 @@ struct magpy_b200_plan {
     uint64_t S = 0;
     bool implicit = false, want_traj = false, injected = false;
     int gauss_mode = 0, field_shape = MAGPY_B200_FIELD_CONSTANT;
+    uint32_t coarsen = 0;   // noise_coarsen_log2
     double Ms = 0;
     Reduced red;
     std::vector<uint64_t> target;   // state index stored by sample k
@@ -230,6 +231,7 @@ namespace {
 
 int plan_noise(const magpy_b200_plan* pl) {
     if (pl->injected) return mb::NOISE_INJECTED;
+    if (pl->coarsen > 0) return mb::NOISE_PHILOX_COARSE;
     if (pl->gauss_mode == MAGPY_B200_GAUSS_F64) return mb::NOISE_PHILOX_F64;
     if (pl->gauss_mode == MAGPY_B200_GAUSS_F32) return mb::NOISE_PHILOX_F32;
     return mb::NOISE_PHILOX_PACKED;
@@ -289,6 +291,11 @@ int validate(const magpy_b200_ensemble* a) {
         a->gauss_mode != MAGPY_B200_GAUSS_F32_PACKED)
         return fail(MAGPY_B200_ERR_BAD_ARG, "gauss_mode must be MAGPY_B200_GAUSS_F32, _F64 or _F32_PACKED");
     if (!(a->magnetisation > 0.0)) return fail(MAGPY_B200_ERR_BAD_ARG, "magnetisation must be > 0");
+    if (a->noise_coarsen_log2 > 0) {
+        if (a->n_particles != 1 || a->injected_dw || a->gauss_mode != MAGPY_B200_GAUSS_F32_PACKED)
+            return fail(MAGPY_B200_ERR_BAD_ARG, "noise_coarsen_log2 needs a single-particle ensemble with the packed Philox stream");
+        if (a->noise_coarsen_log2 > 20) return fail(MAGPY_B200_ERR_BAD_ARG, "noise_coarsen_log2 must be <= 20");
+    }
     if (a->use_implicit) {
         if (a->n_particles > 32) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 32 particles per cluster");
     } else if (a->n_particles > 128) {
@@ -309,6 +316,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     pl->S = a->max_samples;
     pl->implicit = a->use_implicit != 0;
     pl->gauss_mode = a->gauss_mode;
+    pl->coarsen = a->noise_coarsen_log2;
     pl->field_shape = a->field_shape;
     pl->Ms = a->magnetisation;
     pl->injected = a->injected_dw != nullptr;
@@ -548,6 +556,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.axis_rs = a->axis_stride ? 1 : 0;
     P.seeds = pl->d_seeds.p;
     P.stream_offset = a->stream_offset;
+    P.coarsen_log2 = a->noise_coarsen_log2;
     P.state = pl->d_state.p;
     P.target = pl->d_target.p;
     P.field_tab = pl->d_tab.p;

@@ -185,3 +185,32 @@ def test_single_simulate_api_and_schedule_edges(orc, core):
     with pytest.raises(ValueError):
         core.simulate(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True, False,
                       c.dt, c.t_end, 1, 1234)
+
+
+@pytest.mark.parametrize('implicit', [False, True])
+def test_coarsened_noise_is_the_sum_of_the_fine_stream(core, implicit):
+    """noise_coarsen_log2 = L: step s is driven by 2^(-L/2) times the sum of the packed Philox increments of the
+    fine steps s 2^L ... (s+1) 2^L - 1 (test/convergence/task5.cpp:150-158) — checked against an injected-noise
+    run fed with exactly those sums, built on the host from the device's own fine stream."""
+    L, n_coarse, R = 3, 40, 6
+    n_fine = n_coarse << L
+    c = ol.make_case(N=1, radius=6e-9, dt=2e-13, t_end=2e-13 * n_coarse * (1 + 1e-9), S=2, implicit=implicit,
+                     axis=[[0, 0, 1.0]], m0=[[0.6, 0, 0.8]])
+    seeds = np.array([11, 22, 33, 44, 55, 66])
+    offset = 1000
+    fine = np.stack([core.gaussians(int(s), offset + i, 0, 1, n_fine, gauss='f32p') for i, s in enumerate(seeds)])
+    coarse = fine.reshape(R, n_coarse, 1 << L, 3).sum(axis=2) / np.sqrt(1 << L)
+    coarse = np.concatenate([coarse, np.zeros((R, 2, 3))], axis=1)
+    a = gpu_run(core, c, seeds, dW=coarse)
+    b = gpu_run(core, c, seeds, stream_offset=offset, noise_coarsen_log2=L)
+    assert a['stats']['steps_per_member'] == b['stats']['steps_per_member'] == n_coarse
+    assert np.abs(a['final'] - b['final']).max() / c.Ms < 1e-12
+    # L = 0 is the production stream itself, up to fp32 rounding of every increment: the production kernels fold the
+    # amplitude sigma sqrt(dt) into the fp32 Box-Muller radius, the coarsened sums scale unit draws in fp64
+    c0 = ol.Case(dict(c, dt=c.dt / (1 << L)))
+    f = np.concatenate([fine, np.zeros((R, 2, 3))], axis=1)
+    a0 = gpu_run(core, c0, seeds, dW=f)
+    b0 = gpu_run(core, c0, seeds, stream_offset=offset)
+    assert np.abs(a0['final'] - b0['final']).max() / c.Ms < 1e-7
+    with pytest.raises(ValueError):
+        gpu_run(core, ol.make_case(N=2), seeds, noise_coarsen_log2=1)
