@@ -214,3 +214,30 @@ def test_coarsened_noise_is_the_sum_of_the_fine_stream(core, implicit):
     assert np.abs(a0['final'] - b0['final']).max() / c.Ms < 1e-7
     with pytest.raises(ValueError):
         gpu_run(core, ol.make_case(N=2), seeds, noise_coarsen_log2=1)
+
+
+@pytest.mark.parametrize('N,implicit', [(1, False), (3, False), (6, False), (40, False), (1, True), (2, True), (6, True)])
+def test_every_kernel_family_consumes_the_same_philox_stream(core, N, implicit, monkeypatch):
+    """The increment of (seed, member, particle, step) is one function — the one `core.gaussians` exposes and
+    tests/test_parity_gpu.py checks against the oracle — whichever kernel consumes it: pipelined pairs (single
+    particle), blocks carried across sample boundaries (one thread per cluster), pairwise or per-step access
+    (shared-memory clusters), with odd chunk and sample boundaries.  A production (Philox) run therefore equals an
+    injected-noise run fed with `core.gaussians` up to the fp32 rounding of the Heun kernels' folded amplitude."""
+    monkeypatch.setenv('MAGPY_B200_MAX_CHUNK_STEPS', '7')
+    rng = np.random.default_rng(50 + N)
+    c = ol.make_case(N=N, radius=7e-9, anisotropy=1e5, dt=2e-13 if not implicit else 1e-12, S=6, implicit=implicit,
+                     T=330.0, rng=rng)
+    n_steps = 45
+    c['t_end'] = c.dt * n_steps * (1 + 1e-9)
+    seeds = np.array([3, 1 << 33, 77, 2 ** 31 - 1, 12345])
+    offset = 17
+    dW = np.zeros((len(seeds), n_steps + 2, 3 * N))
+    for i, s in enumerate(seeds):
+        for p in range(N):
+            dW[i, :n_steps, 3 * p:3 * p + 3] = core.gaussians(int(s), offset + i, p, 1, n_steps, gauss='f32p')
+    a = gpu_run(core, c, seeds, dW=dW)
+    b = gpu_run(core, c, seeds, stream_offset=offset)
+    assert a['stats']['steps_per_member'] == b['stats']['steps_per_member'] == n_steps
+    assert b['stats']['kernel_launches'] > 6
+    err = np.abs(a['trajectories'] - b['trajectories']).max() / c.Ms
+    assert err < (1e-7 if not implicit else 1e-11), err
