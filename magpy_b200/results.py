@@ -32,32 +32,26 @@ class Results:
         self.N = N
 
     def plot(self):
-        """Plot x,y,z of every particle (magpy/results.py:37-59); needs matplotlib."""
-        import matplotlib.pyplot as plt
-        fg, axs = plt.subplots(nrows=self.N)
-        if self.N == 1:
-            axs = [axs]
-        for idx in range(self.N):
-            axs[idx].plot(self.time, self.x[idx], label='x')
-            axs[idx].plot(self.time, self.y[idx], label='y')
-            axs[idx].plot(self.time, self.z[idx], label='z')
-            axs[idx].legend()
-            axs[idx].set_title('Particle {}'.format(idx))
-            axs[idx].set_xlabel('Reduced time [dimless]')
-            fg.tight_layout()
-        return fg
+        """One panel per particle with its three magnetisation components against time
+        (same figure as magpy/results.py:37-59); needs matplotlib."""
+        from matplotlib import pyplot
+        figure, panels = pyplot.subplots(nrows=self.N, squeeze=False)
+        for particle, panel in enumerate(panels[:, 0]):
+            for name in 'xyz':
+                panel.plot(self.time, getattr(self, name)[particle], label=name)
+            panel.set_title('Particle {}'.format(particle))
+            panel.set_xlabel('Reduced time [dimless]')
+            panel.legend()
+        figure.tight_layout()
+        return figure
 
     def magnetisation(self, direction='z'):
         """Total (summed over particles) magnetisation along `direction` (magpy/results.py:61-75)."""
         return np.sum([vals for vals in getattr(self, direction).values()], axis=0)
 
     def final_state(self):
-        """Last sample of every particle (magpy/results.py:77-91)."""
-        return {
-            'x': {k: v[-1] for k, v in self.x.items()},
-            'y': {k: v[-1] for k, v in self.y.items()},
-            'z': {k: v[-1] for k, v in self.z.items()},
-        }
+        """Last sample of every particle (magpy/results.py:77-91): {'x': {id: value}, 'y': ..., 'z': ...}."""
+        return {name: {pid: series[-1] for pid, series in getattr(self, name).items()} for name in 'xyz'}
 
 
 class _LazyResults:
