@@ -54,6 +54,23 @@ class Results:
         return {name: {pid: series[-1] for pid, series in getattr(self, name).items()} for name in 'xyz'}
 
 
+def save_results(fname, results, particle=0):
+    """Write one particle of a :class:`Results` to disk in the reference's raw format
+    (lib/simulation.cpp:38-63, include/io.hpp:12-27): native-endian float64 arrays, no header, in the five
+    files `fname.mx`, `fname.my`, `fname.mz`, `fname.field`, `fname.time`."""
+    for suffix, arr in (('mx', results.x[particle]), ('my', results.y[particle]), ('mz', results.z[particle]),
+                        ('field', results.field), ('time', results.time)):
+        np.ascontiguousarray(arr, dtype=np.float64).tofile('%s.%s' % (fname, suffix))
+
+
+def load_results(fname):
+    """Read the five raw float64 files written by :func:`save_results` (or by the reference's
+    `simulation::save_results`) back into a single-particle :class:`Results`."""
+    arr = {suffix: np.fromfile('%s.%s' % (fname, suffix), dtype=np.float64)
+           for suffix in ('mx', 'my', 'mz', 'field', 'time')}
+    return Results(arr['time'], arr['field'], {0: arr['mx']}, {0: arr['my']}, {0: arr['mz']}, 1)
+
+
 class _LazyResults:
     """Sequence of per-member ``Results`` views over one [R, N, 3, S] array."""
     def __init__(self, time, field, traj):

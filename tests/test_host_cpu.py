@@ -165,6 +165,24 @@ def test_results_api_matches_reference_semantics():
     assert np.allclose(se, traj[:, :, 2].sum(1).std(axis=0, ddof=1) / np.sqrt(R))
 
 
+def test_results_persistence_round_trip(tmp_path):
+    import pickle
+    from magpy_b200.results import save_results, load_results, EnsembleResults
+    time, field, traj, sums = _fake_results(R=4, N=2, S=7)
+    ens = EnsembleResults.from_arrays(time, field, 4, trajectories=traj, sums=sums, final=traj[..., -1])
+    prefix = str(tmp_path / 'member3')
+    save_results(prefix, ens.results[3], particle=1)
+    # raw native float64, no header: the reference's io::write_array (include/io.hpp:12-27)
+    assert os.path.getsize(prefix + '.mz') == 7 * 8
+    back = load_results(prefix)
+    assert np.array_equal(back.z[0], traj[3, 1, 2]) and np.array_equal(back.time, time)
+    assert np.array_equal(back.field, field) and back.N == 1
+    # magpy/data.py shelves pickles of the results: the array-backed ensemble survives a round trip
+    again = pickle.loads(pickle.dumps(ens))
+    assert np.array_equal(again.ensemble_magnetisation(), ens.ensemble_magnetisation())
+    assert np.array_equal(again.results[2].x[1], traj[2, 1, 0])
+
+
 def test_sar_is_cycle_energy_times_frequency_over_density():
     from magpy_b200.results import EnsembleResults
     from magpy_b200.core import get_mu0
