@@ -42,8 +42,12 @@ __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V
               fma(-hm.x, u.y, fma(hm.y, u.x, h.z))};
 }
 
+#ifndef MB_K1_MIN_BLOCKS
+#define MB_K1_MIN_BLOCKS 1   // resident CTAs per SM the register allocation must allow (tuning knob)
+#endif
+
 template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool RENORM>
-__global__ void __launch_bounds__(SINGLE_THREADS) heun_single_kernel(const __grid_constant__ RunParams P) {
+__global__ void __launch_bounds__(SINGLE_THREADS, MB_K1_MIN_BLOCKS) heun_single_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
     const bool live = r_raw < P.R;

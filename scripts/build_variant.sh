@@ -1,13 +1,23 @@
 #!/bin/bash
-# Build an experimental variant of the library with extra nvcc flags into variants/<name>/magpy_b200
-# (git-ignored; travels to the GPU box).  Usage: scripts/build_variant.sh <name> [-DFLAG ...]
-#   then on the box:  MB_ROOT=variants/<name> python scripts/probe2.py
+# Build an experimental variant of the library into variants/<name>/magpy_b200 (git- and gpurun-ignored... the
+# latter only if you remove `variants/` from .gpurunignore for the experiment).
+#   scripts/build_variant.sh <name> <unit.cu> [extra nvcc flags for that unit ...]
+#   on the box:  MB_ROOT=variants/<name> python scripts/probe2.py f32p
 set -e
-name=$1; shift
+name=$1; unit=$2; shift 2
 root=$(cd "$(dirname "$0")/.." && pwd)
+src=$root/magpy_b200/csrc
 dst=$root/variants/$name/magpy_b200
-mkdir -p $dst
+mkdir -p $dst/obj
 cp $root/magpy_b200/*.py $root/magpy_b200/core*.so $dst/
-nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" \
-    -shared -o $dst/libmagpy_b200.so $root/magpy_b200/csrc/magpy_b200.cu -lcudart
+objs=""
+for u in magpy_b200 heun_single imid_single small cluster service; do
+    if [ "$u.cu" == "$unit" ]; then
+        nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -c -o $dst/obj/$u.o $src/$u.cu
+        objs="$objs $dst/obj/$u.o"
+    else
+        objs="$objs $src/build/$u.o"
+    fi
+done
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $dst/libmagpy_b200.so $objs -lcudart
 echo built $dst
