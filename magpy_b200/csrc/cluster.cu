@@ -1,6 +1,13 @@
 #include "common.cuh"
 #include "launch.h"
 
+#ifndef MB_DIP_UNROLL
+#define MB_DIP_UNROLL 2   // unroll factor of the j loop of the dipolar sum (tuning knob)
+#endif
+#define MB_PRAGMA_STR(x) #x
+#define MB_PRAGMA(x) _Pragma(MB_PRAGMA_STR(x))
+#define MB_DIP_UNROLL_PRAGMA MB_PRAGMA(unroll MB_DIP_UNROLL)
+
 namespace mb {
 
 // ---------------------------------------------------------------------------------
@@ -30,7 +37,7 @@ __device__ __forceinline__ void add_dipolar(V3 (&h)[NP], const uint32_t (&p)[NP]
     const double2* row[NP];
 #pragma unroll
     for (int q = 0; q < NP; ++q) row[q] = reinterpret_cast<const double2*>(dip) + (uint64_t)p[q] * N * 2;
-#pragma unroll 2
+    MB_DIP_UNROLL_PRAGMA
     for (uint32_t jq = 0; jq < N; ++jq) {
         const double* mj = sm + (uint64_t)jq * 3 * CL_LANES + lane;
         const double mx = mj[0], my = mj[CL_LANES], mz = mj[2 * CL_LANES];
