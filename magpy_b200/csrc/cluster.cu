@@ -67,6 +67,21 @@ __device__ __forceinline__ V3 cluster_field(const RunParams& P, const double* sm
     return h[0];
 }
 
+// effective fields of ALL own particles of the implicit kernel: anisotropy + applied, then one pass of the
+// j-outer dipolar sum that reads every shared-memory moment once for all of them
+template <int NP>
+__device__ __forceinline__ void own_fields(V3 (&h)[NP], const RunParams& P, const double* sm, const double* dip_smem,
+                                           const Own (&own)[NP], const V3 (&x)[NP], const double hz, const int lane) {
+    uint32_t pid[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const double s = dot(x[q], own[q].e) * own[q].kred;
+        h[q] = V3{s * own[q].e.x, s * own[q].e.y, fma(s, own[q].e.z, hz)};
+        pid[q] = own[q].p;
+    }
+    if (P.interactions) add_dipolar<NP, true>(h, pid, sm, dip_smem, P.N, lane);
+}
+
 // K2: Heun.  Per step: fields of the own particles from sm_m -> predictor moments into sm_t -> barrier ->
 // fields from sm_t -> corrected moments into sm_m -> barrier.  Same fused arithmetic as K1.
 //
@@ -334,7 +349,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
             double part = 0.0;
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                if (!own[q].valid) continue;
+                if (!own[q].valid) { X[q] = m[q]; continue; }   // padding slot: defined, never stored
                 const V3 w = draw_noise<NOISE>(P, key0, key1, j, own[q].p, member, r);
                 wm[q] = V3{fmax(-clampA, fmin(clampA, w.x)) * sqrt_dt, fmax(-clampA, fmin(clampA, w.y)) * sqrt_dt,
                            fmax(-clampA, fmin(clampA, w.z)) * sqrt_dt};
@@ -361,13 +376,14 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
                 if (active) { active = iter > 0; --iter; }
                 // barrier + vote: also orders the previous iteration's sm_x / sm_red traffic
                 if (!__syncthreads_or(active ? 1 : 0)) break;
-                V3 dl[NP];
+                V3 dl[NP], hq[NP];
+                own_fields<NP>(hq, P, sm_x, sm_tab, own, X, hz1, lane);
                 bool ok = true;
                 part = 0.0;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     if (!own[q].valid) continue;
-                    const V3 h = cluster_field(P, sm_x, sm_tab, own[q], X[q], hz1, lane);
+                    const V3 h = hq[q];
                     const V3 g{fma(h.x, dt, sw[q].x), fma(h.y, dt, sw[q].y), fma(h.z, dt, sw[q].z)};
                     const V3 f = llg_f(X[q], g, alpha);
                     double b[3] = {-(X[q].x - m[q].x - 0.5 * f.x), -(X[q].y - m[q].y - 0.5 * f.y),

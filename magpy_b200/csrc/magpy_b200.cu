@@ -355,7 +355,9 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         pl->np = 1;
     } else {
         const uint32_t max_slots = pl->implicit ? 8 : 16;
-        int np = pl->implicit ? 1 : 2;   // Heun: >= 2 own particles per thread reuse every shared-memory moment read
+        // >= 2 own particles per thread reuse every shared-memory moment read of the dipolar sum; the implicit kernel's
+        // per-particle Newton work dominates below 8 particles, where one particle per thread (no padding slot) is faster
+        int np = (pl->implicit && N < 8) ? 1 : 2;
         while ((N + np - 1) / np > max_slots) np *= 2;
         pl->np = np;
         const uint32_t slots = (N + np - 1) / np;
