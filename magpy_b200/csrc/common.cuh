@@ -10,14 +10,16 @@
 //   field_tab [steps][2]    applied field at the two evaluation times of every step
 //   dW        [steps][n][R] injected unit-variance increments (parity mode only)
 //
-// K1 heun_single      one thread per member, N = 1, state in fp64 registers
-// K3 imid_single      same mapping, implicit midpoint with the reference's quasi-Newton
-// K2 heun_cluster     one warp-wide CTA row per particle slot: lanes = 32 members,
-//                     threadIdx.y = particle slot; moments staged in shared memory for
-//                     the all-pairs dipolar sum
-// K4 imid_cluster     same mapping; block-diagonal quasi-Newton, CTA-wide convergence
-// K5 ensemble sums    fused into K1-K4 (warp shuffle -> smem -> per-CTA partial) +
-//                     reduce_partials (fixed-order, deterministic)
+//   dip       [N][N][4]     static pair table {sqrt(3) r_hat_ij, c_dip v_j / cube_ij}, zero diagonal
+//
+// K1 heun_single  (heun_single.cu)  one thread per member, N = 1, state in fp64 registers
+// K3 imid_single  (imid_single.cu)  same mapping, implicit midpoint with the reference's quasi-Newton
+// K2s/K4s *_small (small.cu)        N = 2..4: one thread per cluster, all moments in registers
+// K2 heun_cluster (cluster.cu)      N = 5..128: CTA = 32 members (lanes) x particle slots, 2/4/8 own particles
+//                                   per thread, moments (and the pair table, N <= 64) in shared memory
+// K4 imid_cluster (cluster.cu)      N = 5..32: same mapping; block-diagonal quasi-Newton, CTA-wide convergence
+// K5 ensemble sums                  fused into all of them (warp shuffle -> smem -> per-CTA partial) +
+//                                   reduce_partials (fixed order, deterministic)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -1,23 +1,24 @@
 // rng.cuh — in-kernel counter-based Gaussian stream (replaces lib/rng.cpp:14-24,
 // std::mt19937_64 + std::normal_distribution, which cannot be reproduced on the device
 // at speed).  Philox4x32-10 (Salmon et al. SC'11) is used as a pure function of
-//   counter = (step index [32 bit, like the reference's step counter], global member index,
-//              seed low word, seed high word)   -- the member's seed of magpy/model.py:202-203
-//   key     = (particle | block<<24, MB_PHILOX_KEY1)
+//   counter = (step index — or step-pair index in the packed mode — [32 bit, like the reference's step
+//              counter], global member index, seed low word, seed high word)
+//              -- the member's seed of magpy/model.py:202-203
+//   key     = (particle | mode/block tag << 24, MB_PHILOX_KEY1)
 // so the Wiener increment of (member, particle, step) does not depend on how the ensemble is
 // chunked in time, laid out over CTAs, or sharded over GPUs.  Everything that varies per thread
 // sits in the counter: the key schedule (20 adds per block) is warp-uniform and, for the
 // single-particle kernels, a compile-time constant.
 //
-// Two Gaussian transforms of the Philox words:
+// Three Gaussian transforms of the Philox words:
 //   GAUSS_F32: Box-Muller in fp32 on the otherwise idle FP32/SFU pipes, widened to fp64
 //              (keeps the FP64 pipe for the integrator).  One Philox call yields the 3 draws of
 //              a particle-step.
 //   GAUSS_F64: Box-Muller in fp64 from 53-bit uniforms (two Philox calls per particle-step).
-//   GAUSS_F32_PACKED: fp32 Box-Muller with 24-bit radius / 18-bit angle uniforms, so that one
-//              Philox block feeds TWO particle-steps (the integer multiplies of Philox share an
-//              issue port with DFMA on sm_100a — profiles/README.md — so halving them is what
-//              raises the FP64 pipe's share of the cycle).
+//   GAUSS_F32_PACKED (production default): fp32 Box-Muller with 23-bit radius / 18-bit angle
+//              uniforms, so that one Philox block feeds TWO particle-steps (the wide integer
+//              multiplies of Philox take FP64-pipe time on sm_100a — profiles/README.md — so halving
+//              them is what raises the FP64 pipe's share of the cycle).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
