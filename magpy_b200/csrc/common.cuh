@@ -1,5 +1,5 @@
 // common.cuh — shared declarations of the sm_100a kernels of the ensemble sLLG integrator
-// (kernels: heun_single.cu, imid_single.cu, small.cu, cluster.cu, service.cu; launchers: launch.h).
+// (kernels: heun_single.cu, imid_single.cu, small_heun.cu, small_imid.cu, cluster.cu, service.cu; launchers: launch.h).
 //
 // Data layout in HBM (R = members on this device, N = particles per cluster, n = 3N):
 //   state     [n][R]        fp64, member index fastest -> every load/store is coalesced
@@ -14,8 +14,8 @@
 //
 // K1 heun_single  (heun_single.cu)  one thread per member, N = 1, state in fp64 registers
 // K3 imid_single  (imid_single.cu)  same mapping, implicit midpoint with the reference's quasi-Newton
-// K2s/K4s *_small (small.cu)        N = 2..4: one thread per cluster, all moments in registers
-// K2 heun_cluster (cluster.cu)      N = 5..128: CTA = 32 members (lanes) x particle slots, 2/4/8 own particles
+// K2s/K4s *_small (small_*.cu)      Heun N = 2..7, implicit N = 2..4: one thread per cluster, moments in registers
+// K2 heun_cluster (cluster.cu)      N = 8..128: CTA = 32 members (lanes) x particle slots, 2/4/8 own particles
 //                                   per thread, moments (and the pair table, N <= 64) in shared memory
 // K4 imid_cluster (cluster.cu)      N = 5..32: same mapping; block-diagonal quasi-Newton, CTA-wide convergence
 // K5 ensemble sums                  fused into all of them (warp shuffle -> smem -> per-CTA partial) +

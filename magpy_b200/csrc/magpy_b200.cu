@@ -193,7 +193,7 @@ struct magpy_b200_plan {
     int layout = 0;        // Heun cluster kernel: see cluster.cu
     bool use_table = false;
     bool axis_z = false;   // N = 1 and one shared easy axis exactly along +z: specialised Heun kernel
-    bool small = false;    // 2 <= N <= 4: one thread per cluster, all moments in registers
+    bool small = false;    // few particles: one thread per cluster, all moments in registers
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
@@ -347,7 +347,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         pl->grid = (unsigned)((R + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
         pl->smem = 0;
         pl->np = 1;
-    } else if (N <= 4) {   // one thread per cluster (small.cu)
+    } else if (N <= 4 || (!pl->implicit && N <= 7)) {   // one thread per cluster (small_heun.cu: 2..7, small_imid.cu: 2..4)
         pl->small = true;
         pl->block = dim3(mb::SINGLE_THREADS);
         pl->grid = (unsigned)((R + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);

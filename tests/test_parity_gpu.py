@@ -138,11 +138,11 @@ def test_implicit_single_injected(orc, core, field_shape, H0, f, renorm, eps, ax
     assert out['stats']['newton_failures'] == 0
 
 
-# N = 2..4: one thread per cluster (small.cu); 5..32: two particles per thread, pair table in shared memory;
+# N = 2..7: one thread per cluster (small_heun.cu); 8..32: two particles per thread, pair table in shared memory;
 # 40: four per thread; 64: four per thread with ONE moment buffer next to the 128 KB table; 70: eight per
 # thread, table in global memory; 128: the largest supported cluster (cluster.cu)
 @pytest.mark.parametrize('N,interactions,renorm', [(2, True, False), (3, True, True), (4, True, True), (5, False, False),
-                                                   (8, True, False), (20, True, False), (40, True, False),
+                                                   (7, True, True), (8, True, False), (20, True, False), (40, True, False),
                                                    (64, True, False), (70, True, True), (128, True, False)])
 def test_heun_cluster_injected(orc, core, N, interactions, renorm):
     rng = np.random.default_rng(N)
