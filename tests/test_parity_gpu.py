@@ -216,7 +216,7 @@ def test_coarsened_noise_is_the_sum_of_the_fine_stream(core, implicit):
         gpu_run(core, ol.make_case(N=2), seeds, noise_coarsen_log2=1)
 
 
-@pytest.mark.parametrize('N,implicit', [(1, False), (3, False), (6, False), (40, False), (1, True), (2, True), (6, True)])
+@pytest.mark.parametrize('N,implicit', [(1, False), (3, False), (6, False), (12, False), (40, False), (1, True), (2, True), (6, True)])
 def test_every_kernel_family_consumes_the_same_philox_stream(core, N, implicit, monkeypatch):
     """The increment of (seed, member, particle, step) is one function — the one `core.gaussians` exposes and
     tests/test_parity_gpu.py checks against the oracle — whichever kernel consumes it: pipelined pairs (single
