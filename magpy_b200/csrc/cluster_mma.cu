@@ -1,0 +1,326 @@
+// cluster_mma.cu — K2m: Heun for interacting clusters with the dipolar field as a matrix product on the
+// FP64 MMA path (DMMA.8x8x4) of sm_100a.
+//
+// The all-pairs dipolar field (lib/field.cpp:187-225) of ONE member is a matrix-vector product with a matrix
+// that depends on the geometry only,
+//     H[(i,a)] = sum_{(j,b)} D[(i,a),(j,b)] M[(j,b)],   D = c_dip / cube_ij (3 r_a r_b - delta_ab),  M_j = v_red,j m_j,
+// and the geometry is shared by every member of the ensemble, so for a CTA's members it is the product
+// H[3N x members] = D[3N x 3N] . M[3N x members]: the same 9 FMA per ordered pair as the scalar loop of cluster.cu,
+// but issued as one DMMA per 256 FMA (instead of one DFMA per 32) and fed with 5 shared-memory operand loads per
+// 6 DMMA (instead of 11 per 36 DFMA).  Measured on B200 (profiles/r01_dmma_microbench.txt): DMMA.8x8x4 runs at
+// 16 cycles per SM sub-partition = the full rate of the FP64 pipe (37.1 TFLOP/s), also when fed from shared memory.
+//
+// Index order of the rows of D and of M: (particle group pg = p / 8, component a, g = p % 8) -> 24 pg + 8 a + g.
+// A warp owns one particle group (three 8-row tiles = x, y, z of 8 particles) and one 16-member half of the CTA's
+// members (two 8-column tiles), so that after the product thread (g, t) holds all three field components of
+// particle 8 pg + g for its four members 16 mh + 8 j + 2 t + e — exactly what the per-particle Heun update needs,
+// with no exchange between threads.
+//
+// D is symmetric (v_red is folded into M), so only the 24 x 24 blocks with pg <= kg are kept in shared memory
+// (N = 64: 36 blocks = 162 KB instead of 288 KB); a warp reads the blocks left of its diagonal transposed.  Inside
+// a block, element (i, c) sits at i * 24 + (c ^ 4 ((i >> 1) & 1)), which makes both the direct and the
+// transposed fragment loads bank-conflict free.
+//
+// Every group of warps that shares a 16-member half is an independent problem: it
+// synchronises on its own named barrier, so the halves drift out of phase and the update / noise phase of one
+// overlaps the matrix product of the others.
+#include "common.cuh"
+#include "launch.h"
+
+namespace mb {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void group_barrier(const int id, const int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+constexpr int MMA_BLK = 576;   // doubles per 24 x 24 block of D
+
+// acc[a][j][e] = H_a(particle 8 pg + g, member 16 mh + 8 j + 2 t + e)
+__device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double* __restrict__ sm_d,
+                                            const double* __restrict__ sm_b /* + 16 mh + g + t * LD */, const int G,
+                                            const int pg, const int LD, const int g, const int t) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
+    const int sg = (g >> 1) & 1, st4 = ((t >> 1) & 1) << 2;
+    const int off_direct = 24 * g + t, off_transp = 24 * t + (g ^ st4);
+    for (int kg = 0; kg < G; ++kg) {
+        const double* brow = sm_b + (size_t)(24 * kg) * LD;
+        if (kg >= pg) {
+            const double* blk = sm_d + (size_t)(pg * G - (pg * (pg - 1)) / 2 + (kg - pg)) * MMA_BLK + off_direct;
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks) {
+                double af[3], bf[2];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) af[a] = blk[192 * a + 4 * (ks ^ sg)];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bf[j] = brow[(size_t)(4 * ks) * LD + 8 * j];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma884(acc[a][j][0], acc[a][j][1], af[a], bf[j]);
+            }
+        } else {
+            const double* blk = sm_d + (size_t)(kg * G - (kg * (kg - 1)) / 2 + (pg - kg)) * MMA_BLK + off_transp;
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks) {
+                double af[3], bf[2];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) af[a] = blk[96 * ks + 8 * a];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bf[j] = brow[(size_t)(4 * ks) * LD + 8 * j];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma884(acc[a][j][0], acc[a][j][1], af[a], bf[j]);
+            }
+        }
+    }
+}
+
+// blockDim.x = 32 * G * MH.  Warp w: particle group pg = w % G, member half mh = w / G.
+template <int NOISE, bool FIELD_TAB, bool ONE_BUF>
+__global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_constant__ RunParams P) {
+    extern __shared__ double smem[];
+    const int N = (int)P.N, G = (int)P.G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int n_warps = blockDim.x >> 5, MH = n_warps / G, MB = 16 * MH, LD = MB + 4;
+    const int pg = warp % G, mh = warp / G;
+    const int n_blk = G * (G + 1) / 2;
+    double* sm_d = smem;                                              // [n_blk][576]
+    double* sm_m = sm_d + (size_t)n_blk * MMA_BLK;                    // [24 G][LD] current moments (times v_red)
+    double* sm_t = ONE_BUF ? sm_m : sm_m + (size_t)24 * G * LD;       // [24 G][LD] predictor moments
+    double* sm_red = sm_t + (size_t)24 * G * LD;                      // [G][3][MB] sample reduction
+    {
+        const int nd = n_blk * MMA_BLK;
+        for (int q = threadIdx.x; q < nd; q += blockDim.x) sm_d[q] = P.dmat[q];
+        const int nm = 24 * G * LD * (ONE_BUF ? 1 : 2);
+        for (int q = threadIdx.x; q < nm; q += blockDim.x) sm_m[q] = 0.0;   // rows of padding particles stay zero
+    }
+    __syncthreads();
+
+    const int p_raw = 8 * pg + g;
+    const bool valid = p_raw < N;
+    const uint32_t pid = valid ? (uint32_t)p_raw : 0u;
+    const double alpha = P.alpha, dt = P.dt;
+    const bool renorm = P.renorm != 0, inter = P.interactions != 0;
+    const double kred = __ldg(P.k_red + pid), vred = __ldg(P.v_red + pid);
+    const double csig = __ldg(P.sig + pid) * P.sqrt_dt;
+    const float bm = scale_to_bm(csig);
+    const int bar_id = 1 + mh, bar_n = 32 * G;
+
+    // the thread's four members: q = 2 j + e  ->  local column 16 mh + 8 j + 2 t + e
+    uint64_t r[4];
+    bool live[4];
+    V3 m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int col = 16 * mh + 8 * (q >> 1) + 2 * t + (q & 1);
+        const uint64_t r_raw = (uint64_t)blockIdx.x * MB + col;
+        live[q] = r_raw < P.R;
+        r[q] = live[q] ? r_raw : P.R - 1;
+        const uint64_t c0 = 3ull * pid;
+        m[q] = V3{P.state[c0 * P.R + r[q]], P.state[(c0 + 1) * P.R + r[q]], P.state[(c0 + 2) * P.R + r[q]]};
+    }
+    // own rows of the moment buffers: row(comp a) = 24 pg + 8 a + g, columns 16 mh + 8 j + 2 t + {0, 1}
+    const int own_off = (24 * pg + g) * LD + 16 * mh + 2 * t;
+    auto put = [&](double* buf, const V3 (&x)[4]) {
+        if (!valid) return;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double* d = buf + own_off + 8 * j;
+            *reinterpret_cast<double2*>(d) = make_double2(vred * x[2 * j].x, vred * x[2 * j + 1].x);
+            *reinterpret_cast<double2*>(d + 8 * LD) = make_double2(vred * x[2 * j].y, vred * x[2 * j + 1].y);
+            *reinterpret_cast<double2*>(d + 16 * LD) = make_double2(vred * x[2 * j].z, vred * x[2 * j + 1].z);
+        }
+    };
+    put(sm_m, m);
+    __syncthreads();
+
+    const double* b_m = sm_m + t * LD + 16 * mh + g;
+    const double* b_t = sm_t + t * LD + 16 * mh + g;
+
+    // g_q = dt h_q + cw_q with h = anisotropy + applied + dipolar (acc)
+    auto stage_g = [&](V3 (&gq)[4], const V3 (&x)[4], const double (&acc)[3][2][2], const double hz, const V3 (&cw)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint64_t c0 = 3ull * pid;
+            const V3 e{__ldg(P.axis + c0 * P.axis_cs + r[q] * P.axis_rs), __ldg(P.axis + (c0 + 1) * P.axis_cs + r[q] * P.axis_rs),
+                       __ldg(P.axis + (c0 + 2) * P.axis_cs + r[q] * P.axis_rs)};
+            const double s = dot(x[q], e) * kred;
+            const V3 h{fma(s, e.x, acc[0][q >> 1][q & 1]), fma(s, e.y, acc[1][q >> 1][q & 1]),
+                       fma(s, e.z, hz) + acc[2][q >> 1][q & 1]};
+            gq[q] = V3{fma(h.x, dt, cw[q].x), fma(h.y, dt, cw[q].y), fma(h.z, dt, cw[q].z)};
+        }
+    };
+
+    auto advance = [&](const V3 (&cw)[4], const uint64_t jj) {
+        double hz0 = P.h_const, hz1 = P.h_const;
+        if (FIELD_TAB) {
+            const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (jj - P.j0));
+            hz0 = h.x; hz1 = h.y;
+        }
+        double acc[3][2][2];
+        V3 gq[4], mt[4];
+        if (inter) dipolar_mma(acc, sm_d, b_m, G, pg, LD, g, t);
+        else {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) acc[a][0][0] = acc[a][0][1] = acc[a][1][0] = acc[a][1][1] = 0.0;
+        }
+        stage_g(gq, m, acc, hz0, cw);
+        if (ONE_BUF) group_barrier(bar_id, bar_n);   // every warp of the group has read the current moments
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const V3 pc = cross(m[q], gq[q]);
+            const V3 u{fma(alpha, pc.x, gq[q].x), fma(alpha, pc.y, gq[q].y), fma(alpha, pc.z, gq[q].z)};
+            mt[q] = V3{fma(-m[q].y, u.z, fma(m[q].z, u.y, m[q].x)), fma(-m[q].z, u.x, fma(m[q].x, u.z, m[q].y)),
+                       fma(-m[q].x, u.y, fma(m[q].y, u.x, m[q].z))};
+        }
+        put(sm_t, mt);
+        group_barrier(bar_id, bar_n);
+        if (inter) dipolar_mma(acc, sm_d, b_t, G, pg, LD, g, t);
+        stage_g(gq, mt, acc, hz1, cw);
+        if (ONE_BUF) group_barrier(bar_id, bar_n);   // every warp of the group has read the predictor moments
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const V3 pc = cross(mt[q], gq[q]);
+            const V3 u{fma(alpha, pc.x, gq[q].x), fma(alpha, pc.y, gq[q].y), fma(alpha, pc.z, gq[q].z)};
+            const V3 hm{0.5 * mt[q].x, 0.5 * mt[q].y, 0.5 * mt[q].z};
+            const V3 hh{fma(0.5, m[q].x, hm.x), fma(0.5, m[q].y, hm.y), fma(0.5, m[q].z, hm.z)};
+            m[q] = V3{fma(-hm.y, u.z, fma(hm.z, u.y, hh.x)), fma(-hm.z, u.x, fma(hm.x, u.z, hh.y)),
+                      fma(-hm.x, u.y, fma(hm.y, u.x, hh.z))};
+            if (renorm) renormalise(m[q]);
+        }
+        put(sm_m, m);
+        group_barrier(bar_id, bar_n);
+    };
+
+    constexpr bool PACKED = NOISE == NOISE_PHILOX_PACKED;
+    float carry[PACKED ? 4 : 1][3];
+    bool have_carry = false;
+    uint64_t j = P.j0;
+    for (uint32_t k = P.k0; k <= P.k1; ++k) {
+        const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+        for (; j < tgt; ++j) {
+            V3 cw[4];
+            if (PACKED) {
+                const bool odd = (j & 1) != 0;
+                if (odd && have_carry) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cw[q] = V3{widen_f32(carry[q][0]), widen_f32(carry[q][1]), widen_f32(carry[q][2])};
+                    have_carry = false;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint64_t seed = (uint64_t)__ldg(P.seeds + r[q]);
+                        float g6[6];
+                        philox_gauss6_f32((uint32_t)seed, (uint32_t)(seed >> 32), j >> 1, pid, (uint32_t)(r[q] + P.stream_offset),
+                                          bm, g6);
+                        cw[q] = odd ? V3{widen_f32(g6[3]), widen_f32(g6[4]), widen_f32(g6[5])}
+                                    : V3{widen_f32(g6[0]), widen_f32(g6[1]), widen_f32(g6[2])};
+                        carry[q][0] = g6[3]; carry[q][1] = g6[4]; carry[q][2] = g6[5];
+                    }
+                    have_carry = !odd;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint64_t seed = (uint64_t)__ldg(P.seeds + r[q]);
+                    cw[q] = draw_scaled<NOISE>(P, (uint32_t)seed, (uint32_t)(seed >> 32), j, pid, (uint32_t)(r[q] + P.stream_offset),
+                                               r[q], csig, bm);
+                }
+            }
+            advance(cw, j);
+        }
+        if (k < P.k1) {
+            if (P.traj != nullptr && valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!live[q]) continue;
+                    double* o = P.traj + ((uint64_t)k * 3 * N + 3ull * pid) * P.R + r[q];
+                    o[0] = m[q].x; o[P.R] = m[q].y; o[2 * P.R] = m[q].z;
+                }
+            }
+            if (P.partial != nullptr) {
+                // cluster magnetisation of each member: particles of a group by shuffles over g, groups in fixed order
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    double sx = valid ? m[q].x : 0.0, sy = valid ? m[q].y : 0.0, sz = valid ? m[q].z : 0.0;
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+                    }
+                    if (g == 0) {
+                        const int col = 16 * mh + 8 * (q >> 1) + 2 * t + (q & 1);
+                        double* rr = sm_red + (size_t)pg * 3 * MB + col;
+                        rr[0] = live[q] ? sx : 0.0; rr[MB] = live[q] ? sy : 0.0; rr[2 * MB] = live[q] ? sz : 0.0;
+                    }
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                    for (int col = lane; col < MB; col += 32) {
+                        double Mx = 0, My = 0, Mz = 0;
+                        for (int s2 = 0; s2 < G; ++s2) {
+                            const double* q2 = sm_red + (size_t)s2 * 3 * MB + col;
+                            Mx += q2[0]; My += q2[MB]; Mz += q2[2 * MB];
+                        }
+                        v0 += Mx; v1 += My; v2 += Mz; v3 += Mz * Mz;
+                    }
+                    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+                    if (lane == 0) {
+                        double* o = P.partial + ((uint64_t)(k - P.k0) * gridDim.x + blockIdx.x) * 4;
+                        o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!live[q]) continue;
+            const uint64_t c0 = 3ull * pid;
+            P.state[c0 * P.R + r[q]] = m[q].x; P.state[(c0 + 1) * P.R + r[q]] = m[q].y; P.state[(c0 + 2) * P.R + r[q]] = m[q].z;
+        }
+    }
+}
+
+template <int NOISE, bool TAB>
+static cudaError_t launch_hm(bool one_buf, unsigned grid, unsigned threads, size_t smem, cudaStream_t s, const RunParams& P) {
+    auto go = [&](auto kernel) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kernel<<<grid, threads, smem, s>>>(P);
+        return cudaGetLastError();
+    };
+    return one_buf ? go(heun_cluster_mma_kernel<NOISE, TAB, true>) : go(heun_cluster_mma_kernel<NOISE, TAB, false>);
+}
+
+cudaError_t launch_heun_cluster_mma(int noise, bool tab, bool one_buf, unsigned grid, unsigned threads, size_t smem,
+                                    cudaStream_t s, const RunParams& P) {
+    switch (noise) {
+        case NOISE_PHILOX_F32: return tab ? launch_hm<NOISE_PHILOX_F32, true>(one_buf, grid, threads, smem, s, P)
+                                          : launch_hm<NOISE_PHILOX_F32, false>(one_buf, grid, threads, smem, s, P);
+        case NOISE_PHILOX_F64: return tab ? launch_hm<NOISE_PHILOX_F64, true>(one_buf, grid, threads, smem, s, P)
+                                          : launch_hm<NOISE_PHILOX_F64, false>(one_buf, grid, threads, smem, s, P);
+        case NOISE_INJECTED: return tab ? launch_hm<NOISE_INJECTED, true>(one_buf, grid, threads, smem, s, P)
+                                        : launch_hm<NOISE_INJECTED, false>(one_buf, grid, threads, smem, s, P);
+        default: return tab ? launch_hm<NOISE_PHILOX_PACKED, true>(one_buf, grid, threads, smem, s, P)
+                            : launch_hm<NOISE_PHILOX_PACKED, false>(one_buf, grid, threads, smem, s, P);
+    }
+}
+
+}  // namespace mb

@@ -17,6 +17,8 @@
 // K2s/K4s *_small (small_*.cu)      Heun N = 2..7, implicit N = 2..4: one thread per cluster, moments in registers
 // K2 heun_cluster (cluster.cu)      N = 8..128: CTA = 32 members (lanes) x particle slots, 2/4/8 own particles
 //                                   per thread, moments (and the pair table, N <= 64) in shared memory
+// K2m heun_cluster_mma (cluster_mma.cu) N = 8..64 with a dense enough 8-particle grouping: the dipolar field as
+//                                   D[3N x 3N] . M[3N x members] on DMMA.8x8x4, D packed in shared memory
 // K4 imid_cluster (cluster.cu)      N = 5..32: same mapping; block-diagonal quasi-Newton, CTA-wide convergence
 // K5 ensemble sums                  fused into all of them (warp shuffle -> smem -> per-CTA partial) +
 //                                   reduce_partials (fixed order, deterministic)
@@ -41,6 +43,9 @@ struct RunParams {
     const double* k_red; // [N]
     const double* sig;   // [N] thermal field strength sigma_i
     const double* dip;   // [N][N][4] {sqrt(3) r_hat_ij (3), c_dip * v_j / cube_ij}; diagonal zero
+    const double* dmat;  // K2m: packed upper 24x24 blocks of the symmetric dipolar matrix (cluster_mma.cu) or nullptr
+    const double* v_red; // [N] reduced volumes (K2m folds them into the moments)
+    uint32_t G;          // K2m: particle groups of 8 (= ceil(N / 8))
     const double* axis;  // see layout
     uint64_t axis_cs, axis_rs;  // component stride, member stride
     const int64_t* seeds;       // [R]

@@ -194,10 +194,13 @@ struct magpy_b200_plan {
     bool use_table = false;
     bool axis_z = false;   // N = 1 and one shared easy axis exactly along +z: specialised Heun kernel
     bool small = false;    // few particles: one thread per cluster, all moments in registers
+    bool mma = false;      // Heun cluster kernel on the FP64 MMA path (cluster_mma.cu)
+    bool one_buf = false;  //   ... with one shared-memory moment buffer
+    uint32_t G = 0;        //   ... particle groups of 8
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
-    DevBuf<double> d_state0, d_state, d_axis, d_kred, d_sig, d_dip, d_traj, d_sums, d_partial, d_tab, d_dW, d_stage;
+    DevBuf<double> d_state0, d_state, d_axis, d_kred, d_sig, d_dip, d_dmat, d_vred, d_traj, d_sums, d_partial, d_tab, d_dW, d_stage;
     DevBuf<int64_t> d_seeds;
     DevBuf<uint64_t> d_target;
     DevBuf<unsigned long long> d_newton;
@@ -209,6 +212,7 @@ struct magpy_b200_plan {
     ~magpy_b200_plan() {
         cudaSetDevice(device);
         d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
+        d_dmat.release(); d_vred.release();
         d_traj.release(); d_sums.release(); d_partial.release(); d_tab.release(); d_dW.release(); d_stage.release();
         d_seeds.release(); d_target.release(); d_newton.release();
         if (stream) cudaStreamSynchronize(stream);
@@ -247,6 +251,8 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
     } else if (pl->small) {
         if (pl->implicit) LAUNCH_TRY(mb::launch_imid_small(noise, tab, pl->N, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_small(noise, tab, pl->N, pl->grid, pl->stream, P));
+    } else if (pl->mma) {
+        LAUNCH_TRY(mb::launch_heun_cluster_mma(noise, tab, pl->one_buf, pl->grid, pl->block.x, pl->smem, pl->stream, P));
     } else if (pl->implicit) {
         LAUNCH_TRY(mb::launch_imid_cluster(noise, tab, pl->np, dim3(pl->grid), pl->block, pl->smem, pl->stream, P));
     } else {
@@ -304,6 +310,34 @@ int validate(const magpy_b200_ensemble* a) {
     return MAGPY_B200_OK;
 }
 
+// K2m (cluster_mma.cu) applies to Heun clusters of 8..64 interacting particles.  Particles are handled in groups of
+// 8 (rows of the 8x8x4 MMA), so a cluster that fills its last group badly does padded work: the scalar kernel keeps
+// those unless MAGPY_B200_CLUSTER_KERNEL=mma asks otherwise (=simt forces the scalar kernel everywhere).
+bool choose_mma(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
+    const uint32_t N = pl->N;
+    if (pl->implicit || N < 8 || N > 64 || a->interactions == 0) return false;
+    const char* force = std::getenv("MAGPY_B200_CLUSTER_KERNEL");
+    if (force && std::strcmp(force, "simt") == 0) return false;
+    const uint32_t G = (N + 7) / 8;
+    const double fill = (double)N * N / (64.0 * G * G);
+    if (!(force && std::strcmp(force, "mma") == 0) && fill < 0.7) return false;
+    uint32_t MH = std::min<uint32_t>(8, 16 / G);
+    const size_t cap = 227 * 1024;
+    for (; MH >= 1; --MH) {
+        const size_t MB = 16 * MH, LD = MB + 4;
+        const size_t dmat = (size_t)G * (G + 1) / 2 * 576 * 8, mom = (size_t)24 * G * LD * 8, red = (size_t)G * 3 * MB * 8;
+        if (dmat + 2 * mom + red <= cap) { pl->one_buf = false; pl->smem = dmat + 2 * mom + red; break; }
+        if (dmat + mom + red <= cap) { pl->one_buf = true; pl->smem = dmat + mom + red; break; }
+    }
+    if (MH == 0) return false;
+    pl->mma = true;
+    pl->G = G;
+    pl->np = 1;
+    pl->block = dim3(32 * G * MH);
+    pl->grid = (unsigned)((pl->R + 16 * MH - 1) / (16 * MH));
+    return true;
+}
+
 int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     int rc = validate(a);
     if (rc) return rc;
@@ -353,6 +387,8 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         pl->grid = (unsigned)((R + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
         pl->smem = 0;
         pl->np = 1;
+    } else if (choose_mma(a, pl)) {
+        // cluster_mma.cu: dipolar field as a matrix product on DMMA; geometry set by choose_mma
     } else {
         const uint32_t max_slots = pl->implicit ? 8 : 16;
         // >= 2 own particles per thread reuse every shared-memory moment read of the dipolar sum; the implicit kernel's
@@ -536,6 +572,36 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         CU_TRY(cudaStreamSynchronize(pl->stream));
         pl->h2d += tab.size() * 8;
     }
+    if (pl->mma) {
+        // symmetric dipolar matrix D[(i,a),(j,b)] = c_dip / cube_ij (3 r_a r_b - delta_ab) in the row order
+        // 24 (p / 8) + 8 a + p % 8, upper 24 x 24 blocks only, swizzled inside a block (cluster_mma.cu)
+        const uint32_t G = pl->G;
+        std::vector<double> dm((size_t)G * (G + 1) / 2 * 576, 0.0);
+        const double lscale = std::pow(rd.V_av, 1. / 3);
+        for (uint32_t i = 0; i < N; ++i)
+            for (uint32_t jx = 0; jx < N; ++jx) {
+                if (i == jx || jx / 8 < i / 8) continue;
+                double d[3];
+                for (int c = 0; c < 3; ++c) d[c] = a->location[3 * jx + c] - a->location[3 * i + c];
+                const double mag = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                const double cube = std::pow(mag / lscale, 3);
+                const double pre = rd.dip_pre / cube;
+                const uint32_t pg = i / 8, kg = jx / 8;
+                double* blk = &dm[((size_t)pg * G - (size_t)pg * (pg - 1) / 2 + (kg - pg)) * 576];
+                for (int aa = 0; aa < 3; ++aa)
+                    for (int bb = 0; bb < 3; ++bb) {
+                        const uint32_t row = 8 * aa + i % 8, col = 8 * bb + jx % 8;
+                        blk[row * 24 + (col ^ (((row >> 1) & 1) << 2))] =
+                            pre * (3.0 * (d[aa] / mag) * (d[bb] / mag) - (aa == bb ? 1.0 : 0.0));
+                    }
+            }
+        CU_TRY(pl->d_dmat.alloc(dm.size(), pl->stream));
+        CU_TRY(pl->d_vred.alloc(N, pl->stream));
+        CU_TRY(cudaMemcpyAsync(pl->d_dmat.p, dm.data(), dm.size() * 8, cudaMemcpyHostToDevice, pl->stream));
+        CU_TRY(cudaMemcpyAsync(pl->d_vred.p, rd.v_red.data(), N * 8, cudaMemcpyHostToDevice, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->h2d += dm.size() * 8 + N * 8;
+    }
     if (pl->want_traj) CU_TRY(pl->d_traj.alloc((size_t)pl->S * n * R, pl->stream));
     CU_TRY(cudaStreamSynchronize(pl->stream));
 
@@ -553,6 +619,9 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.k_red = pl->d_kred.p;
     P.sig = pl->d_sig.p;
     P.dip = pl->d_dip.p;
+    P.dmat = pl->d_dmat.p;
+    P.v_red = pl->d_vred.p;
+    P.G = pl->G;
     P.axis = pl->d_axis.p;
     P.axis_cs = a->axis_stride ? R : 1;
     P.axis_rs = a->axis_stride ? 1 : 0;

@@ -154,6 +154,23 @@ def test_heun_cluster_injected(orc, core, N, interactions, renorm):
     assert_traj(ref, out, c)
 
 
+# The same clusters through K2m (cluster_mma.cu): dipolar field as D[3N x 3N] . M[3N x members] on DMMA.8x8x4.
+# 8: one particle group, 8 member halves per CTA; 12 / 20: padded last group (forced: the default keeps the scalar
+# kernel for badly filled groups); 24, 40: two moment buffers; 56: seven groups; 64: ONE moment buffer next to the 162 KB matrix.
+# 140 members: several CTAs, ragged last one, both member halves and all column tiles populated.
+@pytest.mark.parametrize('N,renorm,members', [(8, False, 140), (12, True, 35), (20, False, 35), (24, True, 70), (40, False, 35),
+                                              (56, False, 20), (64, False, 35), (64, True, 9)])
+def test_heun_cluster_mma_injected(orc, core, N, renorm, members, monkeypatch):
+    monkeypatch.setenv('MAGPY_B200_CLUSTER_KERNEL', 'mma')
+    rng = np.random.default_rng(N)
+    c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
+                     dt=1e-13, t_end=3e-11, S=25, interactions=True, renorm=renorm, field_shape='sine',
+                     H0=1e4, f=1e10, T=330.0, rng=rng)
+    seeds = np.arange(1, members + 1) * 101
+    t, fl, ref, out, _ = injected_pair(orc, core, c, seeds)
+    assert_traj(ref, out, c)
+
+
 @pytest.mark.parametrize('N,interactions', [(2, True), (3, False), (4, True), (5, True), (12, True), (32, True)])
 def test_implicit_cluster_injected(orc, core, N, interactions):
     rng = np.random.default_rng(100 + N)
