@@ -185,6 +185,9 @@ int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t par
 /* sustained FP64 FMA rate of the device (TFLOP/s), measured with a register-resident
  * DFMA chain kernel — the roofline denominator for the integration kernels */
 int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz);
+/* the same for the FP64 matrix instruction (DMMA.8x8x4, register-resident accumulator chains) — the roofline
+ * denominator of the cluster kernel that evaluates the dipolar field as a matrix product (cluster_mma.cu) */
+int magpy_b200_fp64_mma_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

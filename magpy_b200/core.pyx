@@ -111,6 +111,7 @@ cdef extern from "magpy_b200.h" nogil:
     int magpy_b200_philox_words(int, const uint32_t*, const uint32_t*, uint32_t*)
     int magpy_b200_gaussians(int, int64_t, uint64_t, uint32_t, uint64_t, uint64_t, int, double*)
     int magpy_b200_fp64_peak(int, double*, double*)
+    int magpy_b200_fp64_mma_peak(int, double*)
 
 
 # field::options numbering (include/field.hpp:95-97, magpy/core.pyx:38-42)
@@ -520,3 +521,14 @@ def fp64_peak(int device=0):
     if rc != 0:
         _raise(rc)
     return tf, mhz
+
+
+def fp64_mma_peak(int device=0):
+    """Measured sustained rate of the FP64 matrix instruction (DMMA.8x8x4) in TFLOP/s."""
+    cdef double tf = 0.0
+    cdef int rc
+    with nogil:
+        rc = magpy_b200_fp64_mma_peak(device, &tf)
+    if rc != 0:
+        _raise(rc)
+    return tf

@@ -21,9 +21,10 @@
 // a block, element (i, c) sits at i * 24 + (c ^ 4 ((i >> 1) & 1)), which makes both the direct and the
 // transposed fragment loads bank-conflict free.
 //
-// Every group of warps that shares a 16-member half is an independent problem: it
-// synchronises on its own named barrier, so the halves drift out of phase and the update / noise phase of one
-// overlaps the matrix product of the others.
+// Every group of warps that shares a 16-member half is an independent problem and synchronises on its own named
+// barrier.  (DFMA and DMMA share the FP64 datapath — scripts/micro/dmma.cu — so running one group's update under
+// another's product hides latency only; a forced phase offset between the groups measured no gain.)
+#include <type_traits>
 #include "common.cuh"
 #include "launch.h"
 
@@ -40,7 +41,26 @@ __device__ __forceinline__ void group_barrier(const int id, const int threads) {
 
 constexpr int MMA_BLK = 576;   // doubles per 24 x 24 block of D
 
-// acc[a][j][e] = H_a(particle 8 pg + g, member 16 mh + 8 j + 2 t + e)
+// Operand addressing of one 24 x 24 block for this thread.  Fragment element (row 8 a + g, column 4 ks + t) of the
+// warp's A operand sits at  a_base + ks * sks + a * sa -/+ dsw  (the swizzle of a directly read block moves the
+// even k-steps up and the odd ones down by 4 sg doubles; a transposed block needs no correction).
+struct BlockPtr {
+    const double* a;
+    const double* b;
+    int sks, sa, dsw;
+};
+
+__device__ __forceinline__ void load_frags(double (&af)[3], double (&bf)[2], const BlockPtr& bp, const int ks, const int LD4) {
+    const double* ap = bp.a + ks * bp.sks + ((ks & 1) ? -bp.dsw : bp.dsw);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) af[a] = ap[a * bp.sa];
+    const double* bq = bp.b + ks * LD4;
+    bf[0] = bq[0];
+    bf[1] = bq[8];
+}
+
+// acc[a][j][e] = H_a(particle 8 pg + g, member 16 mh + 8 j + 2 t + e).  The operand fragments of the next k-step
+// (also across block boundaries) are loaded before the six DMMAs of the current one are issued.
 __device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double* __restrict__ sm_d,
                                             const double* __restrict__ sm_b /* + 16 mh + g + t * LD */, const int G,
                                             const int pg, const int LD, const int g, const int t) {
@@ -48,39 +68,40 @@ __device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
-    const int sg = (g >> 1) & 1, st4 = ((t >> 1) & 1) << 2;
+    const int dsw = ((g >> 1) & 1) << 2, st4 = ((t >> 1) & 1) << 2;
     const int off_direct = 24 * g + t, off_transp = 24 * t + (g ^ st4);
-    for (int kg = 0; kg < G; ++kg) {
-        const double* brow = sm_b + (size_t)(24 * kg) * LD;
+    const int LD4 = 4 * LD, LD24 = 24 * LD;
+    auto block_ptr = [&](const int kg) {
+        BlockPtr bp;
+        bp.b = sm_b + kg * LD24;
         if (kg >= pg) {
-            const double* blk = sm_d + (size_t)(pg * G - (pg * (pg - 1)) / 2 + (kg - pg)) * MMA_BLK + off_direct;
-#pragma unroll
-            for (int ks = 0; ks < 6; ++ks) {
-                double af[3], bf[2];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) af[a] = blk[192 * a + 4 * (ks ^ sg)];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) bf[j] = brow[(size_t)(4 * ks) * LD + 8 * j];
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) dmma884(acc[a][j][0], acc[a][j][1], af[a], bf[j]);
-            }
+            bp.a = sm_d + (pg * G - (pg * (pg - 1)) / 2 + (kg - pg)) * MMA_BLK + off_direct;
+            bp.sks = 4; bp.sa = 192; bp.dsw = dsw;
         } else {
-            const double* blk = sm_d + (size_t)(kg * G - (kg * (kg - 1)) / 2 + (pg - kg)) * MMA_BLK + off_transp;
-#pragma unroll
-            for (int ks = 0; ks < 6; ++ks) {
-                double af[3], bf[2];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) af[a] = blk[96 * ks + 8 * a];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) bf[j] = brow[(size_t)(4 * ks) * LD + 8 * j];
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) dmma884(acc[a][j][0], acc[a][j][1], af[a], bf[j]);
-            }
+            bp.a = sm_d + (kg * G - (kg * (kg - 1)) / 2 + (pg - kg)) * MMA_BLK + off_transp;
+            bp.sks = 96; bp.sa = 8; bp.dsw = 0;
         }
+        return bp;
+    };
+    BlockPtr cur = block_ptr(0);
+    double af[3], bf[2];
+    load_frags(af, bf, cur, 0, LD4);
+    for (int kg = 0; kg < G; ++kg) {
+        const BlockPtr nxt = block_ptr(kg + 1 < G ? kg + 1 : kg);   // the last prefetch re-reads a valid block
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) {
+            double an[3], bn[2];
+            if (ks < 5) load_frags(an, bn, cur, ks + 1, LD4);
+            else load_frags(an, bn, nxt, 0, LD4);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma884(acc[a][j][0], acc[a][j][1], af[a], bf[j]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) af[a] = an[a];
+            bf[0] = bn[0]; bf[1] = bn[1];
+        }
+        cur = nxt;
     }
 }
 
@@ -116,17 +137,17 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     const int bar_id = 1 + mh, bar_n = 32 * G;
 
     // the thread's four members: q = 2 j + e  ->  local column 16 mh + 8 j + 2 t + e
-    uint64_t r[4];
-    bool live[4];
+    const uint64_t r_base = (uint64_t)blockIdx.x * MB + 16 * mh + 2 * t;
+    auto is_live = [&](const int q) { return r_base + 8 * (q >> 1) + (q & 1) < P.R; };
+    auto member = [&](const int q) {   // members past the end repeat the last one (computed, never stored)
+        const uint64_t r_raw = r_base + 8 * (q >> 1) + (q & 1);
+        return r_raw < P.R ? r_raw : P.R - 1;
+    };
     V3 m[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int col = 16 * mh + 8 * (q >> 1) + 2 * t + (q & 1);
-        const uint64_t r_raw = (uint64_t)blockIdx.x * MB + col;
-        live[q] = r_raw < P.R;
-        r[q] = live[q] ? r_raw : P.R - 1;
-        const uint64_t c0 = 3ull * pid;
-        m[q] = V3{P.state[c0 * P.R + r[q]], P.state[(c0 + 1) * P.R + r[q]], P.state[(c0 + 2) * P.R + r[q]]};
+        const uint64_t c0 = 3ull * pid, rq = member(q);
+        m[q] = V3{P.state[c0 * P.R + rq], P.state[(c0 + 1) * P.R + rq], P.state[(c0 + 2) * P.R + rq]};
     }
     // own rows of the moment buffers: row(comp a) = 24 pg + 8 a + g, columns 16 mh + 8 j + 2 t + {0, 1}
     const int own_off = (24 * pg + g) * LD + 16 * mh + 2 * t;
@@ -142,32 +163,49 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     };
     put(sm_m, m);
     __syncthreads();
-
     const double* b_m = sm_m + t * LD + 16 * mh + g;
     const double* b_t = sm_t + t * LD + 16 * mh + g;
 
-    // g_q = dt h_q + cw_q with h = anisotropy + applied + dipolar (acc)
-    auto stage_g = [&](V3 (&gq)[4], const V3 (&x)[4], const double (&acc)[3][2][2], const double hz, const V3 (&cw)[4]) {
+    constexpr bool PACKED = NOISE == NOISE_PHILOX_PACKED;
+    // scaled increments of the current step: kept as the fp32 the packed generator produces (widened at use) so that
+    // they cost 12 registers, not 24, across the two matrix products
+    struct Inc {
+        typename std::conditional<PACKED, float, double>::type x, y, z;
+    };
+    const double inv_v = 1.0 / vred;
+    auto get = [&](const double* buf, V3 (&x)[4]) {   // own moments back from a moment buffer
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint64_t c0 = 3ull * pid;
-            const V3 e{__ldg(P.axis + c0 * P.axis_cs + r[q] * P.axis_rs), __ldg(P.axis + (c0 + 1) * P.axis_cs + r[q] * P.axis_rs),
-                       __ldg(P.axis + (c0 + 2) * P.axis_cs + r[q] * P.axis_rs)};
-            const double s = dot(x[q], e) * kred;
-            const V3 h{fma(s, e.x, acc[0][q >> 1][q & 1]), fma(s, e.y, acc[1][q >> 1][q & 1]),
-                       fma(s, e.z, hz) + acc[2][q >> 1][q & 1]};
-            gq[q] = V3{fma(h.x, dt, cw[q].x), fma(h.y, dt, cw[q].y), fma(h.z, dt, cw[q].z)};
+        for (int j = 0; j < 2; ++j) {
+            const double* d = buf + own_off + 8 * j;
+            const double2 vx = *reinterpret_cast<const double2*>(d), vy = *reinterpret_cast<const double2*>(d + 8 * LD),
+                          vz = *reinterpret_cast<const double2*>(d + 16 * LD);
+            x[2 * j] = V3{vx.x * inv_v, vy.x * inv_v, vz.x * inv_v};
+            x[2 * j + 1] = V3{vx.y * inv_v, vy.y * inv_v, vz.y * inv_v};
         }
     };
 
-    auto advance = [&](const V3 (&cw)[4], const uint64_t jj) {
+    // g_q = dt h_q + cw_q with h = anisotropy + applied + dipolar (acc)
+    auto stage_g = [&](V3 (&gq)[4], const V3 (&x)[4], const double (&acc)[3][2][2], const double hz, const Inc (&cw)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint64_t c0 = 3ull * pid, rq = member(q);
+            const V3 e{__ldg(P.axis + c0 * P.axis_cs + rq * P.axis_rs), __ldg(P.axis + (c0 + 1) * P.axis_cs + rq * P.axis_rs),
+                       __ldg(P.axis + (c0 + 2) * P.axis_cs + rq * P.axis_rs)};
+            const double s = dot(x[q], e) * kred;
+            const V3 h{fma(s, e.x, acc[0][q >> 1][q & 1]), fma(s, e.y, acc[1][q >> 1][q & 1]),
+                       fma(s, e.z, hz) + acc[2][q >> 1][q & 1]};
+            gq[q] = V3{fma(h.x, dt, (double)cw[q].x), fma(h.y, dt, (double)cw[q].y), fma(h.z, dt, (double)cw[q].z)};
+        }
+    };
+
+    auto advance = [&](const Inc (&cw)[4], const uint64_t jj) {
         double hz0 = P.h_const, hz1 = P.h_const;
         if (FIELD_TAB) {
             const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (jj - P.j0));
             hz0 = h.x; hz1 = h.y;
         }
         double acc[3][2][2];
-        V3 gq[4], mt[4];
+        V3 gq[4];
         if (inter) dipolar_mma(acc, sm_d, b_m, G, pg, LD, g, t);
         else {
 #pragma unroll
@@ -175,16 +213,23 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
         }
         stage_g(gq, m, acc, hz0, cw);
         if (ONE_BUF) group_barrier(bar_id, bar_n);   // every warp of the group has read the current moments
+        {
+            V3 mt[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const V3 pc = cross(m[q], gq[q]);
-            const V3 u{fma(alpha, pc.x, gq[q].x), fma(alpha, pc.y, gq[q].y), fma(alpha, pc.z, gq[q].z)};
-            mt[q] = V3{fma(-m[q].y, u.z, fma(m[q].z, u.y, m[q].x)), fma(-m[q].z, u.x, fma(m[q].x, u.z, m[q].y)),
-                       fma(-m[q].x, u.y, fma(m[q].y, u.x, m[q].z))};
+            for (int q = 0; q < 4; ++q) {
+                const V3 pc = cross(m[q], gq[q]);
+                const V3 u{fma(alpha, pc.x, gq[q].x), fma(alpha, pc.y, gq[q].y), fma(alpha, pc.z, gq[q].z)};
+                mt[q] = V3{fma(-m[q].y, u.z, fma(m[q].z, u.y, m[q].x)), fma(-m[q].z, u.x, fma(m[q].x, u.z, m[q].y)),
+                           fma(-m[q].x, u.y, fma(m[q].y, u.x, m[q].z))};
+            }
+            put(sm_t, mt);
         }
-        put(sm_t, mt);
         group_barrier(bar_id, bar_n);
         if (inter) dipolar_mma(acc, sm_d, b_t, G, pg, LD, g, t);
+        // the predictor moments are not kept in registers across the second product: the thread reads its own back
+        // from shared memory (exact when v_red = 1; otherwise one rounding of v (1/v), 12 orders below the noise)
+        V3 mt[4];
+        get(sm_t, mt);
         stage_g(gq, mt, acc, hz1, cw);
         if (ONE_BUF) group_barrier(bar_id, bar_n);   // every warp of the group has read the predictor moments
 #pragma unroll
@@ -201,29 +246,27 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
         group_barrier(bar_id, bar_n);
     };
 
-    constexpr bool PACKED = NOISE == NOISE_PHILOX_PACKED;
     float carry[PACKED ? 4 : 1][3];
     bool have_carry = false;
     uint64_t j = P.j0;
     for (uint32_t k = P.k0; k <= P.k1; ++k) {
         const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
         for (; j < tgt; ++j) {
-            V3 cw[4];
-            if (PACKED) {
+            Inc cw[4];
+            if constexpr (PACKED) {
                 const bool odd = (j & 1) != 0;
                 if (odd && have_carry) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) cw[q] = V3{widen_f32(carry[q][0]), widen_f32(carry[q][1]), widen_f32(carry[q][2])};
+                    for (int q = 0; q < 4; ++q) cw[q] = Inc{carry[q][0], carry[q][1], carry[q][2]};
                     have_carry = false;
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const uint64_t seed = (uint64_t)__ldg(P.seeds + r[q]);
+                        const uint64_t rq = member(q), seed = (uint64_t)__ldg(P.seeds + rq);
                         float g6[6];
-                        philox_gauss6_f32((uint32_t)seed, (uint32_t)(seed >> 32), j >> 1, pid, (uint32_t)(r[q] + P.stream_offset),
+                        philox_gauss6_f32((uint32_t)seed, (uint32_t)(seed >> 32), j >> 1, pid, (uint32_t)(rq + P.stream_offset),
                                           bm, g6);
-                        cw[q] = odd ? V3{widen_f32(g6[3]), widen_f32(g6[4]), widen_f32(g6[5])}
-                                    : V3{widen_f32(g6[0]), widen_f32(g6[1]), widen_f32(g6[2])};
+                        cw[q] = odd ? Inc{g6[3], g6[4], g6[5]} : Inc{g6[0], g6[1], g6[2]};
                         carry[q][0] = g6[3]; carry[q][1] = g6[4]; carry[q][2] = g6[5];
                     }
                     have_carry = !odd;
@@ -231,9 +274,10 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const uint64_t seed = (uint64_t)__ldg(P.seeds + r[q]);
-                    cw[q] = draw_scaled<NOISE>(P, (uint32_t)seed, (uint32_t)(seed >> 32), j, pid, (uint32_t)(r[q] + P.stream_offset),
-                                               r[q], csig, bm);
+                    const uint64_t rq = member(q), seed = (uint64_t)__ldg(P.seeds + rq);
+                    const V3 w = draw_scaled<NOISE>(P, (uint32_t)seed, (uint32_t)(seed >> 32), j, pid,
+                                                    (uint32_t)(rq + P.stream_offset), rq, csig, bm);
+                    cw[q] = Inc{w.x, w.y, w.z};
                 }
             }
             advance(cw, j);
@@ -242,8 +286,8 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
             if (P.traj != nullptr && valid) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (!live[q]) continue;
-                    double* o = P.traj + ((uint64_t)k * 3 * N + 3ull * pid) * P.R + r[q];
+                    if (!is_live(q)) continue;
+                    double* o = P.traj + ((uint64_t)k * 3 * N + 3ull * pid) * P.R + member(q);
                     o[0] = m[q].x; o[P.R] = m[q].y; o[2 * P.R] = m[q].z;
                 }
             }
@@ -262,7 +306,8 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
                     if (g == 0) {
                         const int col = 16 * mh + 8 * (q >> 1) + 2 * t + (q & 1);
                         double* rr = sm_red + (size_t)pg * 3 * MB + col;
-                        rr[0] = live[q] ? sx : 0.0; rr[MB] = live[q] ? sy : 0.0; rr[2 * MB] = live[q] ? sz : 0.0;
+                        const bool lv = is_live(q);
+                        rr[0] = lv ? sx : 0.0; rr[MB] = lv ? sy : 0.0; rr[2 * MB] = lv ? sz : 0.0;
                     }
                 }
                 __syncthreads();
@@ -289,9 +334,9 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     if (valid) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (!live[q]) continue;
-            const uint64_t c0 = 3ull * pid;
-            P.state[c0 * P.R + r[q]] = m[q].x; P.state[(c0 + 1) * P.R + r[q]] = m[q].y; P.state[(c0 + 2) * P.R + r[q]] = m[q].z;
+            if (!is_live(q)) continue;
+            const uint64_t c0 = 3ull * pid, rq = member(q);
+            P.state[c0 * P.R + rq] = m[q].x; P.state[(c0 + 1) * P.R + rq] = m[q].y; P.state[(c0 + 2) * P.R + rq] = m[q].z;
         }
     }
 }

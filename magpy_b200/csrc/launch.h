@@ -30,6 +30,7 @@ cudaError_t launch_transpose(const double* in, double* out, uint64_t rows, uint6
                              uint64_t in_rs, uint64_t out_bs, uint64_t out_rs, double scale, cudaStream_t s);
 cudaError_t launch_broadcast_rows(const double* in, double* out, uint64_t n, uint64_t R, cudaStream_t s);
 cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t s);
+cudaError_t launch_fp64_mma_peak(double* out, int blocks, int threads, int iters, cudaStream_t s);
 cudaError_t launch_philox_words(const uint32_t ctr[4], const uint32_t key[2], uint32_t* out);
 cudaError_t launch_gaussians(int noise, uint64_t seed, uint32_t member, uint32_t particle, uint64_t first_step,
                              uint64_t n_steps, double* out);

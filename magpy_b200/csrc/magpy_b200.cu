@@ -1011,7 +1011,7 @@ int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz) {
     if (!tflops) return fail(MAGPY_B200_ERR_BAD_ARG, "tflops is NULL");
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
-    const int iters = 2048;
+    const int iters = 8192;
     cudaEvent_t e0, e1;
     CU_TRY(cudaEventCreate(&e0));
     CU_TRY(cudaEventCreate(&e1));
@@ -1041,6 +1041,35 @@ int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz) {
         cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
         *sm_clock_mhz = khz / 1000.0;
     }
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_fp64_mma_peak(int device, double* tflops) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (!tflops) return fail(MAGPY_B200_ERR_BAD_ARG, "tflops is NULL");
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    const int iters = 4000, threads = 256, blocks = prop.multiProcessorCount;   // 2 warps per scheduler
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    DevBuf<double> d;
+    CU_TRY(d.alloc((size_t)blocks * threads));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU_TRY(cudaEventRecord(e0));
+        CU_TRY(mb::launch_fp64_mma_peak(d.p, blocks, threads, iters, nullptr));
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)blocks * (threads / 32) * iters * 48.0 * 512.0;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
     return MAGPY_B200_OK;
 }
 

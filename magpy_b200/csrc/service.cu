@@ -89,6 +89,27 @@ __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
     out[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// 12 independent DMMA.8x8x4 accumulator chains per warp (512 flop per warp instruction)
+__global__ void fp64_mma_peak_kernel(double* out, int iters, double a0, double b0) {
+    double c[12][2];
+    const double a = a0 + threadIdx.x * 1e-9, b = b0 + threadIdx.x * 1e-9;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { c[i][0] = i; c[i][1] = -i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s += c[i][0] + c[i][1];
+    out[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void philox_words_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                     uint32_t* out) {
     philox4x32_10(c0, c1, c2, c3, k0, k1);
@@ -132,6 +153,11 @@ cudaError_t launch_broadcast_rows(const double* in, double* out, uint64_t n, uin
 
 cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t s) {
     fp64_peak_kernel<<<blocks, threads, 0, s>>>(out, iters, 0.999999, 1e-7);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_mma_peak(double* out, int blocks, int threads, int iters, cudaStream_t s) {
+    fp64_mma_peak_kernel<<<blocks, threads, 0, s>>>(out, iters, 1.0000001, 1e-9);
     return cudaGetLastError();
 }
 
