@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MAGPY_B200_ABI_VERSION 2
+#define MAGPY_B200_ABI_VERSION 3
 
 /* status codes */
 #define MAGPY_B200_OK 0
@@ -57,7 +57,17 @@ typedef struct magpy_b200_stats {
     double integrate_ms;           /* CUDA-event time of the integration kernels alone      */
     uint64_t h2d_bytes;            /* host->device bytes copied by this call                */
     uint64_t d2h_bytes;            /* device->host bytes copied by this call                */
+    uint64_t kernel_family;        /* MAGPY_B200_KERNEL_*: which integration kernel ran (ABI v3) */
 } magpy_b200_stats;
+
+/* integration kernels (magpy_b200/csrc): reported in magpy_b200_stats.kernel_family */
+#define MAGPY_B200_KERNEL_HEUN_SINGLE 1      /* heun_single.cu: one thread per single-particle member       */
+#define MAGPY_B200_KERNEL_IMID_SINGLE 2      /* imid_single.cu                                              */
+#define MAGPY_B200_KERNEL_HEUN_SMALL 3       /* small_heun.cu: one thread per cluster of 2..7 particles      */
+#define MAGPY_B200_KERNEL_IMID_SMALL 4       /* small_imid.cu: 2..4 particles                                */
+#define MAGPY_B200_KERNEL_HEUN_CLUSTER 5     /* cluster.cu: scalar dipolar sum from shared memory            */
+#define MAGPY_B200_KERNEL_IMID_CLUSTER 6     /* cluster.cu                                                   */
+#define MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA 7 /* cluster_mma.cu: dipolar field as a matrix product (DMMA)     */
 
 /* One ensemble of `n_members` independent clusters that share geometry and material
  * (radius, anisotropy, location, Ms, damping, T, field) and may differ in anisotropy

@@ -46,6 +46,7 @@ cdef extern from "magpy_b200.h" nogil:
         double integrate_ms
         uint64_t h2d_bytes
         uint64_t d2h_bytes
+        uint64_t kernel_family
 
     ctypedef struct magpy_b200_ensemble:
         uint32_t abi_version
@@ -132,6 +133,10 @@ cdef _raise(int rc):
     raise RuntimeError(msg)
 
 
+_KERNEL_NAMES = {1: 'heun_single', 2: 'imid_single', 3: 'heun_small', 4: 'imid_small', 5: 'heun_cluster',
+                 6: 'imid_cluster', 7: 'heun_cluster_mma'}
+
+
 cdef dict _stats_dict(magpy_b200_stats* st):
     return {
         'steps_per_member': st.steps_per_member,
@@ -144,6 +149,7 @@ cdef dict _stats_dict(magpy_b200_stats* st):
         'integrate_ms': st.integrate_ms,
         'h2d_bytes': st.h2d_bytes,
         'd2h_bytes': st.d2h_bytes,
+        'kernel': _KERNEL_NAMES.get(st.kernel_family, 'unknown'),
     }
 
 

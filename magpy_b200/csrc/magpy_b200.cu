@@ -311,8 +311,10 @@ int validate(const magpy_b200_ensemble* a) {
 }
 
 // K2m (cluster_mma.cu) applies to Heun clusters of 8..64 interacting particles.  Particles are handled in groups of
-// 8 (rows of the 8x8x4 MMA), so a cluster that fills its last group badly does padded work: the scalar kernel keeps
-// those unless MAGPY_B200_CLUSTER_KERNEL=mma asks otherwise (=simt forces the scalar kernel everywhere).
+// 8 (rows of the 8x8x4 MMA), so a cluster that fills its last group badly does padded work.  Measured
+// (profiles/r01_probe_cluster_mma_fill.log): the matrix kernel wins when N^2 / (8 G)^2 >= 0.7 and for every N > 32;
+// the scalar kernel keeps the rest unless MAGPY_B200_CLUSTER_KERNEL=mma asks otherwise (=simt forces the scalar
+// kernel everywhere).
 bool choose_mma(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     const uint32_t N = pl->N;
     if (pl->implicit || N < 8 || N > 64 || a->interactions == 0) return false;
@@ -320,7 +322,7 @@ bool choose_mma(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     if (force && std::strcmp(force, "simt") == 0) return false;
     const uint32_t G = (N + 7) / 8;
     const double fill = (double)N * N / (64.0 * G * G);
-    if (!(force && std::strcmp(force, "mma") == 0) && fill < 0.7) return false;
+    if (!(force && std::strcmp(force, "mma") == 0) && fill < 0.7 && N <= 32) return false;
     uint32_t MH = std::min<uint32_t>(8, 16 / G);
     const size_t cap = 227 * 1024;
     for (; MH >= 1; --MH) {
@@ -680,6 +682,10 @@ int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
     st->kernel_launches = pl->launches;
     st->h2d_bytes = pl->h2d;
     st->d2h_bytes = pl->d2h;
+    st->kernel_family = pl->N == 1 ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SINGLE : MAGPY_B200_KERNEL_HEUN_SINGLE)
+                        : pl->small ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SMALL : MAGPY_B200_KERNEL_HEUN_SMALL)
+                        : pl->mma   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA
+                                    : (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER : MAGPY_B200_KERNEL_HEUN_CLUSTER);
     if (pl->ran) {
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, pl->ev_begin, pl->ev_end));
@@ -927,6 +933,7 @@ int magpy_b200_simulate_ensemble_multi(const magpy_b200_ensemble* args, const in
             total.integrate_ms = std::max(total.integrate_ms, st.integrate_ms);
             total.h2d_bytes += st.h2d_bytes;
             total.d2h_bytes += st.d2h_bytes;
+            total.kernel_family = st.kernel_family;
         }
         if (!rc && args->out_sums) {   // fixed device order: deterministic for a given device list
             std::fill_n(args->out_sums, S * 4, 0.0);

@@ -16,6 +16,8 @@ KEYS = [
     'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
     'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active',
+    'smsp__pipe_tensor_subpipe_dmma_cycles_active.avg',
     'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',

@@ -138,19 +138,22 @@ def test_implicit_single_injected(orc, core, field_shape, H0, f, renorm, eps, ax
     assert out['stats']['newton_failures'] == 0
 
 
-# N = 2..7: one thread per cluster (small_heun.cu); 8..32: two particles per thread, pair table in shared memory;
-# 40: four per thread; 64: four per thread with ONE moment buffer next to the 128 KB table; 70: eight per
-# thread, table in global memory; 128: the largest supported cluster (cluster.cu)
+# Scalar kernels.  N = 2..7: one thread per cluster (small_heun.cu); 8..32: two particles per thread, pair table in
+# shared memory; 40: four per thread; 64: four per thread with ONE moment buffer next to the 128 KB table; 70: eight per
+# thread, table in global memory; 128: the largest supported cluster (cluster.cu).  MAGPY_B200_CLUSTER_KERNEL=simt keeps
+# the clusters the DMMA kernel would take by default on the scalar path.
 @pytest.mark.parametrize('N,interactions,renorm', [(2, True, False), (3, True, True), (4, True, True), (5, False, False),
                                                    (7, True, True), (8, True, False), (20, True, False), (40, True, False),
                                                    (64, True, False), (70, True, True), (128, True, False)])
-def test_heun_cluster_injected(orc, core, N, interactions, renorm):
+def test_heun_cluster_injected(orc, core, N, interactions, renorm, monkeypatch):
+    monkeypatch.setenv('MAGPY_B200_CLUSTER_KERNEL', 'simt')
     rng = np.random.default_rng(N)
     c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
                      dt=1e-13, t_end=3e-11, S=25, interactions=interactions, renorm=renorm, field_shape='sine',
                      H0=1e4, f=1e10, T=330.0, rng=rng)
     seeds = np.arange(1, 36 if N < 100 else 9) * 101     # 35 members: ragged last CTA (8 for the largest cluster: the oracle is dense)
     t, fl, ref, out, _ = injected_pair(orc, core, c, seeds, per_member=(N <= 4))
+    assert out['stats']['kernel'] == ('heun_small' if N <= 7 else 'heun_cluster')
     assert_traj(ref, out, c)
 
 
@@ -161,13 +164,17 @@ def test_heun_cluster_injected(orc, core, N, interactions, renorm):
 @pytest.mark.parametrize('N,renorm,members', [(8, False, 140), (12, True, 35), (20, False, 35), (24, True, 70), (40, False, 35),
                                               (56, False, 20), (64, False, 35), (64, True, 9)])
 def test_heun_cluster_mma_injected(orc, core, N, renorm, members, monkeypatch):
-    monkeypatch.setenv('MAGPY_B200_CLUSTER_KERNEL', 'mma')
+    if N in (12, 20):
+        monkeypatch.setenv('MAGPY_B200_CLUSTER_KERNEL', 'mma')
+    else:
+        monkeypatch.delenv('MAGPY_B200_CLUSTER_KERNEL', raising=False)   # the default choice for these sizes
     rng = np.random.default_rng(N)
     c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
                      dt=1e-13, t_end=3e-11, S=25, interactions=True, renorm=renorm, field_shape='sine',
                      H0=1e4, f=1e10, T=330.0, rng=rng)
     seeds = np.arange(1, members + 1) * 101
-    t, fl, ref, out, _ = injected_pair(orc, core, c, seeds)
+    t, fl, ref, out, _ = injected_pair(orc, core, c, seeds, per_member=(N == 24))
+    assert out['stats']['kernel'] == 'heun_cluster_mma'
     assert_traj(ref, out, c)
 
 
