@@ -41,28 +41,28 @@ __device__ __forceinline__ void group_barrier(const int id, const int threads) {
 
 constexpr int MMA_BLK = 576;   // doubles per 24 x 24 block of D
 
-// Operand addressing of one 24 x 24 block for this thread.  Fragment element (row 8 a + g, column 4 ks + t) of the
-// warp's A operand sits at  a_base + ks * sks + a * sa -/+ dsw  (the swizzle of a directly read block moves the
-// even k-steps up and the odd ones down by 4 sg doubles; a transposed block needs no correction).
-struct BlockPtr {
-    const double* a;
-    const double* b;
-    int sks, sa, dsw;
-};
-
-__device__ __forceinline__ void load_frags(double (&af)[3], double (&bf)[2], const BlockPtr& bp, const int ks, const int LD4) {
-    const double* ap = bp.a + ks * bp.sks + ((ks & 1) ? -bp.dsw : bp.dsw);
+// Operand addressing of one 24 x 24 block for this thread, as indices into the CTA's shared memory (32-bit: the
+// generic-pointer version of this loop cost 8 more registers).  Fragment element (row 8 a + g, column 4 ks + t) of
+// the warp's A operand sits at  a_idx + ks * sks + a * sa -/+ dsw  with (sks, sa) = (4, 192) for a block read directly
+// — where the swizzle moves the even k-steps up and the odd ones down by dsw = 4 sg doubles — and (96, 8), no
+// correction, for a block read transposed.
+__device__ __forceinline__ void load_frags(double (&af)[3], double (&bf)[2], const double* __restrict__ sm, const int a_idx,
+                                           const bool direct, const int dsw, const int b_idx, const int ks, const int LD4) {
+    const int sks = direct ? 4 : 96, sa = direct ? 192 : 8, d = direct ? dsw : 0;
+    const double* ap = sm + a_idx + ks * sks + ((ks & 1) ? -d : d);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) af[a] = ap[a * bp.sa];
-    const double* bq = bp.b + ks * LD4;
+    for (int a = 0; a < 3; ++a) af[a] = ap[a * sa];
+    const double* bq = sm + b_idx + ks * LD4;
     bf[0] = bq[0];
     bf[1] = bq[8];
 }
 
 // acc[a][j][e] = H_a(particle 8 pg + g, member 16 mh + 8 j + 2 t + e).  The operand fragments of the next k-step
-// (also across block boundaries) are loaded before the six DMMAs of the current one are issued.
-__device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double* __restrict__ sm_d,
-                                            const double* __restrict__ sm_b /* + 16 mh + g + t * LD */, const int G,
+// (also across block boundaries) are loaded before the six DMMAs of the current one are issued.  NT = live column
+// tiles of this warp (2, or 1 in a CTA of the partial last wave whose second tile holds no member).
+// sm = the CTA's shared memory: D blocks from index 0, the moment buffer row of this thread's B fragment at b0.
+template <int NT>
+__device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double* __restrict__ sm, const int b0, const int G,
                                             const int pg, const int LD, const int g, const int t) {
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -71,42 +71,37 @@ __device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double
     const int dsw = ((g >> 1) & 1) << 2, st4 = ((t >> 1) & 1) << 2;
     const int off_direct = 24 * g + t, off_transp = 24 * t + (g ^ st4);
     const int LD4 = 4 * LD, LD24 = 24 * LD;
-    auto block_ptr = [&](const int kg) {
-        BlockPtr bp;
-        bp.b = sm_b + kg * LD24;
-        if (kg >= pg) {
-            bp.a = sm_d + (pg * G - (pg * (pg - 1)) / 2 + (kg - pg)) * MMA_BLK + off_direct;
-            bp.sks = 4; bp.sa = 192; bp.dsw = dsw;
-        } else {
-            bp.a = sm_d + (kg * G - (kg * (kg - 1)) / 2 + (pg - kg)) * MMA_BLK + off_transp;
-            bp.sks = 96; bp.sa = 8; bp.dsw = 0;
-        }
-        return bp;
+    auto a_index = [&](const int kg) {
+        return kg >= pg ? (pg * G - (pg * (pg - 1)) / 2 + (kg - pg)) * MMA_BLK + off_direct
+                        : (kg * G - (kg * (kg - 1)) / 2 + (pg - kg)) * MMA_BLK + off_transp;
     };
-    BlockPtr cur = block_ptr(0);
+    int a_cur = a_index(0), b_cur = b0;
     double af[3], bf[2];
-    load_frags(af, bf, cur, 0, LD4);
+    load_frags(af, bf, sm, a_cur, 0 >= pg, dsw, b_cur, 0, LD4);
     for (int kg = 0; kg < G; ++kg) {
-        const BlockPtr nxt = block_ptr(kg + 1 < G ? kg + 1 : kg);   // the last prefetch re-reads a valid block
+        const int kn = kg + 1 < G ? kg + 1 : kg;   // the last prefetch re-reads a valid block
+        const int a_nxt = a_index(kn), b_nxt = b0 + kn * LD24;
 #pragma unroll
         for (int ks = 0; ks < 6; ++ks) {
             double an[3], bn[2];
-            if (ks < 5) load_frags(an, bn, cur, ks + 1, LD4);
-            else load_frags(an, bn, nxt, 0, LD4);
+            if (ks < 5) load_frags(an, bn, sm, a_cur, kg >= pg, dsw, b_cur, ks + 1, LD4);
+            else load_frags(an, bn, sm, a_nxt, kn >= pg, dsw, b_nxt, 0, LD4);
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) dmma884(acc[a][j][0], acc[a][j][1], af[a], bf[j]);
+                for (int j = 0; j < NT; ++j) dmma884(acc[a][j][0], acc[a][j][1], af[a], bf[j]);
 #pragma unroll
             for (int a = 0; a < 3; ++a) af[a] = an[a];
             bf[0] = bn[0]; bf[1] = bn[1];
         }
-        cur = nxt;
+        a_cur = a_nxt;
+        b_cur = b_nxt;
     }
 }
 
-// blockDim.x = 32 * G * MH.  Warp w: particle group pg = w % G, member half mh = w / G.
-template <int NOISE, bool FIELD_TAB, bool ONE_BUF>
+// TAIL = false: a CTA of the whole waves (all column tiles live, the fast path); TAIL = true: a CTA of the partial last
+// wave, launched separately (P.cta_offset), whose warps may have 2, 1 or 0 live column tiles.
+template <int NOISE, bool FIELD_TAB, bool ONE_BUF, bool TAIL>
 __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_constant__ RunParams P) {
     extern __shared__ double smem[];
     const int N = (int)P.N, G = (int)P.G;
@@ -137,12 +132,26 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     const int bar_id = 1 + mh, bar_n = 32 * G;
 
     // the thread's four members: q = 2 j + e  ->  local column 16 mh + 8 j + 2 t + e
-    const uint64_t r_base = (uint64_t)blockIdx.x * MB + 16 * mh + 2 * t;
-    auto is_live = [&](const int q) { return r_base + 8 * (q >> 1) + (q & 1) < P.R; };
-    auto member = [&](const int q) {   // members past the end repeat the last one (computed, never stored)
+    // Members of this CTA: the first P.mma_full CTAs (whole waves) take MB each; the CTAs of the partial last wave
+    // take P.mma_tail (a multiple of 8 <= MB) so that the wave's work is spread over all SMs in column tiles of 8.
+    const uint32_t cta = blockIdx.x + P.cta_offset;
+    const uint64_t cta_start = (!TAIL || cta < P.mma_full)
+                                   ? (uint64_t)cta * MB
+                                   : (uint64_t)P.mma_full * MB + (uint64_t)(cta - P.mma_full) * P.mma_tail;
+    const int cta_cnt = (!TAIL || cta < P.mma_full) ? MB : (int)P.mma_tail;
+    const uint64_t r_base = cta_start + 16 * mh + 2 * t;
+    auto is_live = [&](const int q) {
+        const int o = 8 * (q >> 1) + (q & 1);
+        return (!TAIL || 16 * mh + 2 * t + o < cta_cnt) && r_base + o < P.R;
+    };
+    auto member = [&](const int q) {   // dead columns repeat the last member (computed, never stored)
         const uint64_t r_raw = r_base + 8 * (q >> 1) + (q & 1);
         return r_raw < P.R ? r_raw : P.R - 1;
     };
+    // live column tiles of this warp (the same for all warps of a member half): tile j = columns 16 mh + 8 j .. + 7
+    const int n_tiles = !TAIL ? 2
+                        : (16 * mh < cta_cnt && cta_start + 16 * mh < P.R)
+                            ? ((16 * mh + 8 < cta_cnt && cta_start + 16 * mh + 8 < P.R) ? 2 : 1) : 0;
     V3 m[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -151,20 +160,23 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     }
     // own rows of the moment buffers: row(comp a) = 24 pg + 8 a + g, columns 16 mh + 8 j + 2 t + {0, 1}
     const int own_off = (24 * pg + g) * LD + 16 * mh + 2 * t;
-    auto put = [&](double* buf, const V3 (&x)[4]) {
+    // NT (live column tiles of the warp, a compile-time constant of the step loop) bounds every per-member loop
+    auto put = [&](auto nt, double* buf, const V3 (&x)[4]) {
+        constexpr int NT = decltype(nt)::value;
         if (!valid) return;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < NT; ++j) {
             double* d = buf + own_off + 8 * j;
             *reinterpret_cast<double2*>(d) = make_double2(vred * x[2 * j].x, vred * x[2 * j + 1].x);
             *reinterpret_cast<double2*>(d + 8 * LD) = make_double2(vred * x[2 * j].y, vred * x[2 * j + 1].y);
             *reinterpret_cast<double2*>(d + 16 * LD) = make_double2(vred * x[2 * j].z, vred * x[2 * j + 1].z);
         }
     };
-    put(sm_m, m);
+    put(std::integral_constant<int, 2>{}, sm_m, m);
     __syncthreads();
-    const double* b_m = sm_m + t * LD + 16 * mh + g;
-    const double* b_t = sm_t + t * LD + 16 * mh + g;
+    // this thread's B-fragment row of the two moment buffers, as indices into smem
+    const int b_m = (int)(sm_m - smem) + t * LD + 16 * mh + g;
+    const int b_t = (int)(sm_t - smem) + t * LD + 16 * mh + g;
 
     constexpr bool PACKED = NOISE == NOISE_PHILOX_PACKED;
     // scaled increments of the current step: kept as the fp32 the packed generator produces (widened at use) so that
@@ -173,9 +185,10 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
         typename std::conditional<PACKED, float, double>::type x, y, z;
     };
     const double inv_v = 1.0 / vred;
-    auto get = [&](const double* buf, V3 (&x)[4]) {   // own moments back from a moment buffer
+    auto get = [&](auto nt, const double* buf, V3 (&x)[4]) {   // own moments back from a moment buffer
+        constexpr int NT = decltype(nt)::value;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < NT; ++j) {
             const double* d = buf + own_off + 8 * j;
             const double2 vx = *reinterpret_cast<const double2*>(d), vy = *reinterpret_cast<const double2*>(d + 8 * LD),
                           vz = *reinterpret_cast<const double2*>(d + 16 * LD);
@@ -185,9 +198,11 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     };
 
     // g_q = dt h_q + cw_q with h = anisotropy + applied + dipolar (acc)
-    auto stage_g = [&](V3 (&gq)[4], const V3 (&x)[4], const double (&acc)[3][2][2], const double hz, const Inc (&cw)[4]) {
+    auto stage_g = [&](auto nt, V3 (&gq)[4], const V3 (&x)[4], const double (&acc)[3][2][2], const double hz,
+                       const Inc (&cw)[4]) {
+        constexpr int NQ = 2 * decltype(nt)::value;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const uint64_t c0 = 3ull * pid, rq = member(q);
             const V3 e{__ldg(P.axis + c0 * P.axis_cs + rq * P.axis_rs), __ldg(P.axis + (c0 + 1) * P.axis_cs + rq * P.axis_rs),
                        __ldg(P.axis + (c0 + 2) * P.axis_cs + rq * P.axis_rs)};
@@ -198,7 +213,8 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
         }
     };
 
-    auto advance = [&](const Inc (&cw)[4], const uint64_t jj) {
+    auto advance = [&](auto nt, const Inc (&cw)[4], const uint64_t jj) {
+        constexpr int NT = decltype(nt)::value, NQ = 2 * NT;
         double hz0 = P.h_const, hz1 = P.h_const;
         if (FIELD_TAB) {
             const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (jj - P.j0));
@@ -206,34 +222,34 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
         }
         double acc[3][2][2];
         V3 gq[4];
-        if (inter) dipolar_mma(acc, sm_d, b_m, G, pg, LD, g, t);
+        if (inter) dipolar_mma<NT>(acc, smem, b_m, G, pg, LD, g, t);
         else {
 #pragma unroll
             for (int a = 0; a < 3; ++a) acc[a][0][0] = acc[a][0][1] = acc[a][1][0] = acc[a][1][1] = 0.0;
         }
-        stage_g(gq, m, acc, hz0, cw);
+        stage_g(nt, gq, m, acc, hz0, cw);
         if (ONE_BUF) group_barrier(bar_id, bar_n);   // every warp of the group has read the current moments
         {
             V3 mt[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < NQ; ++q) {
                 const V3 pc = cross(m[q], gq[q]);
                 const V3 u{fma(alpha, pc.x, gq[q].x), fma(alpha, pc.y, gq[q].y), fma(alpha, pc.z, gq[q].z)};
                 mt[q] = V3{fma(-m[q].y, u.z, fma(m[q].z, u.y, m[q].x)), fma(-m[q].z, u.x, fma(m[q].x, u.z, m[q].y)),
                            fma(-m[q].x, u.y, fma(m[q].y, u.x, m[q].z))};
             }
-            put(sm_t, mt);
+            put(nt, sm_t, mt);
         }
         group_barrier(bar_id, bar_n);
-        if (inter) dipolar_mma(acc, sm_d, b_t, G, pg, LD, g, t);
+        if (inter) dipolar_mma<NT>(acc, smem, b_t, G, pg, LD, g, t);
         // the predictor moments are not kept in registers across the second product: the thread reads its own back
         // from shared memory (exact when v_red = 1; otherwise one rounding of v (1/v), 12 orders below the noise)
         V3 mt[4];
-        get(sm_t, mt);
-        stage_g(gq, mt, acc, hz1, cw);
+        get(nt, sm_t, mt);
+        stage_g(nt, gq, mt, acc, hz1, cw);
         if (ONE_BUF) group_barrier(bar_id, bar_n);   // every warp of the group has read the predictor moments
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const V3 pc = cross(mt[q], gq[q]);
             const V3 u{fma(alpha, pc.x, gq[q].x), fma(alpha, pc.y, gq[q].y), fma(alpha, pc.z, gq[q].z)};
             const V3 hm{0.5 * mt[q].x, 0.5 * mt[q].y, 0.5 * mt[q].z};
@@ -242,26 +258,27 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
                       fma(-hm.x, u.y, fma(hm.y, u.x, hh.z))};
             if (renorm) renormalise(m[q]);
         }
-        put(sm_m, m);
+        put(nt, sm_m, m);
         group_barrier(bar_id, bar_n);
     };
 
     float carry[PACKED ? 4 : 1][3];
     bool have_carry = false;
     uint64_t j = P.j0;
-    for (uint32_t k = P.k0; k <= P.k1; ++k) {
-        const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+    // all steps up to state index tgt for a warp with NT live column tiles
+    auto steps_to = [&](auto nt, const uint64_t tgt) {
+        constexpr int NQ = 2 * decltype(nt)::value;
         for (; j < tgt; ++j) {
             Inc cw[4];
             if constexpr (PACKED) {
                 const bool odd = (j & 1) != 0;
                 if (odd && have_carry) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) cw[q] = Inc{carry[q][0], carry[q][1], carry[q][2]};
+                    for (int q = 0; q < NQ; ++q) cw[q] = Inc{carry[q][0], carry[q][1], carry[q][2]};
                     have_carry = false;
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < NQ; ++q) {
                         const uint64_t rq = member(q), seed = (uint64_t)__ldg(P.seeds + rq);
                         float g6[6];
                         philox_gauss6_f32((uint32_t)seed, (uint32_t)(seed >> 32), j >> 1, pid, (uint32_t)(rq + P.stream_offset),
@@ -273,15 +290,21 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < NQ; ++q) {
                     const uint64_t rq = member(q), seed = (uint64_t)__ldg(P.seeds + rq);
                     const V3 w = draw_scaled<NOISE>(P, (uint32_t)seed, (uint32_t)(seed >> 32), j, pid,
                                                     (uint32_t)(rq + P.stream_offset), rq, csig, bm);
                     cw[q] = Inc{w.x, w.y, w.z};
                 }
             }
-            advance(cw, j);
+            advance(nt, cw, j);
         }
+    };
+    for (uint32_t k = P.k0; k <= P.k1; ++k) {
+        const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+        if (!TAIL || n_tiles == 2) steps_to(std::integral_constant<int, 2>{}, tgt);
+        else if (n_tiles == 1) steps_to(std::integral_constant<int, 1>{}, tgt);
+        else j = tgt;   // a member half without members only joins the CTA-wide sample reduction
         if (k < P.k1) {
             if (P.traj != nullptr && valid) {
 #pragma unroll
@@ -323,7 +346,7 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
                     }
                     v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
                     if (lane == 0) {
-                        double* o = P.partial + ((uint64_t)(k - P.k0) * gridDim.x + blockIdx.x) * 4;
+                        double* o = P.partial + ((uint64_t)(k - P.k0) * P.cta_total + cta) * 4;
                         o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3;
                     }
                 }
@@ -342,29 +365,37 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
 }
 
 template <int NOISE, bool TAB>
-static cudaError_t launch_hm(bool one_buf, unsigned grid, unsigned threads, size_t smem, cudaStream_t s, const RunParams& P) {
-    auto go = [&](auto kernel) -> cudaError_t {
+static cudaError_t launch_hm(bool one_buf, unsigned full_ctas, unsigned tail_ctas, unsigned threads, size_t smem, cudaStream_t s,
+                             RunParams P) {
+    auto go = [&](auto kernel, unsigned grid, unsigned offset) -> cudaError_t {
+        if (grid == 0) return cudaSuccess;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
+        P.cta_offset = offset;
         kernel<<<grid, threads, smem, s>>>(P);
         return cudaGetLastError();
     };
-    return one_buf ? go(heun_cluster_mma_kernel<NOISE, TAB, true>) : go(heun_cluster_mma_kernel<NOISE, TAB, false>);
+    P.cta_total = full_ctas + tail_ctas;
+    cudaError_t e = one_buf ? go(heun_cluster_mma_kernel<NOISE, TAB, true, false>, full_ctas, 0)
+                            : go(heun_cluster_mma_kernel<NOISE, TAB, false, false>, full_ctas, 0);
+    if (e != cudaSuccess) return e;
+    return one_buf ? go(heun_cluster_mma_kernel<NOISE, TAB, true, true>, tail_ctas, full_ctas)
+                   : go(heun_cluster_mma_kernel<NOISE, TAB, false, true>, tail_ctas, full_ctas);
 }
 
-cudaError_t launch_heun_cluster_mma(int noise, bool tab, bool one_buf, unsigned grid, unsigned threads, size_t smem,
-                                    cudaStream_t s, const RunParams& P) {
+cudaError_t launch_heun_cluster_mma(int noise, bool tab, bool one_buf, unsigned full_ctas, unsigned tail_ctas, unsigned threads,
+                                    size_t smem, cudaStream_t s, const RunParams& P) {
     switch (noise) {
-        case NOISE_PHILOX_F32: return tab ? launch_hm<NOISE_PHILOX_F32, true>(one_buf, grid, threads, smem, s, P)
-                                          : launch_hm<NOISE_PHILOX_F32, false>(one_buf, grid, threads, smem, s, P);
-        case NOISE_PHILOX_F64: return tab ? launch_hm<NOISE_PHILOX_F64, true>(one_buf, grid, threads, smem, s, P)
-                                          : launch_hm<NOISE_PHILOX_F64, false>(one_buf, grid, threads, smem, s, P);
-        case NOISE_INJECTED: return tab ? launch_hm<NOISE_INJECTED, true>(one_buf, grid, threads, smem, s, P)
-                                        : launch_hm<NOISE_INJECTED, false>(one_buf, grid, threads, smem, s, P);
-        default: return tab ? launch_hm<NOISE_PHILOX_PACKED, true>(one_buf, grid, threads, smem, s, P)
-                            : launch_hm<NOISE_PHILOX_PACKED, false>(one_buf, grid, threads, smem, s, P);
+        case NOISE_PHILOX_F32: return tab ? launch_hm<NOISE_PHILOX_F32, true>(one_buf, full_ctas, tail_ctas, threads, smem, s, P)
+                                          : launch_hm<NOISE_PHILOX_F32, false>(one_buf, full_ctas, tail_ctas, threads, smem, s, P);
+        case NOISE_PHILOX_F64: return tab ? launch_hm<NOISE_PHILOX_F64, true>(one_buf, full_ctas, tail_ctas, threads, smem, s, P)
+                                          : launch_hm<NOISE_PHILOX_F64, false>(one_buf, full_ctas, tail_ctas, threads, smem, s, P);
+        case NOISE_INJECTED: return tab ? launch_hm<NOISE_INJECTED, true>(one_buf, full_ctas, tail_ctas, threads, smem, s, P)
+                                        : launch_hm<NOISE_INJECTED, false>(one_buf, full_ctas, tail_ctas, threads, smem, s, P);
+        default: return tab ? launch_hm<NOISE_PHILOX_PACKED, true>(one_buf, full_ctas, tail_ctas, threads, smem, s, P)
+                            : launch_hm<NOISE_PHILOX_PACKED, false>(one_buf, full_ctas, tail_ctas, threads, smem, s, P);
     }
 }
 

@@ -17,8 +17,9 @@ cudaError_t launch_imid_small(int noise, bool tab, unsigned n_particles, unsigne
 cudaError_t launch_heun_cluster(int noise, bool tab, int np, int layout, dim3 grid, dim3 block, size_t smem,
                                 cudaStream_t s, const RunParams& P);
 // K2m (cluster_mma.cu): threads = 32 * G * member halves; one_buf = predictor overwrites the current moments
-cudaError_t launch_heun_cluster_mma(int noise, bool tab, bool one_buf, unsigned grid, unsigned threads, size_t smem,
-                                    cudaStream_t s, const RunParams& P);
+// two launches: `full_ctas` CTAs with a full set of members (whole waves), then `tail_ctas` CTAs of the partial last wave
+cudaError_t launch_heun_cluster_mma(int noise, bool tab, bool one_buf, unsigned full_ctas, unsigned tail_ctas, unsigned threads,
+                                    size_t smem, cudaStream_t s, const RunParams& P);
 cudaError_t launch_imid_cluster(int noise, bool tab, int np, dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                 const RunParams& P);
 

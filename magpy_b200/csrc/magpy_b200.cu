@@ -197,6 +197,7 @@ struct magpy_b200_plan {
     bool mma = false;      // Heun cluster kernel on the FP64 MMA path (cluster_mma.cu)
     bool one_buf = false;  //   ... with one shared-memory moment buffer
     uint32_t G = 0;        //   ... particle groups of 8
+    uint32_t mma_full = 0, mma_tail = 0;   //   ... member distribution over CTAs (see choose_mma)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
@@ -252,7 +253,9 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
         if (pl->implicit) LAUNCH_TRY(mb::launch_imid_small(noise, tab, pl->N, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_small(noise, tab, pl->N, pl->grid, pl->stream, P));
     } else if (pl->mma) {
-        LAUNCH_TRY(mb::launch_heun_cluster_mma(noise, tab, pl->one_buf, pl->grid, pl->block.x, pl->smem, pl->stream, P));
+        LAUNCH_TRY(mb::launch_heun_cluster_mma(noise, tab, pl->one_buf, pl->mma_full, pl->grid - pl->mma_full, pl->block.x, pl->smem,
+                                               pl->stream, P));
+        if (pl->mma_full > 0 && pl->grid > pl->mma_full) pl->launches++;   // whole waves + partial last wave
     } else if (pl->implicit) {
         LAUNCH_TRY(mb::launch_imid_cluster(noise, tab, pl->np, dim3(pl->grid), pl->block, pl->smem, pl->stream, P));
     } else {
@@ -336,7 +339,26 @@ bool choose_mma(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     pl->G = G;
     pl->np = 1;
     pl->block = dim3(32 * G * MH);
-    pl->grid = (unsigned)((pl->R + 16 * MH - 1) / (16 * MH));
+    // whole waves of full CTAs (one CTA per SM: shared memory) + a last wave spread over all SMs in column tiles of 8
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    const uint64_t MB = 16 * MH, full_ctas = pl->R / MB;
+    const uint64_t threads = 32ull * G * MH;
+    const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>({cap / pl->smem, 65536 / (128 * threads), 2048 / threads}));
+    const uint64_t ctas_per_wave = (uint64_t)sms * per_sm;
+    pl->mma_full = (uint32_t)(full_ctas / ctas_per_wave * ctas_per_wave);
+    // few particle groups: a CTA's time is set by the update / noise latency of a warp, not by its column tiles —
+    // thinning the CTAs of the last wave buys nothing there (measured, N = 8), so it stays a plain ragged grid
+    if (G < 2) pl->mma_full = (uint32_t)((pl->R + MB - 1) / MB);
+    const uint64_t rest = pl->R > (uint64_t)pl->mma_full * MB ? pl->R - (uint64_t)pl->mma_full * MB : 0;
+    pl->mma_tail = (uint32_t)MB;
+    uint64_t tail_ctas = 0;
+    if (rest > 0) {
+        const uint64_t tiles = (rest + 7) / 8, per_cta = std::min<uint64_t>(MB / 8, (tiles + ctas_per_wave - 1) / ctas_per_wave);
+        pl->mma_tail = (uint32_t)(8 * per_cta);
+        tail_ctas = (rest + pl->mma_tail - 1) / pl->mma_tail;
+    }
+    pl->grid = (unsigned)(pl->mma_full + tail_ctas);
     return true;
 }
 
@@ -624,6 +646,8 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.dmat = pl->d_dmat.p;
     P.v_red = pl->d_vred.p;
     P.G = pl->G;
+    P.mma_full = pl->mma_full;
+    P.mma_tail = pl->mma_tail;
     P.axis = pl->d_axis.p;
     P.axis_cs = a->axis_stride ? R : 1;
     P.axis_rs = a->axis_stride ? 1 : 0;

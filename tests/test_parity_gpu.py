@@ -178,6 +178,27 @@ def test_heun_cluster_mma_injected(orc, core, N, renorm, members, monkeypatch):
     assert_traj(ref, out, c)
 
 
+@pytest.mark.parametrize('N', [16, 64])
+def test_mma_member_distribution_is_invisible(core, N):
+    """K2m gives whole waves of CTAs a full set of members and spreads the rest over all SMs in column tiles of 8:
+    a member's trajectory must not depend on where it lands.  A run large enough for full CTAs plus a ragged tail is
+    compared, member by member, with small runs of slices of the same ensemble (same seeds, stream_offset)."""
+    rng = np.random.default_rng(N)
+    c = ol.make_case(N=N, radius=7e-9, anisotropy=1e5, dt=1e-13, t_end=1.2e-12, S=4, interactions=True, T=330.0, rng=rng)
+    per_cta = 32 if N == 64 else 128
+    R = 148 * 2 * per_cta + 3 * per_cta // 2 + 5 if N == 16 else 148 * per_cta + 45
+    seeds = rng.integers(1, 2 ** 31 - 1, R)
+    big = gpu_run(core, c, seeds, return_trajectories=False)
+    assert big['stats']['kernel'] == 'heun_cluster_mma'
+    for lo, hi in ((0, 40), (per_cta - 3, per_cta + 9), (R - 50, R)):
+        small = gpu_run(core, c, seeds[lo:hi], stream_offset=lo, return_trajectories=False)
+        assert np.array_equal(big['final'][lo:hi], small['final'])
+    # fused ensemble sums of the big run against its own final states (last sample = final state)
+    M = big['final'].sum(axis=1)
+    want = np.array([M[:, 0].sum(), M[:, 1].sum(), M[:, 2].sum(), (M[:, 2] ** 2).sum()])
+    assert np.allclose(big['sums'][-1], want, rtol=1e-11)
+
+
 @pytest.mark.parametrize('N,interactions', [(2, True), (3, False), (4, True), (5, True), (12, True), (32, True)])
 def test_implicit_cluster_injected(orc, core, N, interactions):
     rng = np.random.default_rng(100 + N)
