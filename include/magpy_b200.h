@@ -68,6 +68,7 @@ typedef struct magpy_b200_stats {
 #define MAGPY_B200_KERNEL_HEUN_CLUSTER 5     /* cluster.cu: scalar dipolar sum from shared memory            */
 #define MAGPY_B200_KERNEL_IMID_CLUSTER 6     /* cluster.cu                                                   */
 #define MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA 7 /* cluster_mma.cu: dipolar field as a matrix product (DMMA)     */
+#define MAGPY_B200_KERNEL_IMID_SPLIT 8       /* small_imid.cu: one lane per particle (small ensembles, N = 2, 4) */
 
 /* One ensemble of `n_members` independent clusters that share geometry and material
  * (radius, anisotropy, location, Ms, damping, T, field) and may differ in anisotropy

@@ -366,8 +366,9 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
             __syncthreads();
             double nrm = 0.0;
             for (int s2 = 0; s2 < PS; ++s2) nrm += sm_red[s2 * CL_LANES + lane];
-            const double tol = P.eps * sqrt(nrm);
-            double err = 2 * tol;
+            // err > tol is tested on the squares (no square root in the dependent chain of an iteration)
+            const double tol = (P.eps * P.eps) * nrm;
+            double err = 4 * tol;
             int iter = 1000;
             unsigned long long done = 0;
             bool singular = false;
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
                     if (bad != 0.0) {
                         singular = true;
                     } else {
-                        err = sqrt(e2);
+                        err = e2;
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             if (!own[q].valid) continue;

@@ -38,13 +38,23 @@ __device__ __forceinline__ V3 llg_f(const V3& m, const V3& g, const double alpha
 // scheme is usable, where the adjugate matches pivoted elimination to a few ulp: trajectories stay within 1e-10 of
 // the reference and the iteration counts stay identical (tests/test_parity_gpu.py).  det == 0 is reported the way
 // dgesv reports a zero pivot (info > 0).
+// 1 / x for the determinant of a quasi-Newton block: MUFU.RCP64H seed (20 bits) + two Newton steps, <= 1 ulp for the
+// well-scaled determinants (1 + O(dt)) of this iteration, without the exponent range checks and the slow-path call
+// of the IEEE division (which sit in the dependent chain of every iteration).
+__device__ __forceinline__ double rcp_newton(const double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
 __device__ __forceinline__ bool solve3_adjugate(const double A[9], const double b[3], double d[3]) {
     const double c00 = fma(A[4], A[8], -A[5] * A[7]), c01 = fma(A[5], A[6], -A[3] * A[8]), c02 = fma(A[3], A[7], -A[4] * A[6]);
     const double det = fma(A[0], c00, fma(A[1], c01, A[2] * c02));
     if (det == 0.0) return false;
     const double c10 = fma(A[2], A[7], -A[1] * A[8]), c11 = fma(A[0], A[8], -A[2] * A[6]), c12 = fma(A[1], A[6], -A[0] * A[7]);
     const double c20 = fma(A[1], A[5], -A[2] * A[4]), c21 = fma(A[2], A[3], -A[0] * A[5]), c22 = fma(A[0], A[4], -A[1] * A[3]);
-    const double inv = 1.0 / det;
+    const double inv = rcp_newton(det);
     // d = adj(A) b / det,  adj(A)[i][j] = cofactor[j][i]
     d[0] = inv * fma(c00, b[0], fma(c10, b[1], c20 * b[2]));
     d[1] = inv * fma(c01, b[0], fma(c11, b[1], c21 * b[2]));

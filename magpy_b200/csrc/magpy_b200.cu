@@ -194,6 +194,7 @@ struct magpy_b200_plan {
     bool use_table = false;
     bool axis_z = false;   // N = 1 and one shared easy axis exactly along +z: specialised Heun kernel
     bool small = false;    // few particles: one thread per cluster, all moments in registers
+    bool split = false;    //   ... implicit, one lane per particle (imid_split_kernel)
     bool mma = false;      // Heun cluster kernel on the FP64 MMA path (cluster_mma.cu)
     bool one_buf = false;  //   ... with one shared-memory moment buffer
     uint32_t G = 0;        //   ... particle groups of 8
@@ -250,7 +251,8 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
         if (pl->implicit) LAUNCH_TRY(mb::launch_imid_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
     } else if (pl->small) {
-        if (pl->implicit) LAUNCH_TRY(mb::launch_imid_small(noise, tab, pl->N, pl->grid, pl->stream, P));
+        if (pl->split) LAUNCH_TRY(mb::launch_imid_split(noise, tab, pl->N, pl->grid, pl->stream, P));
+        else if (pl->implicit) LAUNCH_TRY(mb::launch_imid_small(noise, tab, pl->N, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_small(noise, tab, pl->N, pl->grid, pl->stream, P));
     } else if (pl->mma) {
         LAUNCH_TRY(mb::launch_heun_cluster_mma(noise, tab, pl->one_buf, pl->mma_full, pl->grid - pl->mma_full, pl->block.x, pl->smem,
@@ -411,6 +413,23 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         pl->grid = (unsigned)((R + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
         pl->smem = 0;
         pl->np = 1;
+        // implicit tetramers that cannot give every warp scheduler two warps at one thread per cluster are latency
+        // bound: one lane per particle instead (small_imid.cu, imid_split_kernel; a dimer's two particles already
+        // interleave in one thread, so it gains nothing).
+        // MAGPY_B200_SMALL_KERNEL=split|thread overrides the choice.
+        if (pl->implicit && (N == 2 || N == 4)) {   // measured (profiles/r01_probe_c2.log): a gain for N = 4 only
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+            bool split = N == 4 && R < (uint64_t)sms * 4 * 2 * 32;
+            if (const char* force = std::getenv("MAGPY_B200_SMALL_KERNEL")) {
+                if (std::strcmp(force, "split") == 0) split = R * N < 0xFFFFFFFFull;
+                else if (std::strcmp(force, "thread") == 0) split = false;
+            }
+            if (split) {
+                pl->split = true;
+                pl->grid = (unsigned)((R * N + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
+            }
+        }
     } else if (choose_mma(a, pl)) {
         // cluster_mma.cu: dipolar field as a matrix product on DMMA; geometry set by choose_mma
     } else {
@@ -707,6 +726,7 @@ int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
     st->h2d_bytes = pl->h2d;
     st->d2h_bytes = pl->d2h;
     st->kernel_family = pl->N == 1 ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SINGLE : MAGPY_B200_KERNEL_HEUN_SINGLE)
+                        : pl->split ? MAGPY_B200_KERNEL_IMID_SPLIT
                         : pl->small ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SMALL : MAGPY_B200_KERNEL_HEUN_SMALL)
                         : pl->mma   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA
                                     : (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER : MAGPY_B200_KERNEL_HEUN_CLUSTER);

@@ -60,12 +60,13 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
                 X[i] = V3{(f.x + m[i].x) / 2, (f.y + m[i].y) / 2, (f.z + m[i].z) / 2};
                 nrm += dot(X[i], X[i]);
             }
-            const double tol = P.eps * sqrt(nrm);
-            double err = 2 * tol;
+            // err > tol is tested on the squares (no square root in the dependent chain of an iteration)
+            const double tol2 = (P.eps * P.eps) * nrm;
+            double err2 = 4 * tol2;
             int iter = 1000;
             unsigned long long done = 0;
             bool singular = false;
-            while ((err > tol) && (iter-- > 0)) {
+            while ((err2 > tol2) && (iter-- > 0)) {
                 small_fields<N>(h, X, e, kred, hz1, sd, inter, zero);
                 V3 dl[N], b[N];
                 bool ok = true;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
                     singular = true;
                     break;
                 }
-                err = sqrt(e2);
+                err2 = e2;
 #pragma unroll
                 for (int i = 0; i < N; ++i) { X[i].x += dl[i].x; X[i].y += dl[i].y; X[i].z += dl[i].z; }
             }
@@ -116,6 +117,141 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
     newton_flush(P, nc, live);
 }
 
+// ---------------------------------------------------------------------------------
+// implicit midpoint, ONE LANE PER PARTICLE (N = 2 or 4 adjacent lanes form a cluster)
+//
+// For small ensembles the thread-per-cluster kernel is latency bound: 10,000 dimers are 313 warps on 592 warp
+// schedulers, each walking the N particles of its cluster one after the other through ~20 quasi-Newton iterations
+// per step.  Here the particles of a cluster sit on adjacent lanes and exchange the midpoint iterate with shuffles
+// (no shared memory, no barrier), which divides the dependent instruction chain of an iteration by N.  Same
+// arithmetic per particle as imid_small_kernel; the two norms are summed by a butterfly over the cluster's lanes,
+// which gives every lane the same value (each level adds the same two numbers in either order) and, for N = 2,
+// the same value as the sequential sum.  The host picks this kernel when the ensemble cannot fill the GPU with
+// one thread per cluster.
+// ---------------------------------------------------------------------------------
+template <int NOISE, bool FIELD_TAB, int N>
+__global__ void __launch_bounds__(SMALL_THREADS) imid_split_kernel(const __grid_constant__ RunParams P) {
+    static_assert(N == 2 || N == 4, "lanes per cluster");
+    __shared__ double red[(SMALL_THREADS / 32) * 4];
+    __shared__ __align__(32) double sd[N * N * 4];
+    stage_pair_table<N>(sd, P, 1.0);
+    const uint32_t tid = blockIdx.x * SMALL_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, p = lane & (N - 1), base = lane & ~(N - 1);
+    const unsigned cmask = ((1u << N) - 1u) << base;   // the lanes of this cluster
+    const uint64_t r_raw = tid / N;
+    const bool live = r_raw < P.R;
+    const uint64_t r = live ? r_raw : P.R - 1;
+    const double alpha = P.alpha, dt = P.dt, clampA = P.clampA, sqrt_dt = P.sqrt_dt;
+    const bool inter = P.interactions != 0, renorm = P.renorm != 0;
+
+    const uint64_t c0 = 3ull * p;
+    V3 m{P.state[c0 * P.R + r], P.state[(c0 + 1) * P.R + r], P.state[(c0 + 2) * P.R + r]};
+    const V3 e{P.axis[c0 * P.axis_cs + r * P.axis_rs], P.axis[(c0 + 1) * P.axis_cs + r * P.axis_rs],
+               P.axis[(c0 + 2) * P.axis_cs + r * P.axis_rs]};
+    const V3 e0{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
+    const double kred = P.k_red[p], sr = P.sig[p];
+    const V3 qu = quirk_u(N, p, e0, P.k_red[0]);
+    const uint64_t seed = (uint64_t)P.seeds[r];
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    NewtonCount nc{0ull, 0ull, 0ull};
+
+    // effective field of the own particle from the cluster's moments (own = x, the others by shuffle)
+    auto field = [&](const V3& x, const double hz) {
+        const double s = dot(x, e) * kred;
+        V3 h{s * e.x, s * e.y, fma(s, e.z, hz)};
+#pragma unroll
+        for (int o = 1; o < N; ++o) {   // partner lanes p ^ o: every lane of the cluster executes every shuffle
+            const int jp = p ^ o;
+            const V3 xj{__shfl_xor_sync(cmask, x.x, o), __shfl_xor_sync(cmask, x.y, o), __shfl_xor_sync(cmask, x.z, o)};
+            if (inter) {
+                const double4 tt = *reinterpret_cast<const double4*>(sd + (p * N + jp) * 4);
+                const double d = xj.x * tt.x + xj.y * tt.y + xj.z * tt.z;
+                h.x = fma(tt.w, fma(d, tt.x, -xj.x), h.x);
+                h.y = fma(tt.w, fma(d, tt.y, -xj.y), h.y);
+                h.z = fma(tt.w, fma(d, tt.z, -xj.z), h.z);
+            }
+        }
+        return h;
+    };
+    auto cluster_sum = [&](double v) {
+#pragma unroll
+        for (int o = 1; o < N; o <<= 1) v += __shfl_xor_sync(cmask, v, o);
+        return v;
+    };
+
+    uint64_t j = P.j0;
+    for (uint32_t k = P.k0; k <= P.k1; ++k) {
+        const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+        for (; j < tgt; ++j) {
+            double hz0 = P.h_const, hz1 = P.h_const;
+            if (FIELD_TAB) {
+                const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - P.j0));
+                hz0 = h.x; hz1 = h.y;
+            }
+            const V3 w = draw_noise<NOISE>(P, key0, key1, j, (uint32_t)p, member, r);
+            const V3 wm{fmax(-clampA, fmin(clampA, w.x)) * sqrt_dt, fmax(-clampA, fmin(clampA, w.y)) * sqrt_dt,
+                        fmax(-clampA, fmin(clampA, w.z)) * sqrt_dt};
+            const V3 sw{sr * wm.x, sr * wm.y, sr * wm.z};
+            V3 X;
+            {
+                const V3 h = field(m, hz0);
+                const V3 g{fma(h.x, dt, sw.x), fma(h.y, dt, sw.y), fma(h.z, dt, sw.z)};
+                const V3 f = llg_f(m, g, alpha);
+                X = V3{(f.x + m.x) / 2, (f.y + m.y) / 2, (f.z + m.z) / 2};
+            }
+            const double tol2 = (P.eps * P.eps) * cluster_sum(dot(X, X));
+            double err2 = 4 * tol2;
+            int iter = 1000;
+            unsigned long long done = 0;
+            bool singular = false;
+            while ((err2 > tol2) && (iter-- > 0)) {   // err2, tol2 and iter are the same on every lane of the cluster
+                const V3 h = field(X, hz1);
+                const V3 g{fma(h.x, dt, sw.x), fma(h.y, dt, sw.y), fma(h.z, dt, sw.z)};
+                const V3 f = llg_f(X, g, alpha);
+                double bb[3] = {-(X.x - m.x - 0.5 * f.x), -(X.y - m.y - 0.5 * f.y), -(X.z - m.z - 0.5 * f.z)};
+                double A[9], d[3];
+                newton_matrix(A, X, alpha, h, sw, qu, e0);
+                const bool ok = solve3_adjugate(A, bb, d);
+                if (!ok) d[0] = d[1] = d[2] = 0.0;
+                const double e2 = cluster_sum(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                const bool all_ok = cluster_sum(ok ? 0.0 : 1.0) == 0.0;
+                ++done;
+                if (!all_ok) {   // dgesv info > 0: the reference returns with x_root = -F (lib/optimisation.cpp:134-137)
+                    X = V3{bb[0], bb[1], bb[2]};
+                    singular = true;
+                    break;
+                }
+                err2 = e2;
+                X.x += d[0]; X.y += d[1]; X.z += d[2];
+            }
+            if (p == 0) {
+                nc.total += done;
+                nc.worst = done > nc.worst ? done : nc.worst;
+                nc.fails += (singular || iter == -1) ? 1ull : 0ull;
+            }
+            m = V3{2 * X.x - m.x, 2 * X.y - m.y, 2 * X.z - m.z};
+            if (renorm) renormalise(m);
+        }
+        if (k < P.k1) {
+            if (P.traj != nullptr && live) {
+                double* t = P.traj + ((uint64_t)k * 3 * N + 3 * p) * P.R + r;
+                t[0] = m.x; t[P.R] = m.y; t[2 * P.R] = m.z;
+            }
+            if (P.partial != nullptr) {
+                const double Mz = cluster_sum(m.z);   // cluster magnetisation, identical on the cluster's lanes
+                const double sx = live ? m.x : 0.0, sy = live ? m.y : 0.0, sz = live ? m.z : 0.0;
+                cta_partial_sums<SMALL_THREADS / 32>(sx, sy, sz, (live && p == 0) ? Mz * Mz : 0.0, red,
+                                                     P.partial + ((uint64_t)(k - P.k0) * gridDim.x + blockIdx.x) * 4);
+            }
+        }
+    }
+    if (live) {
+        P.state[c0 * P.R + r] = m.x; P.state[(c0 + 1) * P.R + r] = m.y; P.state[(c0 + 2) * P.R + r] = m.z;
+    }
+    newton_flush(P, nc, live && p == 0);
+}
+
 template <int NOISE, bool TAB>
 static cudaError_t launch_ism(unsigned N, unsigned grid, cudaStream_t s, const RunParams& P) {
     const dim3 g(grid), b(SMALL_THREADS);
@@ -130,6 +266,22 @@ static cudaError_t launch_ism(unsigned N, unsigned grid, cudaStream_t s, const R
 
 cudaError_t launch_imid_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P) {
     MB_NOISE_TAB_DISPATCH(launch_ism, n_particles, grid, s, P)
+}
+
+template <int NOISE, bool TAB>
+static cudaError_t launch_isp(unsigned N, unsigned grid, cudaStream_t s, const RunParams& P) {
+    const dim3 g(grid), b(SMALL_THREADS);
+    switch (N) {
+        case 2: imid_split_kernel<NOISE, TAB, 2><<<g, b, 0, s>>>(P); break;
+        case 4: imid_split_kernel<NOISE, TAB, 4><<<g, b, 0, s>>>(P); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// one lane per particle (N = 2 or 4): grid = ceil(R N / SMALL_THREADS)
+cudaError_t launch_imid_split(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P) {
+    MB_NOISE_TAB_DISPATCH(launch_isp, n_particles, grid, s, P)
 }
 
 

@@ -200,7 +200,7 @@ def test_mma_member_distribution_is_invisible(core, N):
 
 
 @pytest.mark.parametrize('N,interactions', [(2, True), (3, False), (4, True), (5, True), (12, True), (32, True)])
-def test_implicit_cluster_injected(orc, core, N, interactions):
+def test_implicit_cluster_injected(orc, core, N, interactions, monkeypatch):
     rng = np.random.default_rng(100 + N)
     c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
                      dt=1e-12, t_end=4e-11, S=21, implicit=True, interactions=interactions, T=330.0, rng=rng)
@@ -208,6 +208,13 @@ def test_implicit_cluster_injected(orc, core, N, interactions):
     t, fl, ref, out, newton = injected_pair(orc, core, c, seeds, per_member=(N in (2, 4)))
     assert_traj(ref, out, c)
     assert out['stats']['newton_iterations'] == sum(n[0] - n[2] for n in newton)
+    assert out['stats']['kernel'] == ('imid_split' if N == 4 else 'imid_small' if N <= 3 else 'imid_cluster')
+    if N in (2, 4):   # both mappings of small clusters: one thread per cluster and one lane per particle
+        monkeypatch.setenv('MAGPY_B200_SMALL_KERNEL', 'thread' if N == 4 else 'split')
+        t, fl, ref, out2, newton = injected_pair(orc, core, c, seeds, per_member=True)
+        assert out2['stats']['kernel'] == ('imid_small' if N == 4 else 'imid_split')
+        assert_traj(ref, out2, c)
+        assert out2['stats']['newton_iterations'] == out['stats']['newton_iterations']
 
 
 def test_single_simulate_api_and_schedule_edges(orc, core):
