@@ -1,4 +1,4 @@
-"""Run BASELINE.json configs 2, 4 and 5 through the public API and report throughput (particle-steps/s).
+"""Run BASELINE.json configs 1, 2, 4 and 5 through the public API and report throughput (particle-steps/s).
 
     python scripts/run_configs.py                      # one GPU
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 scripts/run_configs.py
@@ -30,7 +30,12 @@ import magpy_b200 as mp  # noqa: E402
 from magpy_b200 import geometry  # noqa: E402
 
 
+ONLY = [a for a in sys.argv[1:] if a.startswith('C')]   # e.g. `run_configs.py C4` runs config 4 alone
+
+
 def run(name, model, R, end_time, time_step, S, implicit, traj=False, **kw):
+    if ONLY and name.split()[0] not in ONLY:
+        return
     ens = mp.EnsembleModel(R, model)
     shard = (rank, world) if world > 1 else None
     out = None
