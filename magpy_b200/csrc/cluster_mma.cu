@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     const double csig = __ldg(P.sig + pid) * P.sqrt_dt;
     const float bm = scale_to_bm(csig);
     const int bar_id = 1 + mh, bar_n = 32 * G;
+    const bool mono = P.mma_mono != 0;         // every particle has the mean volume (v_red = 1)
+    const bool shared_axis = P.axis_rs == 0;   // one set of easy axes for all members
 
     // the thread's four members: q = 2 j + e  ->  local column 16 mh + 8 j + 2 t + e
     // Members of this CTA: the first P.mma_full CTAs (whole waves) take MB each; the CTAs of the partial last wave
@@ -167,9 +169,15 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             double* d = buf + own_off + 8 * j;
-            *reinterpret_cast<double2*>(d) = make_double2(vred * x[2 * j].x, vred * x[2 * j + 1].x);
-            *reinterpret_cast<double2*>(d + 8 * LD) = make_double2(vred * x[2 * j].y, vred * x[2 * j + 1].y);
-            *reinterpret_cast<double2*>(d + 16 * LD) = make_double2(vred * x[2 * j].z, vred * x[2 * j + 1].z);
+            if (mono) {   // all reduced volumes are 1: the moments go in as they are
+                *reinterpret_cast<double2*>(d) = make_double2(x[2 * j].x, x[2 * j + 1].x);
+                *reinterpret_cast<double2*>(d + 8 * LD) = make_double2(x[2 * j].y, x[2 * j + 1].y);
+                *reinterpret_cast<double2*>(d + 16 * LD) = make_double2(x[2 * j].z, x[2 * j + 1].z);
+            } else {
+                *reinterpret_cast<double2*>(d) = make_double2(vred * x[2 * j].x, vred * x[2 * j + 1].x);
+                *reinterpret_cast<double2*>(d + 8 * LD) = make_double2(vred * x[2 * j].y, vred * x[2 * j + 1].y);
+                *reinterpret_cast<double2*>(d + 16 * LD) = make_double2(vred * x[2 * j].z, vred * x[2 * j + 1].z);
+            }
         }
     };
     put(std::integral_constant<int, 2>{}, sm_m, m);
@@ -192,8 +200,13 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
             const double* d = buf + own_off + 8 * j;
             const double2 vx = *reinterpret_cast<const double2*>(d), vy = *reinterpret_cast<const double2*>(d + 8 * LD),
                           vz = *reinterpret_cast<const double2*>(d + 16 * LD);
-            x[2 * j] = V3{vx.x * inv_v, vy.x * inv_v, vz.x * inv_v};
-            x[2 * j + 1] = V3{vx.y * inv_v, vy.y * inv_v, vz.y * inv_v};
+            if (mono) {
+                x[2 * j] = V3{vx.x, vy.x, vz.x};
+                x[2 * j + 1] = V3{vx.y, vy.y, vz.y};
+            } else {
+                x[2 * j] = V3{vx.x * inv_v, vy.x * inv_v, vz.x * inv_v};
+                x[2 * j + 1] = V3{vx.y * inv_v, vy.y * inv_v, vz.y * inv_v};
+            }
         }
     };
 
@@ -201,11 +214,16 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     auto stage_g = [&](auto nt, V3 (&gq)[4], const V3 (&x)[4], const double (&acc)[3][2][2], const double hz,
                        const Inc (&cw)[4]) {
         constexpr int NQ = 2 * decltype(nt)::value;
+        const uint64_t c0 = 3ull * pid;
+        V3 e{0.0, 0.0, 0.0};
+        if (shared_axis) e = V3{__ldg(P.axis + c0), __ldg(P.axis + c0 + 1), __ldg(P.axis + c0 + 2)};
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const uint64_t c0 = 3ull * pid, rq = member(q);
-            const V3 e{__ldg(P.axis + c0 * P.axis_cs + rq * P.axis_rs), __ldg(P.axis + (c0 + 1) * P.axis_cs + rq * P.axis_rs),
-                       __ldg(P.axis + (c0 + 2) * P.axis_cs + rq * P.axis_rs)};
+            if (!shared_axis) {
+                const uint64_t rq = member(q);
+                e = V3{__ldg(P.axis + c0 * P.axis_cs + rq), __ldg(P.axis + (c0 + 1) * P.axis_cs + rq),
+                       __ldg(P.axis + (c0 + 2) * P.axis_cs + rq)};
+            }
             const double s = dot(x[q], e) * kred;
             const V3 h{fma(s, e.x, acc[0][q >> 1][q & 1]), fma(s, e.y, acc[1][q >> 1][q & 1]),
                        fma(s, e.z, hz) + acc[2][q >> 1][q & 1]};

@@ -47,6 +47,7 @@ struct RunParams {
     const double* v_red; // [N] reduced volumes (K2m folds them into the moments)
     uint32_t G;          // K2m: particle groups of 8 (= ceil(N / 8))
     uint32_t mma_full, mma_tail;  // K2m: CTAs that take a full set of members; members per CTA of the partial last wave
+    uint32_t mma_mono;               // K2m: all reduced volumes are exactly 1 (no scaling of the moments)
     uint32_t cta_offset, cta_total;  // K2m: first CTA index of this launch, CTAs of both launches together
     const double* axis;  // see layout
     uint64_t axis_cs, axis_rs;  // component stride, member stride

@@ -666,6 +666,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.v_red = pl->d_vred.p;
     P.G = pl->G;
     P.mma_full = pl->mma_full;
+    P.mma_mono = std::all_of(rd.v_red.begin(), rd.v_red.end(), [](double v) { return v == 1.0; }) ? 1u : 0u;
     P.mma_tail = pl->mma_tail;
     P.axis = pl->d_axis.p;
     P.axis_cs = a->axis_stride ? R : 1;
