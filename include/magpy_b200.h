@@ -36,6 +36,7 @@ extern "C" {
 #define MAGPY_B200_FIELD_SINE 0
 #define MAGPY_B200_FIELD_SQUARE 1
 #define MAGPY_B200_FIELD_CONSTANT 2
+#define MAGPY_B200_FIELD_SQUARE_FOURIER 3   /* discrete-orientation model only (field::square_fourier, lib/field.cpp:66-79) */
 
 /* Gaussian transform applied to the Philox4x32-10 words (replaces lib/rng.cpp:14-24) */
 #define MAGPY_B200_GAUSS_F32 0 /* Box-Muller in fp32 on the SFU (32-bit uniforms), widened to fp64 */
@@ -186,6 +187,21 @@ int magpy_b200_reduce_units(const double* radius, const double* anisotropy, size
  * (lib/simulation.cpp:171-174, 342-355, 392-405): cum[k] = steps executed when sample k
  * is stored; sample k holds the state after cum[k]-1 steps. */
 int magpy_b200_schedule(double dt_red, double t_end_red, size_t max_samples, uint64_t* cum);
+
+/* ---- discrete-orientation model ------------------------------
+ * Replaces `simulation::dom_ensemble_dynamics` (include/simulation.hpp:101-111, lib/simulation.cpp:660-766) as bound
+ * by `simulate_dom` (magpy/core.pyx:205-278): the two-state master equation of a uniaxial particle in a field along
+ * its axis (lib/dom.cpp:33-101), adaptive Cash-Karp RK45 (lib/integrators.cpp:152-251) with tolerance `time_step`,
+ * first-order-hold samples.  Batched: `n_items` independent particles (volume, anisotropy, initial probabilities per
+ * item; temperature, magnetisation, damping and the field shared), one GPU thread each — the reference call is
+ * n_items = 1.  Outputs: out_time[S] (s), out_field[n_items][S] (A/m, i.e. the reduced field times the item's
+ * H_k = 2K/(mu0 Ms) as magpy/core.pyx:224-225,264), out_mz[n_items][S] (p_0 - p_1, unitless as the reference returns
+ * it), out_steps[n_items] accepted RK45 steps (may be NULL). */
+int magpy_b200_simulate_dom(int device, size_t n_items, const double* volume, const double* anisotropy,
+                            const double* initial_probabilities /* [n_items][2] */, double temperature,
+                            double magnetisation, double damping, double time_step, double end_time, size_t max_samples,
+                            int field_shape, double field_amplitude, double field_frequency, size_t field_n_components,
+                            double* out_time, double* out_field, double* out_mz, uint64_t* out_steps);
 
 /* ---- device self-tests used by the parity suite (tiny kernels) ----------------------- */
 /* raw Philox4x32-10 words computed on the device */

@@ -10,8 +10,8 @@ from . import core
 from . import results
 from . import sharding
 from . import geometry
-from .core import simulate, simulate_ensemble, get_KB, get_mu0, get_gamma
-from .model import Model, EnsembleModel
+from .core import simulate, simulate_ensemble, simulate_dom, simulate_dom_batch, get_KB, get_mu0, get_gamma
+from .model import Model, EnsembleModel, DOModel
 from .results import Results, EnsembleResults
 
 __all__ = ['core', 'results', 'sharding', 'geometry', 'simulate', 'simulate_ensemble', 'get_KB', 'get_mu0', 'get_gamma',

@@ -113,6 +113,8 @@ cdef extern from "magpy_b200.h" nogil:
     int magpy_b200_gaussians(int, int64_t, uint64_t, uint32_t, uint64_t, uint64_t, int, double*)
     int magpy_b200_fp64_peak(int, double*, double*)
     int magpy_b200_fp64_mma_peak(int, double*)
+    int magpy_b200_simulate_dom(int, size_t, const double*, const double*, const double*, double, double, double, double,
+                                double, size_t, int, double, double, size_t, double*, double*, double*, uint64_t*)
 
 
 # field::options numbering (include/field.hpp:95-97, magpy/core.pyx:38-42)
@@ -538,3 +540,56 @@ def fp64_mma_peak(int device=0):
     if rc != 0:
         _raise(rc)
     return tf
+
+
+_DOM_FIELD_LOOKUP = {'sine': 0, 'square': 1, 'constant': 2, 'square_f': 3}
+
+
+def simulate_dom_batch(np.ndarray[double, ndim=2, mode='c'] initial_probabilities,
+                       np.ndarray[double, ndim=1, mode='c'] volume,
+                       np.ndarray[double, ndim=1, mode='c'] anisotropy,
+                       double temperature, double magnetisation, double alpha, double time_step, double end_time,
+                       size_t max_samples, str field_shape='constant', double field_amplitude=0.0,
+                       double field_frequency=0.0, size_t field_n_components=1, int device=0):
+    """Discrete-orientation model of a BATCH of particles (one GPU thread each): `volume`, `anisotropy` (n,) and
+    `initial_probabilities` (n, 2) per item, everything else shared.  Returns {'time' (S,), 'field' (n, S) in A/m,
+    'mz' (n, S) = p_0 - p_1, 'steps' (n,) accepted RK45 steps}.  n = 1 is the reference's `simulate_dom`."""
+    cdef size_t n = volume.shape[0]
+    if anisotropy.shape[0] != n or initial_probabilities.shape[0] != n or initial_probabilities.shape[1] != 2:
+        raise ValueError('volume (n,), anisotropy (n,) and initial_probabilities (n, 2) must match')
+    if max_samples < 2:
+        raise ValueError('max_samples must be >= 2')
+    cdef int code = _DOM_FIELD_LOOKUP[field_shape]   # KeyError on a bad shape
+    cdef np.ndarray[double, ndim=1] t = np.empty(max_samples)
+    cdef np.ndarray[double, ndim=2] fld = np.empty((n, max_samples))
+    cdef np.ndarray[double, ndim=2] mz = np.empty((n, max_samples))
+    cdef np.ndarray[uint64_t, ndim=1] steps = np.empty(n, dtype=np.uint64)
+    cdef const double* p_v = &volume[0]
+    cdef const double* p_k = &anisotropy[0]
+    cdef const double* p_p = &initial_probabilities[0, 0]
+    cdef double* p_t = &t[0]
+    cdef double* p_f = &fld[0, 0]
+    cdef double* p_m = &mz[0, 0]
+    cdef uint64_t* p_s = &steps[0]
+    cdef int rc
+    with nogil:
+        rc = magpy_b200_simulate_dom(device, n, p_v, p_k, p_p, temperature, magnetisation, alpha, time_step, end_time,
+                                     max_samples, code, field_amplitude, field_frequency, field_n_components, p_t, p_f,
+                                     p_m, p_s)
+    if rc != 0:
+        _raise(rc)
+    return {'time': t, 'field': fld, 'mz': mz, 'steps': steps}
+
+
+cpdef simulate_dom(np.ndarray[double, ndim=1, mode='c'] initial_probabilities, double volume, double anisotropy,
+                   double temperature, double magnetisation, double alpha, double time_step, double end_time,
+                   size_t max_samples, str field_shape, double field_amplitude, double field_frequency,
+                   size_t field_n_components):
+    """Same signature and return dict as the reference's ``core.simulate_dom`` (magpy/core.pyx:205-278): 'z' is the
+    unitless p_0 - p_1, 'x' and 'y' are zero, 'field' is in A/m."""
+    out = simulate_dom_batch(np.ascontiguousarray(initial_probabilities[:2]).reshape(1, 2), np.array([volume]),
+                             np.array([anisotropy]), temperature, magnetisation, alpha, time_step, end_time, max_samples,
+                             field_shape, field_amplitude, field_frequency, field_n_components)
+    zeros = np.zeros(max_samples)
+    return {'N': 1, 'time': out['time'], 'field': out['field'][0], 'x': {0: zeros}, 'y': {0: zeros.copy()},
+            'z': {0: out['mz'][0]}}

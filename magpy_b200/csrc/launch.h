@@ -37,4 +37,21 @@ cudaError_t launch_philox_words(const uint32_t ctr[4], const uint32_t key[2], ui
 cudaError_t launch_gaussians(int noise, uint64_t seed, uint32_t member, uint32_t particle, uint64_t first_step,
                              uint64_t n_steps, double* out);
 
+// discrete-orientation model (dom.cu): one thread per batch item
+struct DomBatch {
+    uint64_t n, S;
+    const double* volume;       // [n]
+    const double* anisotropy;   // [n]
+    const double* p0;           // [n][2]
+    double temperature, magnetisation, alpha, mu0;
+    double time_step, end_time;
+    int field_shape;            // 0 sine, 1 square, 2 constant, 3 square_fourier
+    double field_amplitude, field_frequency;
+    unsigned n_components;
+    double* out_field;          // [n][S]  (A/m)
+    double* out_mz;             // [n][S]  (p_0 - p_1)
+    unsigned long long* out_steps;   // [n] accepted RK45 steps, or nullptr
+};
+cudaError_t launch_dom(const DomBatch& B, cudaStream_t s);
+
 }  // namespace mb

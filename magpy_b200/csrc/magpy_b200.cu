@@ -1096,6 +1096,64 @@ int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz) {
     return MAGPY_B200_OK;
 }
 
+int magpy_b200_simulate_dom(int device, size_t n_items, const double* volume, const double* anisotropy,
+                            const double* initial_probabilities, double temperature, double magnetisation, double damping,
+                            double time_step, double end_time, size_t max_samples, int field_shape, double field_amplitude,
+                            double field_frequency, size_t field_n_components, double* out_time, double* out_field,
+                            double* out_mz, uint64_t* out_steps) {
+    if (n_items == 0) return fail(MAGPY_B200_ERR_BAD_ARG, "n_items must be >= 1");
+    if (!volume || !anisotropy || !initial_probabilities) return fail(MAGPY_B200_ERR_BAD_ARG, "volume/anisotropy/initial_probabilities must not be NULL");
+    if (!out_mz) return fail(MAGPY_B200_ERR_BAD_ARG, "out_mz must not be NULL");
+    if (max_samples < 2) return fail(MAGPY_B200_ERR_BAD_ARG, "max_samples must be >= 2 (lib/simulation.cpp:703)");
+    if (max_samples > 0x7FFFFFFFull) return fail(MAGPY_B200_ERR_BAD_ARG, "max_samples too large");
+    if (!(time_step > 0.0) || !(end_time > 0.0)) return fail(MAGPY_B200_ERR_BAD_ARG, "time_step and end_time must be > 0");
+    if (field_shape < MAGPY_B200_FIELD_SINE || field_shape > MAGPY_B200_FIELD_SQUARE_FOURIER)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "field_shape must be a MAGPY_B200_FIELD_* value");
+    if (!(magnetisation > 0.0) || !(temperature > 0.0) || !(damping > 0.0))
+        return fail(MAGPY_B200_ERR_BAD_ARG, "magnetisation, temperature and damping must be > 0");
+    int rc = select_device(device);
+    if (rc) return rc;
+    rc = enable_pool(device);
+    if (rc) return rc;
+    const size_t S = max_samples, n = n_items;
+    cudaStream_t stream = nullptr;
+    CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    struct StreamGuard {
+        cudaStream_t s;
+        ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    } guard{stream};
+    DevBuf<double> d_vol, d_k, d_p0, d_field, d_mz;
+    DevBuf<unsigned long long> d_steps;
+    CU_TRY(d_vol.alloc(n, stream));
+    CU_TRY(d_k.alloc(n, stream));
+    CU_TRY(d_p0.alloc(2 * n, stream));
+    CU_TRY(d_field.alloc(n * S, stream));
+    CU_TRY(d_mz.alloc(n * S, stream));
+    CU_TRY(d_steps.alloc(n, stream));
+    CU_TRY(cudaMemcpyAsync(d_vol.p, volume, n * 8, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(d_k.p, anisotropy, n * 8, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(d_p0.p, initial_probabilities, 2 * n * 8, cudaMemcpyHostToDevice, stream));
+    mb::DomBatch B{};
+    B.n = n; B.S = S;
+    B.volume = d_vol.p; B.anisotropy = d_k.p; B.p0 = d_p0.p;
+    B.temperature = temperature; B.magnetisation = magnetisation; B.alpha = damping; B.mu0 = kMU0;
+    B.time_step = time_step; B.end_time = end_time;
+    B.field_shape = field_shape; B.field_amplitude = field_amplitude; B.field_frequency = field_frequency;
+    B.n_components = (unsigned)field_n_components;
+    B.out_field = d_field.p; B.out_mz = d_mz.p; B.out_steps = d_steps.p;
+    CU_TRY(mb::launch_dom(B, stream));
+    CU_TRY(cudaMemcpyAsync(out_mz, d_mz.p, n * S * 8, cudaMemcpyDeviceToHost, stream));
+    if (out_field) CU_TRY(cudaMemcpyAsync(out_field, d_field.p, n * S * 8, cudaMemcpyDeviceToHost, stream));
+    if (out_steps) CU_TRY(cudaMemcpyAsync(out_steps, d_steps.p, n * 8, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    if (out_time) {   // lib/simulation.cpp:704,759-760
+        const double sampling_time = end_time / (S - 1);
+        out_time[0] = 0;
+        for (unsigned int sample = 1; sample < S; sample++) out_time[sample] = sample * sampling_time;
+    }
+    return MAGPY_B200_OK;
+}
+
 int magpy_b200_fp64_mma_peak(int device, double* tflops) {
     int rc = select_device(device);
     if (rc) return rc;

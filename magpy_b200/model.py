@@ -192,3 +192,45 @@ class EnsembleModel:
             from .sharding import allreduce_sums
             allreduce_sums(sums)
         return EnsembleResults.from_arrays(time, field, R, trajectories=traj, sums=sums, final=final, stats=stats)
+
+
+class DOModel:
+    """Discrete-orientation (two-state master equation) model of a single uniaxial particle in a field along its
+    axis — `magpy.DOModel` (magpy/model.py:211-296): same constructor arguments, `simulate(end_time, time_step,
+    max_samples)` returns a `Results` whose z magnetisation is the unitless p_0 - p_1 the reference returns.
+    `field_shape` may be 'constant', 'sine', 'square' or 'square_f' (`field_n_components` Fourier terms).
+
+    `simulate_batch` integrates many particles in one device call (one GPU thread each): pass arrays of radii and
+    anisotropy constants (e.g. a size distribution) — the case a GPU is for; the reference has no equivalent."""
+
+    def __init__(self, radius, anisotropy, initial_probabilities, magnetisation, damping, temperature,
+                 field_shape='constant', field_frequency=0.0, field_amplitude=0.0, field_n_components=1):
+        self.radius = radius
+        self.volume = 4. / 3 * np.pi * self.radius ** 3
+        self.anisotropy = anisotropy
+        self.initial_probabilities = np.array(initial_probabilities, dtype=np.float64)
+        self.magnetisation = magnetisation
+        self.damping = damping
+        self.temperature = temperature
+        self.field_shape = field_shape
+        self.field_frequency = field_frequency
+        self.field_amplitude = field_amplitude
+        self.field_n_components = field_n_components
+
+    def simulate(self, end_time, time_step, max_samples):
+        results = core.simulate_dom(
+            np.ascontiguousarray(self.initial_probabilities, dtype=np.float64), float(self.volume), float(self.anisotropy),
+            float(self.temperature), float(self.magnetisation), float(self.damping), time_step, end_time, max_samples,
+            self.field_shape, self.field_amplitude, self.field_frequency, self.field_n_components)
+        return Results(**results)
+
+    def simulate_batch(self, radius, anisotropy, end_time, time_step, max_samples, initial_probabilities=None, device=0):
+        """The same model over arrays `radius` and `anisotropy` (n,): {'time', 'field' (n, S), 'mz' (n, S), 'steps'}."""
+        radius = np.atleast_1d(np.asarray(radius, dtype=np.float64))
+        anisotropy = np.ascontiguousarray(np.broadcast_to(np.asarray(anisotropy, dtype=np.float64), radius.shape))
+        p0 = self.initial_probabilities if initial_probabilities is None else np.asarray(initial_probabilities, dtype=np.float64)
+        p0 = np.ascontiguousarray(np.broadcast_to(p0, (len(radius), 2)))
+        volume = 4. / 3 * np.pi * radius ** 3
+        return core.simulate_dom_batch(p0, volume, anisotropy, float(self.temperature), float(self.magnetisation),
+                                       float(self.damping), time_step, end_time, max_samples, self.field_shape,
+                                       self.field_amplitude, self.field_frequency, self.field_n_components, device)

@@ -209,4 +209,24 @@ int ref_driver_implicit_gbm(double a, double b, double x0, double dt, size_t n_s
     return 0;
 }
 
+
+// Discrete-orientation model: simulation::dom_ensemble_dynamics (lib/simulation.cpp:660-766) with the field function
+// bound as magpy/core.pyx:228-246 does (shape: 0 sine, 1 square, 2 constant, 3 square_f; h_red = H0 / H_k).
+void ref_dom_simulate(double volume, double anisotropy, double temperature, double ms, double alpha, int shape, double h_red,
+                      double freq, size_t ncomp, const double* p0, double time_step, double end_time, size_t S,
+                      double* out_time, double* out_field, double* out_mz) {
+    std::function<double(double)> f;
+    if (shape == 0) f = [=](double t) { return field::sinusoidal(t, h_red, freq); };
+    else if (shape == 1) f = [=](double t) { return field::square(t, h_red, freq); };
+    else if (shape == 3) f = [=](double t) { return field::square_fourier(t, h_red, freq, ncomp); };
+    else f = [=](double t) { return field::constant(t, h_red); };
+    const std::array<double, 2> init = {p0[0], p0[1]};
+    simulation::results res = simulation::dom_ensemble_dynamics(volume, anisotropy, temperature, ms, alpha, f, init, time_step,
+                                                                end_time, (int)S);
+    for (size_t i = 0; i < S; ++i) {
+        out_time[i] = res.time[i];
+        out_field[i] = res.field[i];
+        out_mz[i] = res.mz[i];
+    }
+}
 }  // extern "C"

@@ -686,6 +686,125 @@ void orc_dom_transition_matrix(double* W, double k, double v, double T, double h
     W[2] = rate2;  W[3] = -rate1;
 }
 
+/* ------------------------------------------------------------------------- *
+ * Discrete-orientation model, time integration:    *
+ * the two-state master equation dp/dt = W(h(t)) p of lib/dom.cpp:86-101        *
+ * (W p is a 2x2 dgemv, lib/stochastic_processes.cpp:18-25) integrated by the  *
+ * reference's adaptive Cash-Karp RK45 (lib/integrators.cpp:152-251, table      *
+ * include/integrators.hpp:128-160) under the driver of                         *
+ * lib/simulation.cpp:660-766: tolerance = time_step, first step 0.01 time_step,*
+ * step capped at end_time/1000 AFTER each step, samples by first-order hold    *
+ * between the last two states.  field_shape: 0 sine, 1 square, 2 constant,     *
+ * 3 square_fourier (lib/field.cpp:23-79); h_red = H0 / H_k.                    *
+ * Returns the number of accepted RK45 steps.                                   *
+ * ------------------------------------------------------------------------- */
+static double orc_dom_field(int shape, double t, double h, double f, size_t ncomp) {
+    switch (shape) {
+        case 0: return h * sin(2 * M_PI * f * t);
+        case 1: return h * ((int)(t * f * 2) % 2 ? -1 : 1);
+        case 3: {
+            double field = 0;
+            for (unsigned int k = 1; k < ncomp + 1; k++) field += sin(2 * M_PI * (2 * k - 1) * f * t) / (2 * k - 1);
+            field *= 4 / M_PI * h;
+            return field;
+        }
+        default: return h;
+    }
+}
+
+typedef struct {
+    double k, v, T, ms, alpha, h, f;
+    int shape;
+    size_t ncomp;
+} orc_dom_sys;
+
+static void orc_dom_derivs(double* d, const double* p, double t, const orc_dom_sys* s) {
+    double W[4];
+    orc_dom_transition_matrix(W, s->k, s->v, s->T, orc_dom_field(s->shape, t, s->h, s->f, s->ncomp), s->ms, s->alpha);
+    d[0] = W[0] * p[0] + W[1] * p[1];
+    d[1] = W[2] * p[0] + W[3] * p[1];
+}
+
+/* one adaptive step, lib/integrators.cpp:152-251 (n_dims = 2) */
+static void orc_rk45(double* next, double* h_ptr, double* t_ptr, const double* cur, const orc_dom_sys* s, double tol) {
+    const double c11 = 0.2, c21 = 3.0 / 40.0, c22 = 9.0 / 40.0, c31 = 3.0 / 10.0, c32 = -9.0 / 10.0, c33 = 6.0 / 5.0,
+                 c41 = -11.0 / 54.0, c42 = 2.5, c43 = -70.0 / 27.0, c44 = 35.0 / 27.0, c51 = 1631.0 / 55296.0,
+                 c52 = 175.0 / 512.0, c53 = 575.0 / 13824.0, c54 = 44275.0 / 110592.0, c55 = 253.0 / 4096.0,
+                 hc1 = 0.2, hc2 = 0.3, hc3 = 0.6, hc4 = 1.0, hc5 = 7.0 / 8.0,
+                 x11 = 37.0 / 378.0, x13 = 250.0 / 621.0, x14 = 125.0 / 594.0, x16 = 512.0 / 1771.0,
+                 x21 = 2825.0 / 27648.0, x23 = 18575.0 / 48384.0, x24 = 13525.0 / 55296.0, x25 = 277.0 / 14336.0, x26 = 0.25;
+    double k1[2], k2[2], k3[2], k4[2], k5[2], k6[2], tmp[2];
+    int ok = 0;
+    double err = 0, h = *h_ptr, t = *t_ptr;
+    while (!ok) {
+        orc_dom_derivs(k1, cur, t, s);
+        for (int i = 0; i < 2; i++) next[i] = k1[i] * h * c11 + cur[i];
+        orc_dom_derivs(k2, next, t + h * hc1, s);
+        for (int i = 0; i < 2; i++) next[i] = cur[i] + h * (c21 * k1[i] + c22 * k2[i]);
+        orc_dom_derivs(k3, next, t + h * hc2, s);
+        for (int i = 0; i < 2; i++) next[i] = cur[i] + h * (c31 * k1[i] + c32 * k2[i] + c33 * k3[i]);
+        orc_dom_derivs(k4, next, t + h * hc3, s);
+        for (int i = 0; i < 2; i++) next[i] = cur[i] + h * (c41 * k1[i] + c42 * k2[i] + c43 * k3[i] + c44 * k4[i]);
+        orc_dom_derivs(k5, next, t + h * hc4, s);
+        for (int i = 0; i < 2; i++)
+            next[i] = cur[i] + h * (c51 * k1[i] + c52 * k2[i] + c53 * k3[i] + c54 * k4[i] + c55 * k5[i]);
+        orc_dom_derivs(k6, next, t + h * hc5, s);
+        for (int i = 0; i < 2; i++) tmp[i] = cur[i] + h * (x11 * k1[i] + x13 * k3[i] + x14 * k4[i] + x16 * k6[i]);
+        for (int i = 0; i < 2; i++)
+            next[i] = cur[i] + h * (x21 * k1[i] + x23 * k3[i] + x24 * k4[i] + x25 * k5[i] + x26 * k6[i]);
+        err = 0;
+        double mag = 0;
+        for (int i = 0; i < 2; i++) mag += cur[i] * cur[i];
+        mag = pow(mag, 0.5);
+        for (int i = 0; i < 2; i++) err += pow(fabs(tmp[i] - next[i]), 2);
+        err = pow(err, 0.5);
+        err /= (2 * tol * (1 + mag));
+        if (err < 1.0) ok = 1;
+        else {
+            double hf = 0.84 * pow(err, -0.2);
+            hf = fabs(hf) < 0.1 ? 0.1 : hf;
+            h *= hf;
+        }
+    }
+    *t_ptr = t + h;
+    double hf = err == 0.0 ? 5.0 : 0.84 * pow(err, -0.2);
+    hf = hf > 5 ? 5.0 : hf;
+    *h_ptr = hf * h;
+}
+
+uint64_t orc_dom_simulate(double volume, double anisotropy, double temperature, double ms, double alpha, int shape,
+                          double h_red, double freq, size_t ncomp, const double* p0, double time_step, double end_time,
+                          size_t S, double* out_time, double* out_field, double* out_mz) {
+    const orc_dom_sys sys = {anisotropy, volume, temperature, ms, alpha, h_red, freq, shape, ncomp};
+    double last[2], next[2] = {p0[0], p0[1]};
+    const double sampling_time = end_time / (S - 1);
+    out_mz[0] = next[0] - next[1];
+    out_time[0] = 0;
+    out_field[0] = orc_dom_field(shape, 0, h_red, freq, ncomp);
+    double t = 0, t_last = 0;
+    const double max_dt = end_time / 1000.0;
+    double dt = 0.01 * time_step;
+    uint64_t step = 0;
+    const double eps = time_step;
+    for (unsigned int sample = 1; sample < S; sample++) {
+        while (t <= sample * sampling_time) {
+            last[0] = next[0];
+            last[1] = next[1];
+            t_last = t;
+            step++;
+            orc_rk45(next, &dt, &t, last, &sys, eps);
+            dt = dt > max_dt ? max_dt : dt;
+        }
+        const double mz_last = last[0] - last[1], mz_next = next[0] - next[1];
+        const double t_sample = sample * sampling_time;
+        const double beta = (mz_next - mz_last) / (t - t_last);
+        out_mz[sample] = mz_last + beta * (t_sample - t_last);
+        out_time[sample] = t_sample;
+        out_field[sample] = orc_dom_field(shape, t_sample, h_red, freq, ncomp);
+    }
+    return step;
+}
+
 /* Number of N(0,1) draws orc_simulate consumes: 3N * (steps executed). */
 uint64_t orc_steps_executed(double dt_red, double T_red, size_t S) {
     uint64_t* cum = (uint64_t*)malloc(sizeof(uint64_t) * S);

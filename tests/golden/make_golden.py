@@ -44,6 +44,32 @@ CASES = {
 }
 
 
+# Discrete-orientation model (simulation::dom_ensemble_dynamics through ref_dom_simulate), SI arguments of
+# magpy.DOModel.  The 6 nm particle (sigma = 8.7) relaxes / switches on these time scales; 12 nm is blocked.
+DOM_CASES = {
+    'dom_relax_6nm': dict(radius=6e-9, anisotropy=4e4, p0=[1.0, 0.0], Ms=4e5, alpha=0.1, T=300.0, dt=1e-10, t_end=2e-6, S=200),
+    'dom_sine_6nm': dict(radius=6e-9, anisotropy=4e4, p0=[0.5, 0.5], Ms=4e5, alpha=0.1, T=300.0, dt=1e-10, t_end=1e-5, S=300,
+                         field_shape='sine', H0=2e4, f=3e5),
+    'dom_square_7nm': dict(radius=7e-9, anisotropy=3e4, p0=[0.9, 0.1], Ms=4.46e5, alpha=0.05, T=310.0, dt=1e-9, t_end=2e-5,
+                           S=150, field_shape='square', H0=1.5e4, f=1e5),
+    'dom_squaref_6nm': dict(radius=6e-9, anisotropy=4e4, p0=[1.0, 0.0], Ms=4e5, alpha=0.1, T=300.0, dt=1e-10, t_end=1e-5,
+                            S=250, field_shape='square_f', H0=2e4, f=2e5, n_components=7),
+    'dom_blocked_12nm': dict(radius=12e-9, anisotropy=4e4, p0=[1.0, 0.0], Ms=4e5, alpha=0.1, T=300.0, dt=1e-9, t_end=1e-5,
+                             S=50, field_shape='sine', H0=2e4, f=3e5),
+}
+
+
+def main_dom(ref):
+    out = {}
+    for name, kw in DOM_CASES.items():
+        t, fl, mz = ol.dom_simulate(ref, reference=True, **kw)
+        out[name + '/time'] = t
+        out[name + '/field'] = fl
+        out[name + '/mz'] = mz
+        print('%-20s mz[-1] = %.12g' % (name, mz[-1]))
+    np.savez_compressed(os.path.join(HERE, 'reference_dom.npz'), **out)
+
+
 def main():
     ref = ol.load_reference()
     if ref is None:
@@ -70,6 +96,7 @@ def main():
         out[name + '/dw'] = dw.reshape(n_steps, 3 * c.N).astype(np.float64)
         print('%-28s N=%d steps=%d  m[...,-1]=%s' % (name, c.N, n_steps, m[0, :, -1]))
     np.savez_compressed(os.path.join(HERE, 'reference_trajectories.npz'), **out)
+    main_dom(ref)
 
 
 if __name__ == '__main__':

@@ -29,6 +29,7 @@ def load_oracle():
     lib.orc_dgesv.restype = C.c_int
     lib.orc_implicit_midpoint_step.restype = C.c_int
     lib.orc_driver_implicit.restype = C.c_int
+    lib.orc_dom_simulate.restype = C.c_uint64
     return lib
 
 
@@ -170,3 +171,22 @@ def dom_transition_matrix(lib, k, v, T, h, ms, alpha):
     lib.orc_dom_transition_matrix(W, C.c_double(k), C.c_double(v), C.c_double(T), C.c_double(h), C.c_double(ms),
                                   C.c_double(alpha))
     return list(W)
+
+
+DOM_FIELD = {'sine': 0, 'square': 1, 'constant': 2, 'square_f': 3}
+
+
+def dom_simulate(lib, radius, anisotropy, p0, Ms, alpha, T, dt, t_end, S, field_shape='constant', H0=0.0, f=0.0,
+                 n_components=1, reference=False):
+    """Discrete-orientation model of one particle: the oracle's restatement (`orc_dom_simulate`) or, with
+    reference=True, the compiled reference (`ref_dom_simulate` -> simulation::dom_ensemble_dynamics), with the SI ->
+    reduced conversion of magpy/core.pyx:224-225.  Returns (time, field [A/m], mz = p0 - p1)."""
+    V = 4. / 3 * np.pi * radius ** 3
+    H_k = 2.0 * anisotropy / 1.25663706e-6 / Ms
+    t = np.zeros(S); fl = np.zeros(S); mz = np.zeros(S)
+    p0 = np.ascontiguousarray(p0, dtype=np.float64)
+    fn = lib.ref_dom_simulate if reference else lib.orc_dom_simulate
+    fn(C.c_double(V), C.c_double(anisotropy), C.c_double(T), C.c_double(Ms), C.c_double(alpha),
+       C.c_int(DOM_FIELD[field_shape]), C.c_double(H0 / H_k), C.c_double(f), C.c_size_t(n_components), _p(p0),
+       C.c_double(dt), C.c_double(t_end), C.c_size_t(S), _p(t), _p(fl), _p(mz))
+    return t, fl * H_k, mz

@@ -99,6 +99,16 @@ def test_argument_errors_do_not_need_a_device(core):
     with pytest.raises(ValueError):
         core.simulate_ensemble(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False,
                                True, False, c.dt, c.t_end, 10, [1, 2, 3], devices='some')
+    # discrete-orientation model (magpy/core.pyx:205-278): bad shape -> KeyError, too few samples / bad scalars -> ValueError
+    p0 = np.array([1.0, 0.0])
+    with pytest.raises(KeyError):
+        core.simulate_dom(p0, 1e-24, 4e4, 300.0, 4e5, 0.1, 1e-10, 1e-6, 10, 'sawtooth', 0.0, 0.0, 1)
+    with pytest.raises(ValueError):
+        core.simulate_dom(p0, 1e-24, 4e4, 300.0, 4e5, 0.1, 1e-10, 1e-6, 1, 'constant', 0.0, 0.0, 1)
+    with pytest.raises(ValueError):
+        core.simulate_dom(p0, 1e-24, 4e4, 300.0, 4e5, 0.1, -1e-10, 1e-6, 10, 'constant', 0.0, 0.0, 1)
+    with pytest.raises(ValueError):
+        core.simulate_dom_batch(np.ones((3, 2)), np.ones(2), np.ones(3), 300.0, 4e5, 0.1, 1e-10, 1e-6, 10)
 
 
 def test_no_cpu_fallback(core):
@@ -108,6 +118,8 @@ def test_no_cpu_fallback(core):
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         core.simulate(c.radius, c.anisotropy, c.axis, c.m0, c.location, c.Ms, c.alpha, c.T, False, True, False, c.dt,
                       c.t_end, 10, 1)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        core.simulate_dom(np.array([1.0, 0.0]), 1e-24, 4e4, 300.0, 4e5, 0.1, 1e-10, 1e-6, 10, 'constant', 0.0, 0.0, 1)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         core.fp64_peak()
     with pytest.raises(RuntimeError, match='no CPU fallback'):

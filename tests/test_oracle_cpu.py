@@ -6,6 +6,8 @@ import ctypes as C
 import json
 import os
 
+import sys
+
 import numpy as np
 import pytest
 
@@ -316,3 +318,46 @@ def test_schedule_semantics(orc):
         lit.append(step)
     assert cum.tolist() == lit
     assert np.all(np.diff(cum.astype(np.int64)) >= 0) and len(set(cum.tolist())) < 11
+
+
+# ---- discrete-orientation model ---------------------------------------------------------
+DOM_GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_dom.npz'))
+
+
+def _dom_cases():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden
+    return make_golden.DOM_CASES
+
+
+@pytest.mark.parametrize('name', sorted(_dom_cases()))
+def test_dom_oracle_matches_golden_reference(orc, name):
+    """The restated master equation + adaptive RK45 + first-order-hold driver against vectors produced by the
+    compiled reference (simulation::dom_ensemble_dynamics, tests/golden/make_golden.py).  Same operation order and no
+    FMA contraction on either side: the step sequences coincide and the samples agree to the last bits."""
+    kw = _dom_cases()[name]
+    t, fl, mz = ol.dom_simulate(orc, **kw)
+    assert np.array_equal(t, DOM_GOLD[name + '/time'])
+    assert np.allclose(fl, DOM_GOLD[name + '/field'], rtol=1e-15, atol=0)
+    assert np.abs(mz - DOM_GOLD[name + '/mz']).max() <= 1e-14
+    # physics: probabilities stay normalised -> |mz| <= 1; zero field relaxes towards 0 from p = (1, 0)
+    assert np.abs(mz).max() <= 1 + 1e-12
+    if name == 'dom_relax_6nm':
+        assert mz[0] == 1.0 and 0 < mz[-1] < 0.05 and np.all(np.diff(mz) < 0)
+
+
+def test_dom_oracle_matches_compiled_reference_live(orc):
+    ref = ol.load_reference()
+    if ref is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference)')
+    rng = np.random.default_rng(11)
+    for _ in range(6):
+        kw = dict(radius=float(rng.uniform(5e-9, 8e-9)), anisotropy=float(rng.uniform(2e4, 6e4)),
+                  p0=[float(x) for x in rng.dirichlet([1, 1])], Ms=4e5, alpha=float(rng.uniform(0.05, 0.5)), T=300.0,
+                  dt=1e-10, t_end=float(rng.uniform(1e-6, 5e-6)), S=int(rng.integers(20, 120)),
+                  field_shape=str(rng.choice(['constant', 'sine', 'square', 'square_f'])), H0=float(rng.uniform(0, 2.5e4)),
+                  f=float(rng.uniform(1e5, 1e6)), n_components=int(rng.integers(1, 9)))
+        a = ol.dom_simulate(orc, **kw)
+        b = ol.dom_simulate(ref, reference=True, **kw)
+        assert np.array_equal(a[0], b[0]) and np.allclose(a[1], b[1], rtol=1e-15, atol=0)
+        assert np.abs(a[2] - b[2]).max() <= 1e-13
