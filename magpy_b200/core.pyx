@@ -84,6 +84,7 @@ cdef extern from "magpy_b200.h" nogil:
         double* out_sums
         double* out_final
         uint32_t noise_coarsen_log2
+        uint32_t implicit_newton
 
     ctypedef struct magpy_b200_plan:
         pass
@@ -124,6 +125,7 @@ CONSTANT = 2
 
 _FIELD_LOOKUP = {'constant': CONSTANT, 'sine': SINE, 'square': SQUARE}
 _GAUSS_LOOKUP = {'f32': 0, 'f64': 1, 'f32p': 2}
+_NEWTON_LOOKUP = {'reference': 0, 'exact': 1}
 
 
 cdef _raise(int rc):
@@ -260,7 +262,7 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
                                max_samples, seeds, str field_shape, double field_amplitude,
                                double field_frequency, double implicit_tol, int device, stream_offset,
                                bint return_trajectories, bint return_sums, bint return_final, str gauss,
-                               injected_dw, int noise_coarsen_log2=0):
+                               injected_dw, int noise_coarsen_log2=0, str implicit_newton='reference'):
     cdef _EnsembleArgs e = _EnsembleArgs()
     cdef np.ndarray[double, ndim=1, mode='c'] c_radius = np.ascontiguousarray(radius, dtype=np.float64).reshape(-1)
     cdef size_t N = c_radius.shape[0]
@@ -316,6 +318,7 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
     if noise_coarsen_log2 < 0:
         raise ValueError('noise_coarsen_log2 must be >= 0')
     e.a.noise_coarsen_log2 = noise_coarsen_log2
+    e.a.implicit_newton = _NEWTON_LOOKUP[implicit_newton]   # KeyError on anything but 'reference' / 'exact'
     if injected_dw is not None:
         dw = np.ascontiguousarray(injected_dw, dtype=np.float64)
         if dw.ndim != 3 or dw.shape[0] != R or dw.shape[2] != 3 * N:
@@ -354,7 +357,7 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
                       str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
                       double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=True,
                       bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None, devices=None,
-                      int noise_coarsen_log2=0):
+                      int noise_coarsen_log2=0, str implicit_newton='reference'):
     """Integrate R = len(seeds) independent members of one cluster in a single call.
 
     `devices` (list of CUDA ordinals, or 'all') shards the members over several GPUs of this box from this one
@@ -373,7 +376,7 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
                                        magnetisation, damping, temperature, renorm, interactions, use_implicit,
                                        time_step, end_time, max_samples, seeds, field_shape, field_amplitude,
                                        field_frequency, implicit_tol, device, stream_offset, return_trajectories,
-                                       return_sums, return_final, gauss, injected_dw, noise_coarsen_log2)
+                                       return_sums, return_final, gauss, injected_dw, noise_coarsen_log2, implicit_newton)
     cdef magpy_b200_stats st
     cdef int rc
     cdef np.ndarray[int, ndim=1, mode='c'] c_dev
@@ -415,12 +418,13 @@ cdef class EnsemblePlan:
                  bint use_implicit, double time_step, double end_time, max_samples, seeds,
                  str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
                  double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=False,
-                 bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None):
+                 bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None,
+                 str implicit_newton='reference'):
         self.e = _build_args(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
                              magnetisation, damping, temperature, renorm, interactions, use_implicit,
                              time_step, end_time, max_samples, seeds, field_shape, field_amplitude,
                              field_frequency, implicit_tol, device, stream_offset, return_trajectories,
-                             return_sums, return_final, gauss, injected_dw)
+                             return_sums, return_final, gauss, injected_dw, 0, implicit_newton)
         cdef int rc
         with nogil:
             rc = magpy_b200_plan_create(&self.e.a, &self.plan)

@@ -39,6 +39,7 @@ struct RunParams {
     int interactions; // all-pairs dipolar field
     double alpha, dt, sqrt_dt;
     double eps, clampA;  // implicit: tolerance, Ah = sqrt(2*1000*|ln dt|)
+    int newton_exact;    // implicit: 0 = the reference's quasi-Newton iteration (parity), 1 = Newton with the exact Jacobian
     double h_const;      // applied field when no table is used (reduced units)
     const double* k_red; // [N]
     const double* sig;   // [N] thermal field strength sigma_i

@@ -10,7 +10,7 @@ namespace mb {
 // J = I - a'/2 - (B'.w)/2 with no dt on a', tolerance eps*||guess|| fixed before the
 // loop, stop on ||delta||_2 <= tol or after 1000 iterations.
 // ---------------------------------------------------------------------------------
-template <bool AXIS_Z>
+template <bool AXIS_Z, bool EXACT>
 __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const double kred, const double alpha,
                                                const double sr, const double dt, const double clampA,
                                                const double sqrt_dt, const double eps, const V3& w,
@@ -26,7 +26,10 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
         const double s = kred * dot(x0, e);
         const V3 g{fma(s * e.x, dt, sw.x), fma(s * e.y, dt, sw.y), fma(fma(s, e.z, hz_t), dt, sw.z)};
         const V3 f = llg_f(x0, g, alpha);
-        X = V3{(f.x + x0.x) / 2, (f.y + x0.y) / 2, (f.z + x0.z) / 2};
+        // the reference's guess is (x0 + f) / 2 (lib/integrators.cpp:605-614); the midpoint of an Euler step is
+        // x0 + f / 2, which the exact-Newton mode starts from (one iteration fewer)
+        X = EXACT ? V3{fma(0.5, f.x, x0.x), fma(0.5, f.y, x0.y), fma(0.5, f.z, x0.z)}
+                  : V3{(f.x + x0.x) / 2, (f.y + x0.y) / 2, (f.z + x0.z) / 2};
     }
     // err > tol is tested on the squares (no square root inside the loop): tol^2 = eps^2 |X|^2
     const double tol2 = (eps * eps) * dot(X, X);
@@ -37,7 +40,13 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
     while ((err2 > tol2) && (iter-- > 0)) {
         double A[9], d[3];
         V3 g;
-        if (AXIS_Z) {   // easy axis = z: h = (0, 0, k X_z + h_app)
+        if (EXACT) {
+            const double s = kred * dot(X, e);
+            g = V3{fma(s * e.x, dt, sw.x), fma(s * e.y, dt, sw.y), fma(fma(s, e.z, hz_mid), dt, sw.z)};
+            const V3 pg = cross(X, g);
+            const V3 u{fma(alpha, pg.x, g.x), fma(alpha, pg.y, g.y), fma(alpha, pg.z, g.z)};
+            newton_matrix_exact(A, X, alpha, g, u, dt * kred, e);
+        } else if (AXIS_Z) {   // easy axis = z: h = (0, 0, k X_z + h_app)
             const double hz = fma(kred, X.z, hz_mid);
             g = V3{sw.x, sw.y, fma(hz, dt, sw.z)};
             newton_matrix_axis_z(A, X, alpha, hz, sw, nhsw, kred);
@@ -65,7 +74,7 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
     return V3{2 * X.x - x0.x, 2 * X.y - x0.y, 2 * X.z - x0.z};
 }
 
-template <int NOISE, bool FIELD_TAB, bool AXIS_Z>
+template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool EXACT>
 __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
                 const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - P.j0));
                 hz0 = h.x; hz1 = h.y;
             }
-            m = imid_single_step<AXIS_Z>(m, e, kred, P.alpha, sr, P.dt, P.clampA, P.sqrt_dt, P.eps, w, hz0, hz1, nc);
+            m = imid_single_step<AXIS_Z, EXACT>(m, e, kred, P.alpha, sr, P.dt, P.clampA, P.sqrt_dt, P.eps, w, hz0, hz1, nc);
             if (renorm) renormalise(m);
         }
         if (k < P.k1) {
@@ -115,12 +124,15 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
 template <int NOISE>
 static void launch_is(bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
     const dim3 g(grid), b(SINGLE_THREADS);
-    if (tab) {
-        if (axis_z) imid_single_kernel<NOISE, true, true><<<g, b, 0, s>>>(P);
-        else imid_single_kernel<NOISE, true, false><<<g, b, 0, s>>>(P);
+    if (P.newton_exact) {   // opt-in Newton with the exact Jacobian (general-axis arithmetic for every axis)
+        if (tab) imid_single_kernel<NOISE, true, false, true><<<g, b, 0, s>>>(P);
+        else imid_single_kernel<NOISE, false, false, true><<<g, b, 0, s>>>(P);
+    } else if (tab) {
+        if (axis_z) imid_single_kernel<NOISE, true, true, false><<<g, b, 0, s>>>(P);
+        else imid_single_kernel<NOISE, true, false, false><<<g, b, 0, s>>>(P);
     } else {
-        if (axis_z) imid_single_kernel<NOISE, false, true><<<g, b, 0, s>>>(P);
-        else imid_single_kernel<NOISE, false, false><<<g, b, 0, s>>>(P);
+        if (axis_z) imid_single_kernel<NOISE, false, true, false><<<g, b, 0, s>>>(P);
+        else imid_single_kernel<NOISE, false, false, false><<<g, b, 0, s>>>(P);
     }
 }
 

@@ -307,6 +307,10 @@ int validate(const magpy_b200_ensemble* a) {
             return fail(MAGPY_B200_ERR_BAD_ARG, "noise_coarsen_log2 needs a single-particle ensemble with the packed Philox stream");
         if (a->noise_coarsen_log2 > 20) return fail(MAGPY_B200_ERR_BAD_ARG, "noise_coarsen_log2 must be <= 20");
     }
+    if (a->implicit_newton != MAGPY_B200_NEWTON_REFERENCE && a->implicit_newton != MAGPY_B200_NEWTON_EXACT)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "implicit_newton must be MAGPY_B200_NEWTON_REFERENCE or MAGPY_B200_NEWTON_EXACT");
+    if (a->implicit_newton == MAGPY_B200_NEWTON_EXACT && a->use_implicit && a->n_particles > 4)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "implicit_newton = exact supports at most 4 particles per cluster");
     if (a->use_implicit) {
         if (a->n_particles > 32) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 32 particles per cluster");
     } else if (a->n_particles > 128) {
@@ -420,9 +424,9 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         if (pl->implicit && (N == 2 || N == 4)) {   // measured (profiles/r01_probe_c2.log): a gain for N = 4 only
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-            bool split = N == 4 && R < (uint64_t)sms * 4 * 2 * 32;
+            bool split = N == 4 && R < (uint64_t)sms * 4 * 2 * 32 && a->implicit_newton == MAGPY_B200_NEWTON_REFERENCE;
             if (const char* force = std::getenv("MAGPY_B200_SMALL_KERNEL")) {
-                if (std::strcmp(force, "split") == 0) split = R * N < 0xFFFFFFFFull;
+                if (std::strcmp(force, "split") == 0) split = R * N < 0xFFFFFFFFull && a->implicit_newton == MAGPY_B200_NEWTON_REFERENCE;
                 else if (std::strcmp(force, "thread") == 0) split = false;
             }
             if (split) {
@@ -657,6 +661,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.dt = rd.dt;
     P.sqrt_dt = std::sqrt(rd.dt);
     P.eps = a->implicit_tol;
+    P.newton_exact = (a->use_implicit && a->implicit_newton == MAGPY_B200_NEWTON_EXACT) ? 1 : 0;
     P.clampA = std::sqrt(2 * 1000.0 * std::abs(std::log(rd.dt)));  // lib/integrators.cpp:598-599
     P.h_const = rd.h0;
     P.k_red = pl->d_kred.p;

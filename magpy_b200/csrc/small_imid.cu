@@ -5,7 +5,9 @@ namespace mb {
 // ---------------------------------------------------------------------------------
 // implicit midpoint
 // ---------------------------------------------------------------------------------
-template <int NOISE, bool FIELD_TAB, int N>
+// EXACT: Newton with each particle's exact own-particle Jacobian (llg_math.cuh: newton_matrix_exact; the dipolar coupling
+// between particles stays out of the matrix, as in the reference) instead of the reference's quasi-Newton matrix.
+template <int NOISE, bool FIELD_TAB, int N, bool EXACT>
 __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SMALL_THREADS / 32) * 4];
     __shared__ __align__(32) double sd[N * N * 4];
@@ -57,7 +59,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
             for (int i = 0; i < N; ++i) {
                 const V3 g{fma(h[i].x, dt, sw[i].x), fma(h[i].y, dt, sw[i].y), fma(h[i].z, dt, sw[i].z)};
                 const V3 f = llg_f(m[i], g, alpha);
-                X[i] = V3{(f.x + m[i].x) / 2, (f.y + m[i].y) / 2, (f.z + m[i].z) / 2};
+                X[i] = EXACT ? V3{fma(0.5, f.x, m[i].x), fma(0.5, f.y, m[i].y), fma(0.5, f.z, m[i].z)}
+                             : V3{(f.x + m[i].x) / 2, (f.y + m[i].y) / 2, (f.z + m[i].z) / 2};
                 nrm += dot(X[i], X[i]);
             }
             // err > tol is tested on the squares (no square root in the dependent chain of an iteration)
@@ -79,7 +82,13 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
                                     -(X[i].z - m[i].z - 0.5 * f.z)};
                     b[i] = V3{bb[0], bb[1], bb[2]};
                     double A[9], d[3];
-                    newton_matrix(A, X[i], alpha, h[i], sw[i], quirk_u(N, i, e[0], kred[0]), e[0]);
+                    if (EXACT) {
+                        const V3 pg = cross(X[i], g);
+                        const V3 u{fma(alpha, pg.x, g.x), fma(alpha, pg.y, g.y), fma(alpha, pg.z, g.z)};
+                        newton_matrix_exact(A, X[i], alpha, g, u, dt * kred[i], e[i]);
+                    } else {
+                        newton_matrix(A, X[i], alpha, h[i], sw[i], quirk_u(N, i, e[0], kred[0]), e[0]);
+                    }
                     if (!solve3_adjugate(A, bb, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                     dl[i] = V3{d[0], d[1], d[2]};
                     e2 += d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
@@ -255,10 +264,19 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_split_kernel(const __grid_
 template <int NOISE, bool TAB>
 static cudaError_t launch_ism(unsigned N, unsigned grid, cudaStream_t s, const RunParams& P) {
     const dim3 g(grid), b(SMALL_THREADS);
+    if (P.newton_exact) {
+        switch (N) {
+            case 2: imid_small_kernel<NOISE, TAB, 2, true><<<g, b, 0, s>>>(P); break;
+            case 3: imid_small_kernel<NOISE, TAB, 3, true><<<g, b, 0, s>>>(P); break;
+            case 4: imid_small_kernel<NOISE, TAB, 4, true><<<g, b, 0, s>>>(P); break;
+            default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     switch (N) {
-        case 2: imid_small_kernel<NOISE, TAB, 2><<<g, b, 0, s>>>(P); break;
-        case 3: imid_small_kernel<NOISE, TAB, 3><<<g, b, 0, s>>>(P); break;
-        case 4: imid_small_kernel<NOISE, TAB, 4><<<g, b, 0, s>>>(P); break;
+        case 2: imid_small_kernel<NOISE, TAB, 2, false><<<g, b, 0, s>>>(P); break;
+        case 3: imid_small_kernel<NOISE, TAB, 3, false><<<g, b, 0, s>>>(P); break;
+        case 4: imid_small_kernel<NOISE, TAB, 4, false><<<g, b, 0, s>>>(P); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

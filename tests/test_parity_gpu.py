@@ -239,6 +239,35 @@ def test_implicit_cluster_injected(orc, core, N, interactions, monkeypatch):
         assert out2['stats']['newton_iterations'] == out['stats']['newton_iterations']
 
 
+@pytest.mark.parametrize('N,axis_z', [(1, True), (1, False), (2, False), (4, False)])
+def test_exact_newton_mode_is_the_converged_reference_iteration(orc, core, N, axis_z):
+    """`implicit_newton='exact'` (opt-in) solves the reference's implicit-midpoint equation by Newton's method with the
+    exact Jacobian.  The reference's own quasi-Newton iteration converges (linearly) to the same root, so the ORACLE
+    run with eps = 1e-14 — the reference algorithm, merely iterated to convergence — is the pathwise comparator: same
+    injected Wiener stream, trajectories equal to 1e-11, in 3-4 iterations per step instead of ~35 (and ~20 at the
+    default eps = 1e-9, where the reference's truncated iterate sits ~1e-9 from the root)."""
+    rng = np.random.default_rng(300 + N)
+    c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
+                     dt=1e-12, t_end=6e-11, S=16, implicit=True, interactions=True, T=330.0, field_shape='sine', H0=1e4,
+                     f=1e10, eps=1e-14, rng=rng, **(dict(axis=[[0, 0, 1.0]], m0=[[0.6, 0, 0.8]]) if axis_z else {}))
+    seeds = np.arange(1, 20) * 17
+    n_steps = ol.steps_executed(orc, c)
+    dW = np.stack([ol.mt_normal(orc, int(s), n_steps * 3 * N).reshape(n_steps, 3 * N) for s in seeds])
+    ref = np.stack([ol.oracle_simulate(orc, c, seed=int(s))[2] for s in seeds])
+    fast = gpu_run(core, ol.Case(dict(c, eps=1e-9)), seeds, dW=dW, implicit_newton='exact')
+    assert np.abs(fast['trajectories'] - ref).max() / c.Ms < 1e-11
+    per_step = fast['stats']['newton_iterations'] / (len(seeds) * fast['stats']['steps_per_member'])
+    assert per_step <= 4.0 and fast['stats']['newton_failures'] == 0
+    # and the default mode at the default tolerance is the truncated iterate: further from the root, ~20 iterations
+    slow = gpu_run(core, ol.Case(dict(c, eps=1e-9)), seeds, dW=dW)
+    assert slow['stats']['newton_iterations'] > 4 * fast['stats']['newton_iterations']
+    assert 1e-11 < np.abs(slow['trajectories'] - ref).max() / c.Ms < 1e-7
+    with pytest.raises(KeyError):
+        gpu_run(core, c, seeds, dW=dW, implicit_newton='broyden')
+    with pytest.raises(ValueError):
+        gpu_run(core, ol.make_case(N=5, implicit=True), seeds, implicit_newton='exact')
+
+
 def test_single_simulate_api_and_schedule_edges(orc, core):
     """core.simulate keeps the reference's dict; sampling finer than the time step repeats states."""
     c = ol.make_case(N=2, dt=1e-12, t_end=1e-11, S=40, implicit=False)    # Ts < dt: zero-order hold repeats

@@ -304,20 +304,22 @@ def test_full_size_ensembles_checksum_properties(core):
     assert np.abs((f4 * axes[None]).sum(axis=2)).min() > 0.99
 
 
-@pytest.mark.parametrize('N,implicit', [(1, False), (1, True), (2, False), (6, False), (2, True)])
+@pytest.mark.parametrize('N,implicit', [(1, False), (1, True), (2, False), (6, False), (2, True), (1, 'exact'), (3, 'exact')])
 def test_zero_temperature_relaxation_closed_form(orc, core, N, implicit):
     """T = 0 (the in-kernel noise amplitude is exactly zero), no applied field, non-interacting particles with
     their easy axes along z: tan(theta(t)) = tan(theta0) exp(-alpha t) in reduced time (the closed form the
     reference's test/convergence/task4 family uses), through the production (Philox) kernels of every family —
     single, one-thread-per-cluster, shared-memory cluster; Heun and implicit midpoint."""
     th0 = np.pi / 3
+    newton = 'exact' if implicit == 'exact' else 'reference'     # the opt-in exact-Jacobian Newton mode as well
+    implicit = bool(implicit)
     c = ol.make_case(N=N, T=0.0, alpha=0.1, S=11, axis=[[0, 0, 1.0]] * N, m0=[[np.sin(th0), 0, np.cos(th0)]] * N,
                      implicit=implicit, interactions=False)
     tf = ol.reduced_scalars(orc, c)['time_factor']
     dt_red = 0.01
     c['dt'] = dt_red / tf
     c['t_end'] = 4.0 / tf
-    out = gpu(core, c, np.arange(33))
+    out = gpu(core, c, np.arange(33), implicit_newton=newton)
     cum = ol.schedule(orc, dt_red, 4.0, c.S)
     ts = np.maximum(cum.astype(float) - 1, 0) * dt_red
     exact = 1.0 / np.sqrt(1 + np.tan(th0) ** 2 * np.exp(-2 * 0.1 * ts))
