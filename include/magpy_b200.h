@@ -124,7 +124,8 @@ typedef struct magpy_b200_ensemble {
      * Newton's method with the exact Jacobian of the midpoint residual (hard part 1: "worthwhile for
      * throughput but must be opt-in"): the same implicit-midpoint equation solved to a tighter residual in ~3
      * iterations instead of ~20; trajectories differ from the reference's truncated iterates at the 1e-9 level per
-     * step.  Clusters of at most 4 particles. */
+     * step.  For clusters each particle's own exact Jacobian is used; the dipolar coupling between particles stays
+     * out of the matrix (as in the reference), which leaves a fast linear convergence (4-5 iterations). */
     uint32_t implicit_newton;
 } magpy_b200_ensemble;
 #define MAGPY_B200_NEWTON_REFERENCE 0

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t member = (uint32_t)(r + P.stream_offset);
-    const bool renorm = P.renorm != 0;
+    const bool renorm = P.renorm != 0, exact = P.newton_exact != 0;
     NewtonCount nc{0ull, 0ull, 0ull};
 
     Own own[NP];
@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
                 const V3 h = cluster_field(P, sm_m, sm_tab, own[q], m[q], hz0, lane);
                 const V3 g{fma(h.x, dt, sw[q].x), fma(h.y, dt, sw[q].y), fma(h.z, dt, sw[q].z)};
                 const V3 f = llg_f(m[q], g, alpha);
-                X[q] = V3{(f.x + m[q].x) / 2, (f.y + m[q].y) / 2, (f.z + m[q].z) / 2};
+                X[q] = exact ? V3{fma(0.5, f.x, m[q].x), fma(0.5, f.y, m[q].y), fma(0.5, f.z, m[q].z)}
+                             : V3{(f.x + m[q].x) / 2, (f.y + m[q].y) / 2, (f.z + m[q].z) / 2};
                 double* d = sm_x + 3ull * own[q].p * CL_LANES + lane;
                 d[0] = X[q].x; d[CL_LANES] = X[q].y; d[2 * CL_LANES] = X[q].z;
                 part += dot(X[q], X[q]);
@@ -390,7 +391,13 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
                     double b[3] = {-(X[q].x - m[q].x - 0.5 * f.x), -(X[q].y - m[q].y - 0.5 * f.y),
                                    -(X[q].z - m[q].z - 0.5 * f.z)};
                     double A[9], d[3];
-                    newton_matrix(A, X[q], alpha, h, sw[q], qu[q], e0);
+                    if (exact) {   // opt-in: each particle's exact own Jacobian (llg_math.cuh), dipolar coupling left out as in the reference
+                        const V3 pg = cross(X[q], g);
+                        const V3 u{fma(alpha, pg.x, g.x), fma(alpha, pg.y, g.y), fma(alpha, pg.z, g.z)};
+                        newton_matrix_exact(A, X[q], alpha, g, u, dt * own[q].kred, own[q].e);
+                    } else {
+                        newton_matrix(A, X[q], alpha, h, sw[q], qu[q], e0);
+                    }
                     if (!solve3_adjugate(A, b, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                     dl[q] = V3{d[0], d[1], d[2]};
                     part += d[0] * d[0] + d[1] * d[1] + d[2] * d[2];

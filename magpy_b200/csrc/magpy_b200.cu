@@ -309,8 +309,6 @@ int validate(const magpy_b200_ensemble* a) {
     }
     if (a->implicit_newton != MAGPY_B200_NEWTON_REFERENCE && a->implicit_newton != MAGPY_B200_NEWTON_EXACT)
         return fail(MAGPY_B200_ERR_BAD_ARG, "implicit_newton must be MAGPY_B200_NEWTON_REFERENCE or MAGPY_B200_NEWTON_EXACT");
-    if (a->implicit_newton == MAGPY_B200_NEWTON_EXACT && a->use_implicit && a->n_particles > 4)
-        return fail(MAGPY_B200_ERR_BAD_ARG, "implicit_newton = exact supports at most 4 particles per cluster");
     if (a->use_implicit) {
         if (a->n_particles > 32) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 32 particles per cluster");
     } else if (a->n_particles > 128) {
@@ -424,9 +422,9 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         if (pl->implicit && (N == 2 || N == 4)) {   // measured (profiles/r01_probe_c2.log): a gain for N = 4 only
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-            bool split = N == 4 && R < (uint64_t)sms * 4 * 2 * 32 && a->implicit_newton == MAGPY_B200_NEWTON_REFERENCE;
+            bool split = N == 4 && R < (uint64_t)sms * 4 * 2 * 32;
             if (const char* force = std::getenv("MAGPY_B200_SMALL_KERNEL")) {
-                if (std::strcmp(force, "split") == 0) split = R * N < 0xFFFFFFFFull && a->implicit_newton == MAGPY_B200_NEWTON_REFERENCE;
+                if (std::strcmp(force, "split") == 0) split = R * N < 0xFFFFFFFFull;
                 else if (std::strcmp(force, "thread") == 0) split = false;
             }
             if (split) {

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_split_kernel(const __grid_
     const bool live = r_raw < P.R;
     const uint64_t r = live ? r_raw : P.R - 1;
     const double alpha = P.alpha, dt = P.dt, clampA = P.clampA, sqrt_dt = P.sqrt_dt;
-    const bool inter = P.interactions != 0, renorm = P.renorm != 0;
+    const bool inter = P.interactions != 0, renorm = P.renorm != 0, exact = P.newton_exact != 0;
 
     const uint64_t c0 = 3ull * p;
     V3 m{P.state[c0 * P.R + r], P.state[(c0 + 1) * P.R + r], P.state[(c0 + 2) * P.R + r]};
@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_split_kernel(const __grid_
                 const V3 h = field(m, hz0);
                 const V3 g{fma(h.x, dt, sw.x), fma(h.y, dt, sw.y), fma(h.z, dt, sw.z)};
                 const V3 f = llg_f(m, g, alpha);
-                X = V3{(f.x + m.x) / 2, (f.y + m.y) / 2, (f.z + m.z) / 2};
+                X = exact ? V3{fma(0.5, f.x, m.x), fma(0.5, f.y, m.y), fma(0.5, f.z, m.z)}
+                          : V3{(f.x + m.x) / 2, (f.y + m.y) / 2, (f.z + m.z) / 2};
             }
             const double tol2 = (P.eps * P.eps) * cluster_sum(dot(X, X));
             double err2 = 4 * tol2;
@@ -220,7 +221,13 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_split_kernel(const __grid_
                 const V3 f = llg_f(X, g, alpha);
                 double bb[3] = {-(X.x - m.x - 0.5 * f.x), -(X.y - m.y - 0.5 * f.y), -(X.z - m.z - 0.5 * f.z)};
                 double A[9], d[3];
-                newton_matrix(A, X, alpha, h, sw, qu, e0);
+                if (exact) {
+                    const V3 pg = cross(X, g);
+                    const V3 u{fma(alpha, pg.x, g.x), fma(alpha, pg.y, g.y), fma(alpha, pg.z, g.z)};
+                    newton_matrix_exact(A, X, alpha, g, u, dt * kred, e);
+                } else {
+                    newton_matrix(A, X, alpha, h, sw, qu, e0);
+                }
                 const bool ok = solve3_adjugate(A, bb, d);
                 if (!ok) d[0] = d[1] = d[2] = 0.0;
                 const double e2 = cluster_sum(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);

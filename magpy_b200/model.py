@@ -126,7 +126,7 @@ class EnsembleModel:
             implicit_newton ('reference'|'exact'): implicit midpoint only.  'reference' reproduces the reference's
                 quasi-Newton iteration iterate by iterate (~20 iterations per step); 'exact' is Newton's method with the
                 exact Jacobian of the midpoint residual (~3 iterations, several times faster): the same scheme solved to
-                a tighter residual, so paths differ from the reference's at the 1e-9 level per step.  Up to 4 particles.
+                a tighter residual, so paths differ from the reference's at the 1e-9 level per step.
             shard ((rank, world_size)|None): integrate only this rank's contiguous slice of the
                 members (magpy_b200.sharding.shard_bounds) and all-reduce the ensemble sums over the
                 initialised torch.distributed group; per-member outputs then cover the local slice.
