@@ -212,7 +212,7 @@ def test_mma_member_distribution_is_invisible(core, N):
     seeds = rng.integers(1, 2 ** 31 - 1, R)
     big = gpu_run(core, c, seeds, return_trajectories=False)
     assert big['stats']['kernel'] == 'heun_cluster_mma'
-    for lo, hi in ((0, 40), (per_cta - 3, per_cta + 9), (R - 50, R)):
+    for lo, hi in ((0, 1), (0, 40), (per_cta - 3, per_cta + 9), (R - 50, R)):   # (0, 1): a single member (core.simulate's case)
         small = gpu_run(core, c, seeds[lo:hi], stream_offset=lo, return_trajectories=False)
         assert np.array_equal(big['final'][lo:hi], small['final'])
     # fused ensemble sums of the big run against its own final states (last sample = final state)
