@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
     double* sm_x = smem + (uint64_t)N * 3 * CL_LANES;    // [N][3][32] midpoint iterate X
     double* sm_red = sm_x + (uint64_t)N * 3 * CL_LANES;  // [PS][3][32]
     const int lane = threadIdx.x, slot = threadIdx.y, PS = blockDim.y;
-    double* sm_tab = sm_red + (uint64_t)PS * 3 * CL_LANES;   // [N][N][4] pair table (N <= 32: at most 32 KB)
+    double* sm_tab = sm_red + (uint64_t)PS * 3 * CL_LANES;   // [N][N][4] pair table (N <= 64: at most 128 KB)
     for (uint32_t q = slot * CL_LANES + lane; q < N * N * 4; q += PS * CL_LANES) sm_tab[q] = P.dip[q];
     const uint64_t r_raw = (uint64_t)blockIdx.x * CL_LANES + lane;
     const bool live = r_raw < P.R;
@@ -508,7 +508,8 @@ static cudaError_t launch_ic(int np, dim3 g, dim3 b, size_t smem, cudaStream_t s
     switch (np) {
         case 1: return launch_with_smem(imid_cluster_kernel<NOISE, TAB, 1>, g, b, smem, s, P);
         case 2: return launch_with_smem(imid_cluster_kernel<NOISE, TAB, 2>, g, b, smem, s, P);
-        default: return launch_with_smem(imid_cluster_kernel<NOISE, TAB, 4>, g, b, smem, s, P);
+        case 4: return launch_with_smem(imid_cluster_kernel<NOISE, TAB, 4>, g, b, smem, s, P);
+        default: return launch_with_smem(imid_cluster_kernel<NOISE, TAB, 8>, g, b, smem, s, P);   // 33..64 particles
     }
 }
 

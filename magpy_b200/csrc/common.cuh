@@ -19,7 +19,7 @@
 //                                   per thread, moments (and the pair table, N <= 64) in shared memory
 // K2m heun_cluster_mma (cluster_mma.cu) N = 8..64 with a dense enough 8-particle grouping: the dipolar field as
 //                                   D[3N x 3N] . M[3N x members] on DMMA.8x8x4, D packed in shared memory
-// K4 imid_cluster (cluster.cu)      N = 5..32: same mapping; block-diagonal quasi-Newton, CTA-wide convergence
+// K4 imid_cluster (cluster.cu)      N = 5..64: same mapping; block-diagonal quasi-Newton, CTA-wide convergence
 // K5 ensemble sums                  fused into all of them (warp shuffle -> smem -> per-CTA partial) +
 //                                   reduce_partials (fixed order, deterministic)
 #pragma once

@@ -310,7 +310,7 @@ int validate(const magpy_b200_ensemble* a) {
     if (a->implicit_newton != MAGPY_B200_NEWTON_REFERENCE && a->implicit_newton != MAGPY_B200_NEWTON_EXACT)
         return fail(MAGPY_B200_ERR_BAD_ARG, "implicit_newton must be MAGPY_B200_NEWTON_REFERENCE or MAGPY_B200_NEWTON_EXACT");
     if (a->use_implicit) {
-        if (a->n_particles > 32) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 32 particles per cluster");
+        if (a->n_particles > 64) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 64 particles per cluster");
     } else if (a->n_particles > 128) {
         return fail(MAGPY_B200_ERR_BAD_ARG, "Heun supports at most 128 particles per cluster");
     }
@@ -450,7 +450,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         const size_t cap = 227 * 1024;
         pl->layout = 0;
         pl->smem = 2 * moments + red;
-        if (pl->implicit) pl->smem += table;   // N <= 32: the implicit kernel always stages the table
+        if (pl->implicit) pl->smem += table;   // N <= 64: the implicit kernel always stages the table
         if (!pl->implicit) {   // Heun: stage the pair table in shared memory when it fits (cluster.cu)
             if (2 * moments + red + table <= cap) { pl->layout = 1; pl->smem = 2 * moments + red + table; }
             else if (np == 4 && moments + red + table <= cap) { pl->layout = 2; pl->smem = moments + red + table; }
