@@ -54,6 +54,7 @@ struct RunParams {
     uint64_t axis_cs, axis_rs;  // component stride, member stride
     const int64_t* seeds;       // [R]
     uint64_t stream_offset;
+    uint32_t philox_m0, philox_m1;  // the two Philox multipliers, passed at run time for the split multiply of rng.cuh
     uint32_t coarsen_log2;      // NOISE_PHILOX_COARSE: step s sums the packed stream's fine steps s 2^L .. (s+1) 2^L - 1
     double* state;              // [n][R]
     const uint64_t* target;     // [S] state index stored by sample k

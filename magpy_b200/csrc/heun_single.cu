@@ -42,6 +42,9 @@ __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V
               fma(-hm.x, u.y, fma(hm.y, u.x, h.z))};
 }
 
+#ifndef MB_PHILOX_SPLIT
+#define MB_PHILOX_SPLIT 0   // leading Philox rounds whose wide multiplies are issued as IMAD.HI + IMAD (tuning knob, rng.cuh)
+#endif
 #ifndef MB_K1_MIN_BLOCKS
 #define MB_K1_MIN_BLOCKS 1   // resident CTAs per SM the register allocation must allow (tuning knob)
 #endif
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1_MIN_BLOCKS) heun_single_
     bool have = false;
     auto need = [&](const uint32_t blk) {
         if (!have || gblk != blk) {
-            philox_gauss6_f32(key0, key1, blk, 0u, member, bm_scale, g);
+            philox_gauss6_f32<MB_PHILOX_SPLIT>(key0, key1, blk, 0u, member, bm_scale, g, P.philox_m0, P.philox_m1);
             gblk = blk;
             have = true;
         }
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1_MIN_BLOCKS) heun_single_
             if (pairs != 0) need(blk);
             for (uint32_t i = pairs; i != 0; --i, tp += 2) {
                 float gn[6];
-                philox_gauss6_f32(key0, key1, ++blk, 0u, member, bm_scale, gn);
+                philox_gauss6_f32<MB_PHILOX_SPLIT>(key0, key1, ++blk, 0u, member, bm_scale, gn, P.philox_m0, P.philox_m1);
                 advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tp);
                 advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tp + 1);
 #pragma unroll

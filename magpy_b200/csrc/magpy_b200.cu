@@ -677,6 +677,8 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.seeds = pl->d_seeds.p;
     P.stream_offset = a->stream_offset;
     P.coarsen_log2 = a->noise_coarsen_log2;
+    P.philox_m0 = 0xD2511F53u;
+    P.philox_m1 = 0xCD9E8D57u;
     P.state = pl->d_state.p;
     P.target = pl->d_target.p;
     P.field_tab = pl->d_tab.p;

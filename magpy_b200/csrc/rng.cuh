@@ -57,6 +57,34 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
     }
 }
 
+// The same block with the wide multiplies of the first SPLIT rounds issued as IMAD.HI (immediate multiplier) + IMAD
+// (multiplier from a register, m0r / m1r = the same constants passed at run time so that ptxas cannot fuse the pair
+// back into one IMAD.WIDE).  On sm_100a IMAD.WIDE takes FP64-pipe time, IMAD.HI and IMAD do not (profiles/README.md):
+// splitting SOME rounds moves work from the saturated FP64 side to the 32-bit integer pipe.
+template <int SPLIT>
+__device__ __forceinline__ void philox4x32_10_split(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                                    uint32_t k1, const uint32_t m0r, const uint32_t m1r) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0, l0, h1, l1;
+        if (r < SPLIT) {
+            h0 = __umulhi(c0, 0xD2511F53u); l0 = c0 * m0r;
+            h1 = __umulhi(c2, 0xCD9E8D57u); l1 = c2 * m1r;
+        } else {
+            mulhilo32(0xD2511F53u, c0, h0, l0);
+            mulhilo32(0xCD9E8D57u, c2, h1, l1);
+        }
+        const uint32_t n0 = h1 ^ c1 ^ k0;
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
 // float -> double widening of a Gaussian increment.  Measured on B200 (profiles/README.md): in the
 // issue-mix micro-benchmark one F2F.F64.F32 takes ~3.5 cycles of the FP64 pipe away from a DFMA stream,
 // but assembling the double from the float's bits (LOP3, LEA.HI, LOP3, SHF: exponent re-biased by 896,
@@ -134,11 +162,14 @@ __device__ __forceinline__ void bm_pair_packed(uint32_t r23_bits /* 23 bits, alr
     s = r * __sinf(a);
 }
 
+template <int SPLIT = 0>
 __device__ __forceinline__ void philox_gauss6_f32(uint32_t seed_lo, uint32_t seed_hi, uint64_t pair_index,
                                                   uint32_t particle, uint32_t member, float neg2ln2_amp2,
-                                                  float (&g)[6]) {
+                                                  float (&g)[6], const uint32_t m0r = 0xD2511F53u,
+                                                  const uint32_t m1r = 0xCD9E8D57u) {
     uint32_t w0 = (uint32_t)pair_index, w1 = member, w2 = seed_lo, w3 = seed_hi;
-    philox4x32_10(w0, w1, w2, w3, particle | MB_PACKED_KEY_TAG, MB_PHILOX_KEY1);
+    if (SPLIT > 0) philox4x32_10_split<SPLIT>(w0, w1, w2, w3, particle | MB_PACKED_KEY_TAG, MB_PHILOX_KEY1, m0r, m1r);
+    else philox4x32_10(w0, w1, w2, w3, particle | MB_PACKED_KEY_TAG, MB_PHILOX_KEY1);
     // 23-bit radius fields land in mantissa bits 22..0, 18-bit angle fields in mantissa bits 22..5
     const uint32_t r0 = w0 >> 9;                                              // string bits   0..22  (bit 23 unused)
     const uint32_t a0 = (__funnelshift_l(w1, w0, 15)) & 0x007fffe0u;          // string bits  24..41
