@@ -16,6 +16,10 @@
 // particle 8 pg + g for its four members 16 mh + 8 j + 2 t + e — exactly what the per-particle Heun update needs,
 // with no exchange between threads.
 //
+// Clusters of 65..128 particles use the same kernel with the blocks of D read from global memory through the read-only
+// path (template parameter DG): the matrix (up to 612 KB) is shared by every CTA and stays in L2 — measured 30 TFLOP/s
+// by W_alg at N = 128 against 14.8 for the scalar kernel.
+//
 // D is symmetric (v_red is folded into M), so only the 24 x 24 blocks with pg <= kg are kept in shared memory
 // (N = 64: 36 blocks = 162 KB instead of 288 KB); a warp reads the blocks left of its diagonal transposed.  Inside
 // a block, element (i, c) sits at i * 24 + (c ^ 4 ((i >> 1) & 1)), which makes both the direct and the
@@ -46,12 +50,16 @@ constexpr int MMA_BLK = 576;   // doubles per 24 x 24 block of D
 // the warp's A operand sits at  a_idx + ks * sks + a * sa -/+ dsw  with (sks, sa) = (4, 192) for a block read directly
 // — where the swizzle moves the even k-steps up and the odd ones down by dsw = 4 sg doubles — and (96, 8), no
 // correction, for a block read transposed.
-__device__ __forceinline__ void load_frags(double (&af)[3], double (&bf)[2], const double* __restrict__ sm, const int a_idx,
-                                           const bool direct, const int dsw, const int b_idx, const int ks, const int LD4) {
+// DG: the blocks of D are read from global memory (`dg`, read-only path) instead of the CTA's shared memory — clusters
+// of 65..128 particles, whose packed matrix (up to 612 KB) does not fit next to the moments.
+template <bool DG>
+__device__ __forceinline__ void load_frags(double (&af)[3], double (&bf)[2], const double* __restrict__ sm,
+                                           const double* __restrict__ dg, const int a_idx, const bool direct, const int dsw,
+                                           const int b_idx, const int ks, const int LD4) {
     const int sks = direct ? 4 : 96, sa = direct ? 192 : 8, d = direct ? dsw : 0;
-    const double* ap = sm + a_idx + ks * sks + ((ks & 1) ? -d : d);
+    const double* ap = (DG ? dg : sm) + a_idx + ks * sks + ((ks & 1) ? -d : d);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) af[a] = ap[a * sa];
+    for (int a = 0; a < 3; ++a) af[a] = DG ? __ldg(ap + a * sa) : ap[a * sa];
     const double* bq = sm + b_idx + ks * LD4;
     bf[0] = bq[0];
     bf[1] = bq[8];
@@ -61,9 +69,10 @@ __device__ __forceinline__ void load_frags(double (&af)[3], double (&bf)[2], con
 // (also across block boundaries) are loaded before the six DMMAs of the current one are issued.  NT = live column
 // tiles of this warp (2, or 1 in a CTA of the partial last wave whose second tile holds no member).
 // sm = the CTA's shared memory: D blocks from index 0, the moment buffer row of this thread's B fragment at b0.
-template <int NT>
-__device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double* __restrict__ sm, const int b0, const int G,
-                                            const int pg, const int LD, const int g, const int t) {
+template <int NT, bool DG>
+__device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double* __restrict__ sm,
+                                            const double* __restrict__ dg, const int b0, const int G, const int pg,
+                                            const int LD, const int g, const int t) {
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -77,15 +86,15 @@ __device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double
     };
     int a_cur = a_index(0), b_cur = b0;
     double af[3], bf[2];
-    load_frags(af, bf, sm, a_cur, 0 >= pg, dsw, b_cur, 0, LD4);
+    load_frags<DG>(af, bf, sm, dg, a_cur, 0 >= pg, dsw, b_cur, 0, LD4);
     for (int kg = 0; kg < G; ++kg) {
         const int kn = kg + 1 < G ? kg + 1 : kg;   // the last prefetch re-reads a valid block
         const int a_nxt = a_index(kn), b_nxt = b0 + kn * LD24;
 #pragma unroll
         for (int ks = 0; ks < 6; ++ks) {
             double an[3], bn[2];
-            if (ks < 5) load_frags(an, bn, sm, a_cur, kg >= pg, dsw, b_cur, ks + 1, LD4);
-            else load_frags(an, bn, sm, a_nxt, kn >= pg, dsw, b_nxt, 0, LD4);
+            if (ks < 5) load_frags<DG>(an, bn, sm, dg, a_cur, kg >= pg, dsw, b_cur, ks + 1, LD4);
+            else load_frags<DG>(an, bn, sm, dg, a_nxt, kn >= pg, dsw, b_nxt, 0, LD4);
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -101,7 +110,8 @@ __device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double
 
 // TAIL = false: a CTA of the whole waves (all column tiles live, the fast path); TAIL = true: a CTA of the partial last
 // wave, launched separately (P.cta_offset), whose warps may have 2, 1 or 0 live column tiles.
-template <int NOISE, bool FIELD_TAB, bool ONE_BUF, bool TAIL>
+// DG = true: the matrix stays in global memory (N = 65..128), two moment buffers.
+template <int NOISE, bool FIELD_TAB, bool ONE_BUF, bool TAIL, bool DG>
 __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_constant__ RunParams P) {
     extern __shared__ double smem[];
     const int N = (int)P.N, G = (int)P.G;
@@ -109,13 +119,14 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
     const int n_warps = blockDim.x >> 5, MH = n_warps / G, MB = 16 * MH, LD = MB + 4;
     const int pg = warp % G, mh = warp / G;
     const int n_blk = G * (G + 1) / 2;
-    double* sm_d = smem;                                              // [n_blk][576]
-    double* sm_m = sm_d + (size_t)n_blk * MMA_BLK;                    // [24 G][LD] current moments (times v_red)
+    double* sm_d = smem;                                              // [n_blk][576] (not staged when DG)
+    double* sm_m = sm_d + (DG ? 0 : (size_t)n_blk * MMA_BLK);         // [24 G][LD] current moments (times v_red)
     double* sm_t = ONE_BUF ? sm_m : sm_m + (size_t)24 * G * LD;       // [24 G][LD] predictor moments
     double* sm_red = sm_t + (size_t)24 * G * LD;                      // [G][3][MB] sample reduction
     {
         const int nd = n_blk * MMA_BLK;
-        for (int q = threadIdx.x; q < nd; q += blockDim.x) sm_d[q] = P.dmat[q];
+        if (!DG)
+            for (int q = threadIdx.x; q < nd; q += blockDim.x) sm_d[q] = P.dmat[q];
         const int nm = 24 * G * LD * (ONE_BUF ? 1 : 2);
         for (int q = threadIdx.x; q < nm; q += blockDim.x) sm_m[q] = 0.0;   // rows of padding particles stay zero
     }
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
         }
         double acc[3][2][2];
         V3 gq[4];
-        if (inter) dipolar_mma<NT>(acc, smem, b_m, G, pg, LD, g, t);
+        if (inter) dipolar_mma<NT, DG>(acc, smem, P.dmat, b_m, G, pg, LD, g, t);
         else {
 #pragma unroll
             for (int a = 0; a < 3; ++a) acc[a][0][0] = acc[a][0][1] = acc[a][1][0] = acc[a][1][1] = 0.0;
@@ -259,7 +270,7 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
             put(nt, sm_t, mt);
         }
         group_barrier(bar_id, bar_n);
-        if (inter) dipolar_mma<NT>(acc, smem, b_t, G, pg, LD, g, t);
+        if (inter) dipolar_mma<NT, DG>(acc, smem, P.dmat, b_t, G, pg, LD, g, t);
         // the predictor moments are not kept in registers across the second product: the thread reads its own back
         // from shared memory (exact when v_red = 1; otherwise one rounding of v (1/v), 12 orders below the noise)
         V3 mt[4];
@@ -396,11 +407,16 @@ static cudaError_t launch_hm(bool one_buf, unsigned full_ctas, unsigned tail_cta
         return cudaGetLastError();
     };
     P.cta_total = full_ctas + tail_ctas;
-    cudaError_t e = one_buf ? go(heun_cluster_mma_kernel<NOISE, TAB, true, false>, full_ctas, 0)
-                            : go(heun_cluster_mma_kernel<NOISE, TAB, false, false>, full_ctas, 0);
+    if (P.mma_dglobal) {   // N = 65..128: matrix in global memory, always two moment buffers
+        cudaError_t e = go(heun_cluster_mma_kernel<NOISE, TAB, false, false, true>, full_ctas, 0);
+        if (e != cudaSuccess) return e;
+        return go(heun_cluster_mma_kernel<NOISE, TAB, false, true, true>, tail_ctas, full_ctas);
+    }
+    cudaError_t e = one_buf ? go(heun_cluster_mma_kernel<NOISE, TAB, true, false, false>, full_ctas, 0)
+                            : go(heun_cluster_mma_kernel<NOISE, TAB, false, false, false>, full_ctas, 0);
     if (e != cudaSuccess) return e;
-    return one_buf ? go(heun_cluster_mma_kernel<NOISE, TAB, true, true>, tail_ctas, full_ctas)
-                   : go(heun_cluster_mma_kernel<NOISE, TAB, false, true>, tail_ctas, full_ctas);
+    return one_buf ? go(heun_cluster_mma_kernel<NOISE, TAB, true, true, false>, tail_ctas, full_ctas)
+                   : go(heun_cluster_mma_kernel<NOISE, TAB, false, true, false>, tail_ctas, full_ctas);
 }
 
 cudaError_t launch_heun_cluster_mma(int noise, bool tab, bool one_buf, unsigned full_ctas, unsigned tail_ctas, unsigned threads,

@@ -17,7 +17,7 @@
 // K2s/K4s *_small (small_*.cu)      Heun N = 2..7, implicit N = 2..4: one thread per cluster, moments in registers
 // K2 heun_cluster (cluster.cu)      N = 8..128: CTA = 32 members (lanes) x particle slots, 2/4/8 own particles
 //                                   per thread, moments (and the pair table, N <= 64) in shared memory
-// K2m heun_cluster_mma (cluster_mma.cu) N = 8..64 with a dense enough 8-particle grouping: the dipolar field as
+// K2m heun_cluster_mma (cluster_mma.cu) N = 8..128 with a dense enough 8-particle grouping: the dipolar field as
 //                                   D[3N x 3N] . M[3N x members] on DMMA.8x8x4, D packed in shared memory
 // K4 imid_cluster (cluster.cu)      N = 5..64: same mapping; block-diagonal quasi-Newton, CTA-wide convergence
 // K5 ensemble sums                  fused into all of them (warp shuffle -> smem -> per-CTA partial) +
@@ -48,6 +48,7 @@ struct RunParams {
     const double* v_red; // [N] reduced volumes (K2m folds them into the moments)
     uint32_t G;          // K2m: particle groups of 8 (= ceil(N / 8))
     uint32_t mma_full, mma_tail;  // K2m: CTAs that take a full set of members; members per CTA of the partial last wave
+    uint32_t mma_dglobal;            // K2m: the matrix is read from global memory (N = 65..128)
     uint32_t mma_mono;               // K2m: all reduced volumes are exactly 1 (no scaling of the moments)
     uint32_t cta_offset, cta_total;  // K2m: first CTA index of this launch, CTAs of both launches together
     const double* axis;  // see layout

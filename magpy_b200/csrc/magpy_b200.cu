@@ -199,6 +199,7 @@ struct magpy_b200_plan {
     bool one_buf = false;  //   ... with one shared-memory moment buffer
     uint32_t G = 0;        //   ... particle groups of 8
     uint32_t mma_full = 0, mma_tail = 0;   //   ... member distribution over CTAs (see choose_mma)
+    bool mma_dglobal = false;              //   ... matrix read from global memory (N > 64)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
@@ -317,24 +318,27 @@ int validate(const magpy_b200_ensemble* a) {
     return MAGPY_B200_OK;
 }
 
-// K2m (cluster_mma.cu) applies to Heun clusters of 8..64 interacting particles.  Particles are handled in groups of
+// K2m (cluster_mma.cu) applies to Heun clusters of 8..128 interacting particles (above 64 the packed matrix stays in
+// global memory: measured 2.0-2.4x the scalar kernel, profiles/r01_probe_cluster_mma_global.log).  Particles are handled in groups of
 // 8 (rows of the 8x8x4 MMA), so a cluster that fills its last group badly does padded work.  Measured
 // (profiles/r01_probe_cluster_mma_fill.log): the matrix kernel wins when N^2 / (8 G)^2 >= 0.7 and for every N > 32;
 // the scalar kernel keeps the rest unless MAGPY_B200_CLUSTER_KERNEL=mma asks otherwise (=simt forces the scalar
 // kernel everywhere).
 bool choose_mma(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     const uint32_t N = pl->N;
-    if (pl->implicit || N < 8 || N > 64 || a->interactions == 0) return false;
+    if (pl->implicit || N < 8 || N > 128 || a->interactions == 0) return false;
     const char* force = std::getenv("MAGPY_B200_CLUSTER_KERNEL");
     if (force && std::strcmp(force, "simt") == 0) return false;
     const uint32_t G = (N + 7) / 8;
     const double fill = (double)N * N / (64.0 * G * G);
     if (!(force && std::strcmp(force, "mma") == 0) && fill < 0.7 && N <= 32) return false;
+    pl->mma_dglobal = N > 64;   // the packed matrix no longer fits in shared memory: read it from global memory
     uint32_t MH = std::min<uint32_t>(8, 16 / G);
     const size_t cap = 227 * 1024;
     for (; MH >= 1; --MH) {
         const size_t MB = 16 * MH, LD = MB + 4;
-        const size_t dmat = (size_t)G * (G + 1) / 2 * 576 * 8, mom = (size_t)24 * G * LD * 8, red = (size_t)G * 3 * MB * 8;
+        const size_t dmat = pl->mma_dglobal ? 0 : (size_t)G * (G + 1) / 2 * 576 * 8, mom = (size_t)24 * G * LD * 8,
+                     red = (size_t)G * 3 * MB * 8;
         if (dmat + 2 * mom + red <= cap) { pl->one_buf = false; pl->smem = dmat + 2 * mom + red; break; }
         if (dmat + mom + red <= cap) { pl->one_buf = true; pl->smem = dmat + mom + red; break; }
     }
@@ -669,6 +673,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.v_red = pl->d_vred.p;
     P.G = pl->G;
     P.mma_full = pl->mma_full;
+    P.mma_dglobal = pl->mma_dglobal ? 1u : 0u;
     P.mma_mono = std::all_of(rd.v_red.begin(), rd.v_red.end(), [](double v) { return v == 1.0; }) ? 1u : 0u;
     P.mma_tail = pl->mma_tail;
     P.axis = pl->d_axis.p;

@@ -161,8 +161,9 @@ def test_heun_cluster_injected(orc, core, N, interactions, renorm, monkeypatch):
 # 8: one particle group, 8 member halves per CTA; 12 / 20: padded last group (forced: the default keeps the scalar
 # kernel for badly filled groups); 24, 40: two moment buffers; 56: seven groups; 64: ONE moment buffer next to the 162 KB matrix.
 # 140 members: several CTAs, ragged last one, both member halves and all column tiles populated.
+# 70, 128: the matrix read from global memory.
 @pytest.mark.parametrize('N,renorm,members', [(8, False, 140), (12, True, 35), (20, False, 35), (24, True, 70), (40, False, 35),
-                                              (56, False, 20), (64, False, 35), (64, True, 9)])
+                                              (56, False, 20), (64, False, 35), (64, True, 9), (70, True, 20), (128, False, 8)])
 def test_heun_cluster_mma_injected(orc, core, N, renorm, members, monkeypatch):
     if N in (12, 20):
         monkeypatch.setenv('MAGPY_B200_CLUSTER_KERNEL', 'mma')
