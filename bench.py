@@ -41,18 +41,38 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'particle-steps/s (fp64 LLG Heun ensemble)'
 UNIT = 'particle-steps/s'
-W_ALG = 98.0   # fp64 flop per N=1 Heun particle-step
+def w_alg(n_particles):
+    """fp64 flop per Heun particle-step: 98 + 36 (N - 1)."""
+    return 98.0 + 36.0 * (n_particles - 1)
 
-WORKLOAD = dict(
-    name='C3: 1M x 1-particle, sine field 300 kHz / 20 kA/m, Heun dt=1e-12 s, 100k steps per pass',
-    R=1_000_000, radius=12e-9, anisotropy=4e4, Ms=4e5, alpha=0.1, T=300.0,
-    dt=1e-12, t_end=1e-7, S=101, field_shape='sine', H0=2e4, f=3e5, random_state=1001)
+
+# The default workload (c3) is the configuration the BASELINE metric is quoted on.  `--workload c4` runs BASELINE
+# config 4 (64-particle random-geometry clusters, all-pairs dipolar field, Heun) through the same contract — the
+# second kernel family (cluster_mma.cu) with its own roofline line; the driver never passes it.
+WORKLOADS = {
+    'c3': dict(
+        name='C3: 1M x 1-particle, sine field 300 kHz / 20 kA/m, Heun dt=1e-12 s, 100k steps per pass',
+        N=1, R=1_000_000, radius=12e-9, anisotropy=4e4, Ms=4e5, alpha=0.1, T=300.0,
+        dt=1e-12, t_end=1e-7, S=101, field_shape='sine', H0=2e4, f=3e5, random_state=1001),
+    'c4': dict(
+        name='C4: 100k x 64-particle random clusters (min. separation 30 nm), all-pairs dipolar, Heun dt=1e-14 s, '
+             '2000 steps per pass',
+        N=64, R=100_000, radius=12e-9, anisotropy=4e4, Ms=4e5, alpha=0.1, T=300.0,
+        dt=1e-14, t_end=2e-11, S=21, field_shape='constant', H0=0.0, f=0.0, random_state=1001),
+}
+WORKLOAD = WORKLOADS['c3']
 
 
 def workload_arrays(R):
     w = WORKLOAD
-    return dict(radius=np.array([w['radius']]), anisotropy=np.array([w['anisotropy']]),
-                axis=np.array([[0.0, 0.0, 1.0]]), m0=np.array([[0.0, 0.0, 1.0]]), location=np.zeros((1, 3)))
+    N = w['N']
+    if N == 1:
+        return dict(radius=np.array([w['radius']]), anisotropy=np.array([w['anisotropy']]),
+                    axis=np.array([[0.0, 0.0, 1.0]]), m0=np.array([[0.0, 0.0, 1.0]]), location=np.zeros((1, 3)))
+    from magpy_b200 import geometry   # host-side input generation only (numpy)
+    axes = geometry.uniform_random_axes(N, rng=4)
+    return dict(radius=np.full(N, w['radius']), anisotropy=np.full(N, w['anisotropy']), axis=axes, m0=axes.copy(),
+                location=geometry.random_cluster_coordinates(N, 3e-8, rng=4))
 
 
 def member_seeds(R, random_state):
@@ -129,7 +149,7 @@ def load_cpu_reference():
             seeds = np.ascontiguousarray(seeds, dtype=np.int64)
             sums = np.zeros((w['S'], 4))
             el = lib.ref_ensemble(
-                C.c_size_t(len(seeds)), P(seeds), C.c_size_t(1), P(arr['radius']), P(arr['anisotropy']),
+                C.c_size_t(len(seeds)), P(seeds), C.c_size_t(w['N']), P(arr['radius']), P(arr['anisotropy']),
                 P(arr['axis']), C.c_size_t(0), P(arr['m0']), C.c_size_t(0), P(arr['location']),
                 C.c_double(w['Ms']), C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0),
                 C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']),
@@ -150,7 +170,7 @@ def load_cpu_reference():
         sums = np.zeros((w['S'], 4))
         t0 = time.perf_counter()
         lib.orc_ensemble(
-            C.c_size_t(len(seeds)), P(seeds), C.c_int(1), P(arr['radius']), P(arr['anisotropy']), P(arr['axis']),
+            C.c_size_t(len(seeds)), P(seeds), C.c_int(w['N']), P(arr['radius']), P(arr['anisotropy']), P(arr['axis']),
             C.c_size_t(0), P(arr['m0']), C.c_size_t(0), P(arr['location']), C.c_double(w['Ms']),
             C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0), C.c_double(1e-9),
             C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']), C.c_int(field_code),
@@ -191,7 +211,7 @@ def cpu_sample(run, cores, n_steps, target_seconds):
     n1 = int(min(len(seeds), max(n0, rate0 * target_seconds / n_steps)))
     n1 = max(cores, (n1 // cores) * cores)
     el1 = run(seeds[:n1])
-    return n1 * n_steps / el1, n1, el1
+    return WORKLOAD['N'] * n1 * n_steps / el1, n1, el1
 
 
 def reference_arm(args):
@@ -211,8 +231,9 @@ def reference_arm(args):
     t = 0.0
     for _ in range(args.steps):
         t += run(seeds[:n])
-    value = args.steps * n * n_steps / t
-    sample = '%d realisations x %d Heun steps per step (of the 1M-realisation workload), %d host threads' % (n, n_steps, cores)
+    value = WORKLOAD['N'] * args.steps * n * n_steps / t
+    sample = '%d realisations x %d Heun steps per step (of the %d-realisation workload), %d host threads' % (
+        n, n_steps, WORKLOAD['R'], cores)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True,
@@ -304,7 +325,7 @@ def ours(args):
     clocks = sampler.stop()
     gpu_launches = st['kernel_launches'] - launches0
     n_steps = st['steps_per_member']
-    ps_per_pass = R * n_steps
+    ps_per_pass = R * w['N'] * n_steps
 
     ms_per_step = t_dev / args.steps
     if dist is not None:
@@ -315,7 +336,7 @@ def ours(args):
         int_ms = t_int / args.steps
     value = world * ps_per_pass / (ms_per_step * 1e-3)
     out = plan.fetch()
-    mean_mz = float(out['sums'][-1, 2] / (R * world) / w['Ms'])   # the plan's sums were all-reduced in place
+    mean_mz = float(out['sums'][-1, 2] / (R * world) / w['Ms'] / w['N'])   # the plan's sums were all-reduced in place
     del plan
 
     # end to end through the public API with host buffers (H2D + D2H inside the timed region)
@@ -350,10 +371,11 @@ def ours(args):
             dist.destroy_process_group()
         return
 
+    W_ALG = w_alg(w['N'])
     achieved = W_ALG * ps_per_pass / (int_ms * 1e-3) / 1e12
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'heun_single_traffic.json')
-    if os.path.exists(prof):
+    if w['N'] == 1 and os.path.exists(prof):
         try:
             traffic = json.load(open(prof)).get('dram_bytes_per_launch')
         except Exception:
@@ -373,7 +395,7 @@ def ours(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': w['name'], 'realisations_per_gpu': R, 'particles': 1, 'heun_steps_per_pass': n_steps,
+        'config': {'workload': w['name'], 'realisations_per_gpu': R, 'particles': w['N'], 'heun_steps_per_pass': n_steps,
                    'samples': w['S'], 'rng': 'Philox4x32-10 + fp32 Box-Muller in kernel, one Philox block per two steps (gauss=f32p)',
                    'l2': 'state is register resident; no input is re-read between passes (0 B/step steady-state HBM '
                          'traffic), so no L2 flush applies',
@@ -381,7 +403,7 @@ def ours(args):
                    'mean_mz_over_Ms_at_end': mean_mz, 'wall_s_timed_region': wall},
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
                      'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': traffic,
-                     'kernel': 'heun_single_kernel', 'kernel_ms_per_launch': int_ms,
+                     'kernel': st['kernel'] + '_kernel', 'kernel_ms_per_launch': int_ms,
                      'algorithmic_flop_per_particle_step': W_ALG,
                      'peak_dfma_chain': dfma_tflops, 'peak_dmma_chain': dmma_tflops,
                      'peak_source': 'measured in this run: the larger of the library\'s register-resident DFMA-chain and '
@@ -410,7 +432,11 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS),
+                    help='c3 (default): the configuration the BASELINE metric is quoted on; c4: 64-particle clusters')
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = WORKLOADS[args.workload]
     if args.impl == 'reference':
         reference_arm(args)
     else:
