@@ -6,7 +6,8 @@ docs/source/notebooks/convergence.ipynb cells 29-38 (Cauchy differences between 
     dt = 1e-15 s * 2^L, L = 1..10  (2e-15 ... 1.024e-12 s), horizon T = 2.048e-11 s (20 steps at the coarsest dt)
 
 The C1 particle (12 nm, K = 4e4, Ms = 4e5, alpha = 0.1, T = 300 K), m0 tilted off the axis so that the weak error of
-<m_z> does not vanish by symmetry.  Prints one JSON line per scheme."""
+<m_z> does not vanish by symmetry.  Prints one JSON line per scheme; the third line repeats the implicit sweep with the opt-in
+exact-Jacobian Newton (implicit_newton='exact'): same Brownian paths, same scheme, ~2 iterations per step."""
 import json, sys, time
 import numpy as np
 sys.path.insert(0, '.')
@@ -16,7 +17,7 @@ radius, K, Ms, alpha, T = [12e-9], [4e4], 4e5, 0.1, 300.0
 axis, m0, loc = [[0, 0, 1.0]], [[0.6, 0, 0.8]], [[0, 0, 0.0]]
 
 
-def sweep(R, dt_fine, levels, n_coarsest, implicit):
+def sweep(R, dt_fine, levels, n_coarsest, implicit, newton='reference'):
     t0 = time.perf_counter()
     seeds = np.random.default_rng(5).integers(0, 2 ** 31 - 1, R)
     horizon = dt_fine * (1 << levels[-1]) * n_coarsest
@@ -25,7 +26,7 @@ def sweep(R, dt_fine, levels, n_coarsest, implicit):
         dt = dt_fine * (1 << L)
         out = core.simulate_ensemble(radius, K, axis, m0, loc, Ms, alpha, T, False, True, implicit, dt,
                                      horizon * (1 + 1e-9), 2, seeds, implicit_tol=1e-9, return_trajectories=False,
-                                     noise_coarsen_log2=L)
+                                     noise_coarsen_log2=L, implicit_newton=newton)
         st = out['stats']
         assert st['steps_per_member'] == n_coarsest << (levels[-1] - L), (st['steps_per_member'], L)
         steps += st['particle_steps']; dev_ms += st['device_ms']
@@ -39,7 +40,7 @@ def sweep(R, dt_fine, levels, n_coarsest, implicit):
     x = np.arange(n - 1)
     sig = [int(i) for i in x if weak[i] > 3 * weak_se[i]]
     print(json.dumps({
-        'scheme': 'implicit midpoint' if implicit else 'Heun', 'realisations': R, 'horizon_s': horizon,
+        'scheme': ('implicit midpoint' + (' (exact-Jacobian Newton, opt-in)' if newton == 'exact' else '')) if implicit else 'Heun', 'realisations': R, 'horizon_s': horizon,
         'dt_s': [dt_fine * (1 << L) for L in levels],
         'strong_cauchy_diff': strong, 'strong_order': float(np.polyfit(x, np.log2(strong), 1)[0]),
         'strong_local_slopes': [float(v) for v in np.diff(np.log2(strong))],
@@ -52,5 +53,5 @@ def sweep(R, dt_fine, levels, n_coarsest, implicit):
 
 if __name__ == '__main__':
     R = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
-    for implicit in (True, False):
-        sweep(R, 1e-15, list(range(1, 11)), 20, implicit)
+    for implicit, newton in ((True, 'reference'), (False, 'reference'), (True, 'exact')):
+        sweep(R, 1e-15, list(range(1, 11)), 20, implicit, newton)
