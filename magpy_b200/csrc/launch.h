@@ -30,6 +30,9 @@ cudaError_t launch_reduce_partials(const double* partial, double* sums, uint32_t
                                    cudaStream_t s);
 cudaError_t launch_transpose(const double* in, double* out, uint64_t rows, uint64_t cols, uint64_t batches, uint64_t in_bs,
                              uint64_t in_rs, uint64_t out_bs, uint64_t out_rs, double scale, cudaStream_t s);
+// in[S][n][R] -> out[R][n][S] * scale (trajectory fetch)
+cudaError_t launch_traj_fetch(const double* in, double* out, uint64_t R, uint32_t n, uint32_t S, double scale,
+                              cudaStream_t s);
 cudaError_t launch_broadcast_rows(const double* in, double* out, uint64_t n, uint64_t R, cudaStream_t s);
 cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t s);
 cudaError_t launch_fp64_mma_peak(double* out, int blocks, int threads, int iters, cudaStream_t s);

@@ -793,7 +793,12 @@ int plan_fetch(magpy_b200_plan* pl, double* out_time, double* out_field, double*
     if (out_traj) {
         if (!pl->want_traj) return fail(MAGPY_B200_ERR_BAD_ARG, "plan was created without out_trajectories");
         // device [S][n][R] -> host [R][n][S], scaled to A/m (lib/simulation.cpp:617-620)
-        int rc = launch_transpose(pl, pl->d_traj.p, pl->d_stage.p, n, S, R, R, n * R, S, n * S, pl->Ms);
+        int rc = MAGPY_B200_OK;
+        if ((uint64_t)n * S <= 65535ull * 128) {   // dedicated kernel: full 256 B lines on both sides (service.cu)
+            LAUNCH_TRY(mb::launch_traj_fetch(pl->d_traj.p, pl->d_stage.p, R, (uint32_t)n, (uint32_t)S, pl->Ms, pl->stream));
+        } else {
+            rc = launch_transpose(pl, pl->d_traj.p, pl->d_stage.p, n, S, R, R, n * R, S, n * S, pl->Ms);
+        }
         if (rc) return rc;
         CU_TRY(cudaMemcpyAsync(out_traj, pl->d_stage.p, S * n * R * 8, cudaMemcpyDeviceToHost, pl->stream));
         CU_TRY(cudaStreamSynchronize(pl->stream));

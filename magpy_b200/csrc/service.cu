@@ -69,6 +69,36 @@ __global__ void transpose_kernel(const double* in, double* out, uint64_t rows, u
     }
 }
 
+// Trajectory fetch: the kernels store sampled points as in[s][q][r] (member index fastest: one coalesced 256 B line per
+// warp and component); the API wants out[r][q][s] (include/magpy_b200.h, out_trajectories).  For a member the n S
+// values are one contiguous run of the output, so a CTA takes 32 members x TRAJ_TILE_K consecutive output entries
+// k' = q S + s: every load is a full 256 B line of 32 members, every store a full 256 B line of a member's run (the
+// generic 32 x 32 tile transpose writes ragged rows whenever S is not a multiple of 32: 2.95 TB/s at S = 101).
+constexpr int TRAJ_TILE_K = 128;
+__global__ void __launch_bounds__(256) traj_fetch_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                         const uint64_t R, const uint32_t n, const uint32_t S,
+                                                         const double scale) {
+    __shared__ double tile[TRAJ_TILE_K][33];
+    const uint32_t K = n * S;
+    const uint64_t r0 = (uint64_t)blockIdx.x * 32;
+    const uint32_t k0 = blockIdx.y * TRAJ_TILE_K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t kk = warp; kk < TRAJ_TILE_K; kk += 8) {
+        const uint32_t k = k0 + kk;
+        if (k < K && r0 + lane < R) {
+            const uint32_t q = k / S, sidx = k - q * S;
+            tile[kk][lane] = in[((uint64_t)sidx * n + q) * R + r0 + lane];
+        }
+    }
+    __syncthreads();
+    const uint32_t kn = K - k0 < TRAJ_TILE_K ? K - k0 : TRAJ_TILE_K;   // valid entries of this tile
+    for (uint32_t rr = warp; rr < 32; rr += 8) {
+        if (r0 + rr >= R) break;
+        double* dst = out + (r0 + rr) * K + k0;
+        for (uint32_t kk = lane; kk < kn; kk += 32) dst[kk] = tile[kk][rr] * scale;
+    }
+}
+
 // out[q][r] = in[q] for q < n, r < R (shared initial state replicated over the members)
 __global__ void broadcast_rows_kernel(const double* in, double* out, uint64_t n, uint64_t R) {
     const uint64_t total = n * R;
@@ -141,6 +171,15 @@ cudaError_t launch_transpose(const double* in, double* out, uint64_t rows, uint6
                              uint64_t in_rs, uint64_t out_bs, uint64_t out_rs, double scale, cudaStream_t s) {
     const dim3 g((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batches), b(32, 8);
     transpose_kernel<<<g, b, 0, s>>>(in, out, rows, cols, in_bs, in_rs, out_bs, out_rs, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_traj_fetch(const double* in, double* out, uint64_t R, uint32_t n, uint32_t S, double scale,
+                              cudaStream_t s) {
+    const uint64_t gx = (R + 31) / 32;
+    const uint32_t gy = (n * S + TRAJ_TILE_K - 1) / TRAJ_TILE_K;
+    if (gx > 0x7FFFFFFFull || gy > 65535) return cudaErrorInvalidValue;
+    traj_fetch_kernel<<<dim3((unsigned)gx, gy), 256, 0, s>>>(in, out, R, n, S, scale);
     return cudaGetLastError();
 }
 
