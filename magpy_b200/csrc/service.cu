@@ -1,3 +1,4 @@
+#include <cstdlib>
 #include "common.cuh"
 #include "launch.h"
 
@@ -74,7 +75,7 @@ __global__ void transpose_kernel(const double* in, double* out, uint64_t rows, u
 // values are one contiguous run of the output, so a CTA takes 32 members x TRAJ_TILE_K consecutive output entries
 // k' = q S + s: every load is a full 256 B line of 32 members, every store a full 256 B line of a member's run (the
 // generic 32 x 32 tile transpose writes ragged rows whenever S is not a multiple of 32: 2.95 TB/s at S = 101).
-constexpr int TRAJ_TILE_K = 128;
+template <int TRAJ_TILE_K>
 __global__ void __launch_bounds__(256) traj_fetch_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                          const uint64_t R, const uint32_t n, const uint32_t S,
                                                          const double scale) {
@@ -96,6 +97,31 @@ __global__ void __launch_bounds__(256) traj_fetch_kernel(const double* __restric
         if (r0 + rr >= R) break;
         double* dst = out + (r0 + rr) * K + k0;
         for (uint32_t kk = lane; kk < kn; kk += 32) dst[kk] = tile[kk][rr] * scale;
+    }
+}
+
+// The same for short runs (n S <= 800 doubles): the CTA stages ALL n S entries of its 32 members (dynamic shared
+// memory), whose output is then one contiguous, 256 B-aligned region written linearly.
+__global__ void __launch_bounds__(512) traj_fetch_full_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                              const uint64_t R, const uint32_t n, const uint32_t S,
+                                                              const double scale) {
+    extern __shared__ double ftile[];   // [K][33]
+    const uint32_t K = n * S;
+    const uint64_t r0 = (uint64_t)blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t k = warp; k < K; k += 16) {
+        if (r0 + lane < R) {
+            const uint32_t q = k / S, sidx = k - q * S;
+            ftile[k * 33 + lane] = in[((uint64_t)sidx * n + q) * R + r0 + lane];
+        }
+    }
+    __syncthreads();
+    const uint32_t members = R - r0 < 32 ? (uint32_t)(R - r0) : 32u;
+    const uint32_t total = members * K;
+    double* dst = out + r0 * K;
+    for (uint32_t e = threadIdx.x; e < total; e += 512) {
+        const uint32_t rr = e / K, k = e - rr * K;
+        dst[e] = ftile[k * 33 + rr] * scale;
     }
 }
 
@@ -177,9 +203,24 @@ cudaError_t launch_transpose(const double* in, double* out, uint64_t rows, uint6
 cudaError_t launch_traj_fetch(const double* in, double* out, uint64_t R, uint32_t n, uint32_t S, double scale,
                               cudaStream_t s) {
     const uint64_t gx = (R + 31) / 32;
-    const uint32_t gy = (n * S + TRAJ_TILE_K - 1) / TRAJ_TILE_K;
+    if ((uint64_t)n * S <= 800 && gx <= 0x7FFFFFFFull && !std::getenv("MAGPY_B200_TRAJ_TILE")) {
+        const size_t smem = (size_t)n * S * 33 * sizeof(double);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(traj_fetch_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        traj_fetch_full_kernel<<<(unsigned)gx, 512, smem, s>>>(in, out, R, n, S, scale);
+        return cudaGetLastError();
+    }
+    int tk = 128;
+    if (const char* env = std::getenv("MAGPY_B200_TRAJ_TILE")) tk = std::atoi(env);   // tuning knob: 32, 64 or 128
+    const uint32_t gy = (n * S + tk - 1) / tk;
     if (gx > 0x7FFFFFFFull || gy > 65535) return cudaErrorInvalidValue;
-    traj_fetch_kernel<<<dim3((unsigned)gx, gy), 256, 0, s>>>(in, out, R, n, S, scale);
+    const dim3 g((unsigned)gx, gy);
+    if (tk == 64) traj_fetch_kernel<64><<<g, 256, 0, s>>>(in, out, R, n, S, scale);
+    else if (tk == 32) traj_fetch_kernel<32><<<g, 256, 0, s>>>(in, out, R, n, S, scale);
+    else if (tk == 128) traj_fetch_kernel<128><<<g, 256, 0, s>>>(in, out, R, n, S, scale);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
