@@ -333,3 +333,25 @@ def test_sharded_ensemble_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+@pytest.mark.parametrize('workload', ['c3', 'c4'])
+def test_bench_reference_arm_contract(workload):
+    """`bench.py --impl reference` (the reference's own CPU path on the host cores, a bounded sample per step) prints ONE
+    JSON line with the contract's keys; it needs no GPU and never touches the product library."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--workload', workload,
+                          '--steps', '1', '--warmup', '0'], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['unit'] == 'particle-steps/s' and line['value'] > 1e5
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['gpu_launches'] == 0
+    assert line['config']['workload'].startswith(workload.upper())
