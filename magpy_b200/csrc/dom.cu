@@ -23,6 +23,7 @@ constexpr double DOM_PI = 3.14159265358979323846;
 
 struct DomSys {
     double k, v, T, ms, alpha, h, f;
+    double sigma, pre0;   // field-independent parts of lib/dom.cpp:44-53, hoisted (same operations, same order)
     int shape;
     unsigned ncomp;
 };
@@ -45,10 +46,9 @@ __device__ double dom_field(const DomSys& s, const double t) {
 // lib/dom.cpp:33-59 then W p (lib/stochastic_processes.cpp:18-25)
 __device__ void dom_derivs(double (&d)[2], const double (&p)[2], const double t, const DomSys& s) {
     const double h = dom_field(s, t);
-    const double sigma = s.k * s.v / DOM_KB / s.T;
-    const double taun = s.v * s.ms * (1 + s.alpha * s.alpha) / 2.0 / DOM_GYROMAG / s.alpha / DOM_KB / s.T;
+    const double sigma = s.sigma;
     const double e1 = sigma * (1 - h) * (1 - h), e2 = sigma * (1 + h) * (1 + h);
-    const double prefactor = taun * sqrt(DOM_PI) / pow(sigma, 1.5) / (1 - h * h);
+    const double prefactor = s.pre0 / (1 - h * h);   // ((taun sqrt(pi)) / sigma^1.5) / (1 - h^2), left to right as the reference
     const double rate1 = 1.0 / prefactor * (1 - h) * exp(-e1);
     const double rate2 = 1.0 / prefactor * (1 + h) * exp(-e2);
     d[0] = -rate2 * p[0] + rate1 * p[1];
@@ -112,6 +112,11 @@ __global__ void dom_kernel(const DomBatch B) {
     s.k = B.anisotropy[b]; s.v = B.volume[b]; s.T = B.temperature; s.ms = B.magnetisation; s.alpha = B.alpha;
     const double H_k = 2.0 * s.k / B.mu0 / s.ms;              // magpy/core.pyx:224-225
     s.h = B.field_amplitude / H_k; s.f = B.field_frequency; s.shape = B.field_shape; s.ncomp = B.n_components;
+    s.sigma = s.k * s.v / DOM_KB / s.T;
+    {
+        const double taun = s.v * s.ms * (1 + s.alpha * s.alpha) / 2.0 / DOM_GYROMAG / s.alpha / DOM_KB / s.T;
+        s.pre0 = taun * sqrt(DOM_PI) / pow(s.sigma, 1.5);
+    }
     double last[2], next[2] = {B.p0[2 * b], B.p0[2 * b + 1]};
     const uint64_t S = B.S;
     const double sampling_time = B.end_time / (S - 1);
