@@ -127,6 +127,11 @@ typedef struct magpy_b200_ensemble {
      * step.  For clusters each particle's own exact Jacobian is used; the dipolar coupling between particles stays
      * out of the matrix (as in the reference), which leaves a fast linear convergence (4-5 iterations). */
     uint32_t implicit_newton;
+    /* Per-member radii (ABI v3): 0 = `radius` holds the N radii shared by all members; N = `radius` holds
+     * [R][N] values.  Supported for single-particle ensembles (N = 1) — a size distribution integrated in one
+     * launch: with one particle the radius enters only through the thermal field strength sigma_i
+     * (lib/simulation.cpp:531-535), which becomes a per-member array. */
+    uint64_t radius_stride;
 } magpy_b200_ensemble;
 #define MAGPY_B200_NEWTON_REFERENCE 0
 #define MAGPY_B200_NEWTON_EXACT 1

@@ -85,6 +85,7 @@ cdef extern from "magpy_b200.h" nogil:
         double* out_final
         uint32_t noise_coarsen_log2
         uint32_t implicit_newton
+        uint64_t radius_stride
 
     ctypedef struct magpy_b200_plan:
         pass
@@ -264,8 +265,11 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
                                bint return_trajectories, bint return_sums, bint return_final, str gauss,
                                injected_dw, int noise_coarsen_log2=0, str implicit_newton='reference'):
     cdef _EnsembleArgs e = _EnsembleArgs()
-    cdef np.ndarray[double, ndim=1, mode='c'] c_radius = np.ascontiguousarray(radius, dtype=np.float64).reshape(-1)
-    cdef size_t N = c_radius.shape[0]
+    # radius: (N,) shared by all members, or (R, N) per member (single-particle ensembles: a size distribution)
+    rad = np.ascontiguousarray(radius, dtype=np.float64)
+    cdef bint member_radii = rad.ndim == 2
+    cdef np.ndarray[double, ndim=1, mode='c'] c_radius = rad.reshape(-1)
+    cdef size_t N = rad.shape[1] if member_radii else c_radius.shape[0]
     cdef np.ndarray[double, ndim=1, mode='c'] c_anis = np.ascontiguousarray(anisotropy, dtype=np.float64).reshape(-1)
     cdef np.ndarray[double, ndim=2, mode='c'] c_loc = np.ascontiguousarray(location, dtype=np.float64).reshape(-1, 3)
     if N == 0 or c_anis.shape[0] != N or c_loc.shape[0] != N:
@@ -274,6 +278,8 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
     cdef size_t R = c_seeds.shape[0]
     if R == 0:
         raise ValueError('seeds must hold one seed per ensemble member')
+    if member_radii and (rad.shape[0] != R or N != 1):
+        raise ValueError('per-member radii need shape (R, 1): supported for single-particle ensembles only')
     if int(max_samples) < 2:
         raise ValueError('max_samples must be >= 2')
     cdef size_t S = int(max_samples)
@@ -293,6 +299,7 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
     e.a.n_members = R
     e.a.n_particles = N
     e.a.radius = &c_radius[0]
+    e.a.radius_stride = N if member_radii else 0
     e.a.anisotropy = &c_anis[0]
     e.a.location = &c_loc[0, 0]
     e.a.anisotropy_axis = &c_ax[0]

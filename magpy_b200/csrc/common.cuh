@@ -42,7 +42,8 @@ struct RunParams {
     int newton_exact;    // implicit: 0 = the reference's quasi-Newton iteration (parity), 1 = Newton with the exact Jacobian
     double h_const;      // applied field when no table is used (reduced units)
     const double* k_red; // [N]
-    const double* sig;   // [N] thermal field strength sigma_i
+    const double* sig;   // [N] thermal field strength sigma_i; N = 1 with per-member radii: [R] (sig_rs = 1)
+    uint64_t sig_rs;     // member stride of `sig` (0 or 1)
     const double* dip;   // [N][N][4] {sqrt(3) r_hat_ij (3), c_dip * v_j / cube_ij}; diagonal zero
     const double* dmat;  // K2m: packed upper 24x24 blocks of the symmetric dipolar matrix (cluster_mma.cu) or nullptr
     const double* v_red; // [N] reduced volumes (K2m folds them into the moments)

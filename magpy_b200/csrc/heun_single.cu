@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1_MIN_BLOCKS) heun_single_
     const double alpha = P.alpha, dt = P.dt;
     const double kdt = P.k_red[0] * dt;
     const V3 edt{e.x * kdt, e.y * kdt, e.z * kdt};
-    const double c = P.sig[0] * P.sqrt_dt;
+    const double c = P.sig[r * P.sig_rs] * P.sqrt_dt;   // per-member sigma when the radii differ between members
     const float bm_scale = scale_to_bm(c);
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
 
     V3 m{P.state[r], P.state[P.R + r], P.state[2 * P.R + r]};
     const V3 e{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
-    const double kred = P.k_red[0], sr = P.sig[0];
+    const double kred = P.k_red[0], sr = P.sig[r * P.sig_rs];   // per-member sigma when the radii differ
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t member = (uint32_t)(r + P.stream_offset);

@@ -144,7 +144,9 @@ class EnsembleModel:
         if return_trajectories is None:
             return_trajectories = (hi - lo) * N * 3 * int(max_samples) * 8 <= _TRAJ_BYTES_AUTO
 
-        other_keys = [k for k in self._overrides if k not in _PER_MEMBER_FAST]
+        # per-member radii of single-particle members go to the device as an array too (one launch for a size distribution)
+        fast = _PER_MEMBER_FAST + (('radius',) if N == 1 else ())
+        other_keys = [k for k in self._overrides if k not in fast]
         if other_keys:
             groups = {}
             for i in range(lo, hi):
@@ -174,8 +176,12 @@ class EnsembleModel:
                         np.asarray([self._overrides[key][i] for i in idx], dtype=np.float64).reshape(len(idx), N, 3))
                 return np.ascontiguousarray(np.asarray(base[key], dtype=np.float64).reshape(N, 3))
 
+            radius = params['radius']
+            if N == 1 and 'radius' in self._overrides:
+                radius = np.ascontiguousarray(
+                    np.asarray([self._overrides['radius'][i] for i in idx], dtype=np.float64).reshape(len(idx), 1))
             out = core.simulate_ensemble(
-                params['radius'], params['anisotropy'], member_array('anisotropy_axis'),
+                radius, params['anisotropy'], member_array('anisotropy_axis'),
                 member_array('magnetisation_direction'), params['location'], params['magnetisation'],
                 params['damping'], params['temperature'], renorm, interactions, implicit_solve, time_step,
                 end_time, S, seeds[lo:hi] if single else seeds[idx], params['field_shape'],

@@ -276,6 +276,41 @@ def test_exact_newton_mode_is_the_converged_reference_iteration(orc, core, N, ax
         assert np.abs(fast2['trajectories'] - ref).max() / c.Ms < 1e-11
 
 
+@pytest.mark.parametrize('implicit', [False, True])
+def test_per_member_radii_single_particle(orc, core, implicit):
+    """A size distribution in ONE launch: single-particle members that differ in radius (radius of shape (R, 1) ->
+    `radius_stride`), each against the oracle run with its own radius and the reference's Wiener stream of its seed.
+    Through EnsembleModel the same ensemble (radius=[...] per member) takes one device call instead of one per size."""
+    rng = np.random.default_rng(9)
+    R = 40
+    radii = rng.uniform(5e-9, 9e-9, R)
+    seeds = np.arange(1, R + 1) * 37
+    base = ol.make_case(N=1, dt=1e-13 if not implicit else 1e-12, t_end=2e-11 if not implicit else 6e-11, S=17, implicit=implicit,
+                        field_shape='sine', H0=1.5e4, f=5e9, axis=[[0.6, 0, 0.8]], m0=[[0, 0, 1.0]])
+    n_steps = ol.steps_executed(orc, base)          # the schedule does not depend on the radius
+    dW = np.stack([ol.mt_normal(orc, int(s), n_steps * 3).reshape(n_steps, 3) for s in seeds])
+    ref = np.stack([ol.oracle_simulate(orc, ol.Case(dict(base, radius=np.array([radii[i]]))), seed=int(seeds[i]))[2]
+                    for i in range(R)])
+    out = core.simulate_ensemble(radii.reshape(R, 1), base.anisotropy, base.axis, base.m0, base.location, base.Ms, base.alpha,
+                                 base.T, False, True, implicit, base.dt, base.t_end, base.S, seeds, field_shape='sine',
+                                 field_amplitude=base.H0, field_frequency=base.f, injected_dw=dW)
+    assert np.abs(out['trajectories'] - ref).max() / base.Ms <= TOL
+    assert out['stats']['kernel_launches'] < 12            # one integration launch, not one per radius
+    # the noise amplitude really is per member: the smallest particle wanders furthest from its start
+    spread = np.abs(out['trajectories'][:, 0, :, -1] / base.Ms - np.array([0, 0, 1.0])).max(axis=1)
+    assert spread[np.argmin(radii)] > spread[np.argmax(radii)]
+    with pytest.raises(ValueError):                          # clusters: per-member radii change the geometry-dependent tables
+        c2 = ol.make_case(N=2)
+        core.simulate_ensemble(np.full((3, 2), 7e-9), c2.anisotropy, c2.axis, c2.m0, c2.location, c2.Ms, c2.alpha, c2.T,
+                               False, True, False, c2.dt, c2.t_end, c2.S, [1, 2, 3])
+    import magpy_b200 as mp
+    model = mp.Model(np.array([7e-9]), base.anisotropy, base.axis, base.m0, base.location, base.Ms, base.alpha, base.T,
+                     field_shape='sine', field_frequency=base.f, field_amplitude=base.H0)
+    ens = mp.EnsembleModel(R, model, radius=[np.array([r]) for r in radii])
+    res = ens.simulate(base.t_end, base.dt, base.S, 1001, implicit_solve=implicit)
+    assert len(res.stats) == 1 and res.stats[0]['particle_steps'] == R * n_steps - R   # the product skips the last, never-sampled step
+
+
 def test_single_simulate_api_and_schedule_edges(orc, core):
     """core.simulate keeps the reference's dict; sampling finer than the time step repeats states."""
     c = ol.make_case(N=2, dt=1e-12, t_end=1e-11, S=40, implicit=False)    # Ts < dt: zero-order hold repeats
