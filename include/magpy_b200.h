@@ -132,6 +132,9 @@ typedef struct magpy_b200_ensemble {
      * launch: with one particle the radius enters only through the thermal field strength sigma_i
      * (lib/simulation.cpp:531-535), which becomes a per-member array. */
     uint64_t radius_stride;
+    /* Per-member temperatures (ABI v3): NULL, or [R] temperatures in K that replace `temperature` member by member.
+     * Single-particle ensembles only, for the same reason (the temperature enters through sigma_i alone). */
+    const double* member_temperature;
 } magpy_b200_ensemble;
 #define MAGPY_B200_NEWTON_REFERENCE 0
 #define MAGPY_B200_NEWTON_EXACT 1

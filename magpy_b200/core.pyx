@@ -86,6 +86,7 @@ cdef extern from "magpy_b200.h" nogil:
         uint32_t noise_coarsen_log2
         uint32_t implicit_newton
         uint64_t radius_stride
+        const double* member_temperature
 
     ctypedef struct magpy_b200_plan:
         pass
@@ -258,7 +259,7 @@ cdef class _EnsembleArgs:
 
 
 cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
-                               double magnetisation, double damping, double temperature, bint renorm,
+                               double magnetisation, double damping, temperature, bint renorm,
                                bint interactions, bint use_implicit, double time_step, double end_time,
                                max_samples, seeds, str field_shape, double field_amplitude,
                                double field_frequency, double implicit_tol, int device, stream_offset,
@@ -308,7 +309,17 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
     e.a.m0_stride = 3 * N if m0.ndim == 3 else 0
     e.a.magnetisation = magnetisation
     e.a.damping = damping
-    e.a.temperature = temperature
+    # temperature: a scalar, or one value per member (single-particle ensembles: a temperature sweep in one launch)
+    cdef np.ndarray[double, ndim=1, mode='c'] c_temp
+    if np.ndim(temperature) == 0:
+        e.a.temperature = float(temperature)
+    else:
+        c_temp = np.ascontiguousarray(temperature, dtype=np.float64).reshape(-1)
+        if c_temp.shape[0] != R or N != 1:
+            raise ValueError('per-member temperatures need one value per member: supported for single-particle ensembles only')
+        e.keep.append(c_temp)
+        e.a.temperature = c_temp[0]
+        e.a.member_temperature = &c_temp[0]
     e.a.renorm = renorm
     e.a.interactions = interactions
     e.a.use_implicit = use_implicit
@@ -359,7 +370,7 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
 
 
 def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
-                      double magnetisation, double damping, double temperature, bint renorm, bint interactions,
+                      double magnetisation, double damping, temperature, bint renorm, bint interactions,
                       bint use_implicit, double time_step, double end_time, max_samples, seeds,
                       str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
                       double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=True,
@@ -421,7 +432,7 @@ cdef class EnsemblePlan:
         self.plan = NULL
 
     def __init__(self, radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
-                 double magnetisation, double damping, double temperature, bint renorm, bint interactions,
+                 double magnetisation, double damping, temperature, bint renorm, bint interactions,
                  bint use_implicit, double time_step, double end_time, max_samples, seeds,
                  str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
                  double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=False,

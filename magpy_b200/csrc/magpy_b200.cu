@@ -294,6 +294,8 @@ int validate(const magpy_b200_ensemble* a) {
     if (a->m0_stride != 0 && a->m0_stride != n) return fail(MAGPY_B200_ERR_BAD_ARG, "m0_stride must be 0 or 3N");
     if (a->radius_stride != 0 && (a->radius_stride != a->n_particles || a->n_particles != 1))
         return fail(MAGPY_B200_ERR_BAD_ARG, "per-member radii (radius_stride = N) are supported for single-particle ensembles only");
+    if (a->member_temperature && a->n_particles != 1)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "per-member temperatures are supported for single-particle ensembles only");
     if (a->max_samples < 2) return fail(MAGPY_B200_ERR_BAD_ARG, "max_samples must be >= 2 (lib/simulation.cpp:174)");
     if (a->max_samples > 0x7FFFFFFFull) return fail(MAGPY_B200_ERR_BAD_ARG, "max_samples too large");
     if (!(a->time_step > 0.0) || !(a->end_time > 0.0)) return fail(MAGPY_B200_ERR_BAD_ARG, "time_step and end_time must be > 0");
@@ -536,7 +538,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     CU_TRY(pl->d_state0.alloc(n * R, pl->stream));
     CU_TRY(pl->d_state.alloc(n * R, pl->stream));
     CU_TRY(pl->d_kred.alloc(N, pl->stream));
-    const bool member_radii = a->radius_stride != 0;   // N = 1: sigma per member
+    const bool member_radii = a->radius_stride != 0 || a->member_temperature != nullptr;   // N = 1: sigma per member
     CU_TRY(pl->d_sig.alloc(member_radii ? R : N, pl->stream));
     CU_TRY(pl->d_seeds.alloc(R, pl->stream));
     CU_TRY(pl->d_target.alloc(pl->S, pl->stream));
@@ -550,9 +552,10 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         // lib/simulation.cpp:531-535 per member: sigma = sqrt(alpha KB T / (K_av V_r) / (1 + alpha^2)), same order as reduce_units
         member_sigma.resize(R);
         for (uint64_t r = 0; r < R; ++r) {
-            const double rad = a->radius[r];
+            const double rad = a->radius[a->radius_stride ? r : 0];
             const double vol = 4.0 / 3.0 * M_PI * rad * rad * rad;
-            member_sigma[r] = std::sqrt(a->damping * kKB * a->temperature / (rd.K_av * vol) / (1 + a->damping * a->damping));
+            const double T = a->member_temperature ? a->member_temperature[r] : a->temperature;
+            member_sigma[r] = std::sqrt(a->damping * kKB * T / (rd.K_av * vol) / (1 + a->damping * a->damping));
         }
         CU_TRY(cudaMemcpyAsync(pl->d_sig.p, member_sigma.data(), R * 8, cudaMemcpyHostToDevice, pl->stream));
         CU_TRY(cudaStreamSynchronize(pl->stream));
@@ -685,7 +688,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.h_const = rd.h0;
     P.k_red = pl->d_kred.p;
     P.sig = pl->d_sig.p;
-    P.sig_rs = a->radius_stride != 0 ? 1 : 0;
+    P.sig_rs = (a->radius_stride != 0 || a->member_temperature != nullptr) ? 1 : 0;
     P.dip = pl->d_dip.p;
     P.dmat = pl->d_dmat.p;
     P.v_red = pl->d_vred.p;
@@ -979,6 +982,7 @@ int magpy_b200_simulate_ensemble_multi(const magpy_b200_ensemble* args, const in
             if (a.axis_stride) a.anisotropy_axis += lo * a.axis_stride;
             if (a.m0_stride) a.magnetisation_direction += lo * a.m0_stride;
             if (a.radius_stride) a.radius += lo * a.radius_stride;
+            if (a.member_temperature) a.member_temperature += lo;
             if (a.injected_dw) a.injected_dw += lo * a.injected_steps * n;
             if (a.out_trajectories) a.out_trajectories += lo * n * S;
             if (a.out_final) a.out_final += lo * n;

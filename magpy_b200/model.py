@@ -144,8 +144,9 @@ class EnsembleModel:
         if return_trajectories is None:
             return_trajectories = (hi - lo) * N * 3 * int(max_samples) * 8 <= _TRAJ_BYTES_AUTO
 
-        # per-member radii of single-particle members go to the device as an array too (one launch for a size distribution)
-        fast = _PER_MEMBER_FAST + (('radius',) if N == 1 else ())
+        # per-member radii / temperatures of single-particle members go to the device as arrays too (one launch for a size
+        # distribution or a temperature sweep)
+        fast = _PER_MEMBER_FAST + (('radius', 'temperature') if N == 1 else ())
         other_keys = [k for k in self._overrides if k not in fast]
         if other_keys:
             groups = {}
@@ -180,10 +181,13 @@ class EnsembleModel:
             if N == 1 and 'radius' in self._overrides:
                 radius = np.ascontiguousarray(
                     np.asarray([self._overrides['radius'][i] for i in idx], dtype=np.float64).reshape(len(idx), 1))
+            temperature = params['temperature']
+            if N == 1 and 'temperature' in self._overrides:
+                temperature = np.asarray([self._overrides['temperature'][i] for i in idx], dtype=np.float64)
             out = core.simulate_ensemble(
                 radius, params['anisotropy'], member_array('anisotropy_axis'),
                 member_array('magnetisation_direction'), params['location'], params['magnetisation'],
-                params['damping'], params['temperature'], renorm, interactions, implicit_solve, time_step,
+                params['damping'], temperature, renorm, interactions, implicit_solve, time_step,
                 end_time, S, seeds[lo:hi] if single else seeds[idx], params['field_shape'],
                 params['field_amplitude'], params['field_frequency'], implicit_tol, device=device,
                 stream_offset=int(stream_offset) + first, return_trajectories=return_trajectories,

@@ -309,6 +309,15 @@ def test_per_member_radii_single_particle(orc, core, implicit):
     ens = mp.EnsembleModel(R, model, radius=[np.array([r]) for r in radii])
     res = ens.simulate(base.t_end, base.dt, base.S, 1001, implicit_solve=implicit)
     assert len(res.stats) == 1 and res.stats[0]['particle_steps'] == R * n_steps - R   # the product skips the last, never-sampled step
+    # per-member temperatures ride on the same per-member sigma: a temperature sweep against the oracle, member by member
+    temps = rng.uniform(100.0, 400.0, R)
+    ref_t = np.stack([ol.oracle_simulate(orc, ol.Case(dict(base, T=float(temps[i]))), seed=int(seeds[i]))[2] for i in range(R)])
+    out_t = core.simulate_ensemble(base.radius, base.anisotropy, base.axis, base.m0, base.location, base.Ms, base.alpha,
+                                   temps, False, True, implicit, base.dt, base.t_end, base.S, seeds, field_shape='sine',
+                                   field_amplitude=base.H0, field_frequency=base.f, injected_dw=dW)
+    assert np.abs(out_t['trajectories'] - ref_t).max() / base.Ms <= TOL
+    ens_t = mp.EnsembleModel(R, model, temperature=list(temps), radius=[np.array([r]) for r in radii])
+    assert len(ens_t.simulate(base.t_end, base.dt, base.S, 1001, implicit_solve=implicit).stats) == 1
 
 
 def test_single_simulate_api_and_schedule_edges(orc, core):
