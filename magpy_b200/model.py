@@ -12,6 +12,7 @@ from . import core
 from .results import Results, EnsembleResults
 
 _PER_MEMBER_FAST = ('anisotropy_axis', 'magnetisation_direction')
+_MAX_CONCURRENT_PLANS = 32   # parameter groups in flight at once (each holds its own device buffers)
 _TRAJ_BYTES_AUTO = 2 << 30
 
 
@@ -165,7 +166,30 @@ class EnsembleModel:
             traj = np.empty((hi - lo, N, 3, S)) if return_trajectories else None
             final = np.empty((hi - lo, N, 3))
         sums = np.zeros((S, 4))
-        time = field = None
+        state = dict(time=None, field=None, traj=traj, final=final, sums=sums)
+        pending = []
+
+        def consume(out, idx):
+            if state['time'] is None:
+                state['time'], state['field'] = out['time'], out['field']
+            if single:
+                state['traj'], state['final'], state['sums'] = out['trajectories'], out['final'], out['sums']
+            else:
+                if return_trajectories:
+                    state['traj'][idx - lo] = out['trajectories']
+                state['final'][idx - lo] = out['final']
+                state['sums'] += out['sums']
+            stats.append(out['stats'])
+
+        def flush():
+            for plan, _ in pending:
+                plan.run()
+            for plan, idx in pending:
+                st = plan.sync()
+                out = plan.fetch()
+                out['stats'] = st
+                consume(out, idx)
+            del pending[:]
         stats = []
         for idx in groups:
             first = int(idx[0])
@@ -184,24 +208,23 @@ class EnsembleModel:
             temperature = params['temperature']
             if N == 1 and 'temperature' in self._overrides:
                 temperature = np.asarray([self._overrides['temperature'][i] for i in idx], dtype=np.float64)
-            out = core.simulate_ensemble(
-                radius, params['anisotropy'], member_array('anisotropy_axis'),
-                member_array('magnetisation_direction'), params['location'], params['magnetisation'],
-                params['damping'], temperature, renorm, interactions, implicit_solve, time_step,
-                end_time, S, seeds[lo:hi] if single else seeds[idx], params['field_shape'],
-                params['field_amplitude'], params['field_frequency'], implicit_tol, device=device,
-                stream_offset=int(stream_offset) + first, return_trajectories=return_trajectories,
-                return_sums=True, return_final=True, gauss=gauss, devices=devices, implicit_newton=implicit_newton)
-            if time is None:
-                time, field = out['time'], out['field']
-            if single:
-                traj, final, sums = out['trajectories'], out['final'], out['sums']
+            args = (radius, params['anisotropy'], member_array('anisotropy_axis'),
+                    member_array('magnetisation_direction'), params['location'], params['magnetisation'],
+                    params['damping'], temperature, renorm, interactions, implicit_solve, time_step,
+                    end_time, S, seeds[lo:hi] if single else seeds[idx], params['field_shape'],
+                    params['field_amplitude'], params['field_frequency'], implicit_tol)
+            kwargs = dict(device=device, stream_offset=int(stream_offset) + first, return_trajectories=return_trajectories,
+                          return_sums=True, return_final=True, gauss=gauss, implicit_newton=implicit_newton)
+            if single or devices is not None:
+                consume(core.simulate_ensemble(*args, devices=devices, **kwargs), idx)
             else:
-                if return_trajectories:
-                    traj[idx - lo] = out['trajectories']
-                final[idx - lo] = out['final']
-                sums += out['sums']
-            stats.append(out['stats'])
+                # several parameter groups: one plan (own CUDA stream) per group, all enqueued before the first is waited
+                # for, so that the groups' kernels — each usually far too small to fill the GPU — run concurrently
+                pending.append((core.EnsemblePlan(*args, **kwargs), idx))
+                if len(pending) >= _MAX_CONCURRENT_PLANS:
+                    flush()
+        flush()
+        time, field, traj, final, sums = state['time'], state['field'], state['traj'], state['final'], state['sums']
         if shard is not None:
             from .sharding import allreduce_sums
             allreduce_sums(sums)

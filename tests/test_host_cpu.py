@@ -230,7 +230,25 @@ def test_ensemble_model_seeds_and_grouping(monkeypatch):
                 'trajectories': np.ones((n, 2, 3, S)) * T, 'sums': np.ones((S, 4)) * n, 'final': np.ones((n, 2, 3)) * T,
                 'stats': {}}
     monkeypatch.setattr(model_mod.core, 'simulate_ensemble', fake)
+
+    class FakePlan:   # several parameter groups run as concurrent plans: every plan is enqueued before the first sync
+        events = []
+
+        def __init__(self, *args, **kw):
+            self.out = fake(*args, **kw)
+
+        def run(self):
+            FakePlan.events.append('run')
+
+        def sync(self):
+            FakePlan.events.append('sync')
+            return {'kernel': 'fake'}
+
+        def fetch(self):
+            return dict(self.out)
+    monkeypatch.setattr(model_mod.core, 'EnsemblePlan', FakePlan)
     res = ens.simulate(1e-9, 1e-12, 5, random_state=42, implicit_solve=False, n_jobs=8)
+    assert FakePlan.events == ['run'] * 3 + ['sync'] * 3
     # seeds exactly as magpy/model.py:202-203
     np.random.seed(42)
     want = np.random.randint(np.iinfo(np.int32).max, size=R)

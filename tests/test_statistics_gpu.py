@@ -327,3 +327,32 @@ def test_zero_temperature_relaxation_closed_form(orc, core, N, implicit):
     assert np.abs(mz - exact).max() < (2e-5 if not implicit else 2e-4)
     assert np.abs(np.linalg.norm(out['trajectories'], axis=2) / c.Ms - 1).max() < 1e-5
     assert out['stats']['newton_failures'] == 0
+
+
+def test_parameter_groups_run_concurrently_and_match_blocking_calls(core):
+    """An ensemble whose members differ in a parameter that cannot ride on a per-member array (here the field
+    amplitude: a hysteresis sweep) is split into groups of equal parameters; the groups run as concurrent plans.  Every
+    member must come out exactly as from a blocking call for its group alone, whatever the number of plans in flight."""
+    import magpy_b200 as mp
+    from magpy_b200 import model as model_mod
+    R, groups = 240, 12
+    amps = np.repeat(np.linspace(5e3, 2.5e4, groups), R // groups)
+    base = mp.Model([8e-9], [4e4], [[0, 0, 1.0]], [[0, 0, 1.0]], [[0, 0, 0.0]], 4e5, 0.1, 300.0, field_shape='sine',
+                    field_frequency=1e9, field_amplitude=1e4)
+    ens = mp.EnsembleModel(R, base, field_amplitude=list(amps))
+    res = ens.simulate(2e-9, 1e-13, 21, 7, implicit_solve=False)
+    assert len(res.stats) == groups
+    old = model_mod._MAX_CONCURRENT_PLANS
+    try:
+        model_mod._MAX_CONCURRENT_PLANS = 1          # one plan at a time: the blocking order
+        res1 = ens.simulate(2e-9, 1e-13, 21, 7, implicit_solve=False)
+    finally:
+        model_mod._MAX_CONCURRENT_PLANS = old
+    assert np.array_equal(res.final_state_array(), res1.final_state_array())
+    assert np.allclose(res.ensemble_magnetisation(), res1.ensemble_magnetisation(), rtol=1e-13, atol=0)
+    seeds = ens._member_seeds(7)
+    idx = np.arange(3 * (R // groups), 4 * (R // groups))      # the fourth group through the plain blocking entry point
+    out = core.simulate_ensemble([8e-9], [4e4], [[0, 0, 1.0]], [[0, 0, 1.0]], [[0, 0, 0.0]], 4e5, 0.1, 300.0, False, True, False,
+                                 1e-13, 2e-9, 21, seeds[idx], field_shape='sine', field_amplitude=float(amps[idx[0]]),
+                                 field_frequency=1e9, stream_offset=int(idx[0]))
+    assert np.array_equal(out['final'], res.final_state_array()[idx])
