@@ -167,6 +167,7 @@ class EnsembleModel:
             final = np.empty((hi - lo, N, 3))
         sums = np.zeros((S, 4))
         state = dict(time=None, field=None, traj=traj, final=final, sums=sums)
+        group_fields, group_of = [], np.zeros(hi - lo, dtype=np.int64)   # the applied field each member saw
         pending = []
 
         def consume(out, idx):
@@ -179,6 +180,8 @@ class EnsembleModel:
                     state['traj'][idx - lo] = out['trajectories']
                 state['final'][idx - lo] = out['final']
                 state['sums'] += out['sums']
+                group_of[idx - lo] = len(group_fields)
+                group_fields.append(out['field'])
             stats.append(out['stats'])
 
         def flush():
@@ -228,7 +231,11 @@ class EnsembleModel:
         if shard is not None:
             from .sharding import allreduce_sums
             allreduce_sums(sums)
-        return EnsembleResults.from_arrays(time, field, R, trajectories=traj, sums=sums, final=final, stats=stats)
+        member_fields = None
+        if len(group_fields) > 1 and any(not np.array_equal(f, group_fields[0]) for f in group_fields[1:]):
+            member_fields = (np.stack(group_fields), group_of)   # members see different fields: keep each one's own
+        return EnsembleResults.from_arrays(time, field, R, trajectories=traj, sums=sums, final=final, stats=stats,
+                                           member_fields=member_fields)
 
 
 class DOModel:

@@ -72,9 +72,13 @@ def load_results(fname):
 
 
 class _LazyResults:
-    """Sequence of per-member ``Results`` views over one [R, N, 3, S] array."""
-    def __init__(self, time, field, traj):
+    """Sequence of per-member ``Results`` views over one [R, N, 3, S] array.  `member_fields` = (fields [G, S],
+    group index of every member [R]) when the members do not all see the same applied field (an ensemble whose
+    members differ in field amplitude / frequency / shape): member i then reports its own field, as the reference's
+    per-member ``Results`` do."""
+    def __init__(self, time, field, traj, member_fields=None):
         self._time, self._field, self._traj = time, field, traj
+        self._member_fields = member_fields
 
     def __len__(self):
         return self._traj.shape[0]
@@ -88,7 +92,11 @@ class _LazyResults:
             raise IndexError(i)
         block = self._traj[i]
         N = block.shape[0]
-        return Results(self._time, self._field,
+        field = self._field
+        if self._member_fields is not None:
+            fields, group_of = self._member_fields
+            field = fields[group_of[i]]
+        return Results(self._time, field,
                        {p: block[p, 0] for p in range(N)},
                        {p: block[p, 1] for p in range(N)},
                        {p: block[p, 2] for p in range(N)}, N)
@@ -114,7 +122,7 @@ class EnsembleResults:
         self.stats = None
 
     @classmethod
-    def from_arrays(cls, time, field, n_members, trajectories=None, sums=None, final=None, stats=None):
+    def from_arrays(cls, time, field, n_members, trajectories=None, sums=None, final=None, stats=None, member_fields=None):
         self = cls.__new__(cls)
         self.time = time
         self.field = field
@@ -123,7 +131,7 @@ class EnsembleResults:
         self._final = final
         self._n_members = int(n_members)
         self.stats = stats
-        self.results = _LazyResults(time, field, trajectories) if trajectories is not None else None
+        self.results = _LazyResults(time, field, trajectories, member_fields) if trajectories is not None else None
         return self
 
     def __len__(self):

@@ -262,6 +262,23 @@ def test_ensemble_model_seeds_and_grouping(monkeypatch):
     assert np.allclose(res.ensemble_magnetisation(), 1.0)
     with pytest.raises(TypeError):
         mp.EnsembleModel(3, base, no_such_parameter=[1, 2, 3])
+    assert res.results[0].field is res.field            # all groups saw the same field: one shared array
+    # members that differ in the applied field keep their own field in their per-member Results (magpy/results.py:6-92)
+    def fake_amp(radius, anisotropy, axis, m0, location, Ms, alpha, T, renorm, inter, impl, dt, t_end, S, seeds, shape,
+                 H0, f, tol, **kw):
+        out = fake(radius, anisotropy, axis, m0, location, Ms, alpha, T, renorm, inter, impl, dt, t_end, S, seeds, shape, H0, f,
+                   tol, **kw)
+        out['field'] = np.full(S, H0)
+        return out
+
+    class FakePlanAmp(FakePlan):
+        def __init__(self, *args, **kw):
+            self.out = fake_amp(*args, **kw)
+    monkeypatch.setattr(model_mod.core, 'EnsemblePlan', FakePlanAmp)
+    amps = [1e3, 2e3, 1e3, 3e3, 2e3, 1e3, 1e3]
+    res_a = mp.EnsembleModel(R, base, field_amplitude=amps).simulate(1e-9, 1e-12, 5, random_state=42, implicit_solve=False)
+    assert [float(res_a.results[i].field[0]) for i in range(R)] == amps
+    assert np.array_equal(res_a.field, np.full(5, 1e3))   # the ensemble-level field is the first member's (magpy/results.py:114)
 
 
 def test_geometry_helpers():
