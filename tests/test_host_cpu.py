@@ -390,3 +390,45 @@ def test_bench_reference_arm_contract(workload):
     assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['gpu_launches'] == 0
     assert line['config']['workload'].startswith(workload.upper())
+
+
+def test_single_particle_radius_and_temperature_overrides_are_one_call(monkeypatch):
+    """Single-particle members that differ in radius and temperature go to the device as per-member arrays in ONE call
+    (radius (R, 1), temperature (R,)); for clusters the same overrides still split the ensemble by value."""
+    import magpy_b200 as mp
+    from magpy_b200 import model as model_mod
+    calls = []
+
+    def fake(radius, anisotropy, axis, m0, location, Ms, alpha, T, renorm, inter, impl, dt, t_end, S, seeds, shape, H0, f, tol,
+             **kw):
+        calls.append(dict(radius=np.array(radius), T=np.array(T), n=len(seeds)))
+        n, N = len(seeds), np.asarray(anisotropy).size
+        return {'N': N, 'R': n, 'time': np.arange(S) * 1.0, 'field': np.zeros(S), 'trajectories': np.zeros((n, N, 3, S)),
+                'sums': np.zeros((S, 4)), 'final': np.zeros((n, N, 3)), 'stats': {}}
+
+    class FakePlan:
+        def __init__(self, *a, **kw):
+            self.out = fake(*a, **kw)
+
+        def run(self):
+            pass
+
+        def sync(self):
+            return {}
+
+        def fetch(self):
+            return dict(self.out)
+    monkeypatch.setattr(model_mod.core, 'simulate_ensemble', fake)
+    monkeypatch.setattr(model_mod.core, 'EnsemblePlan', FakePlan)
+    R = 6
+    radii = [np.array([r]) for r in (5e-9, 6e-9, 7e-9, 6e-9, 8e-9, 9e-9)]
+    temps = [300.0, 310.0, 300.0, 320.0, 330.0, 300.0]
+    single = mp.Model([7e-9], [4e4], [[0, 0, 1.0]], [[0, 0, 1.0]], [[0, 0, 0.0]], 4e5, 0.1, 300.0)
+    mp.EnsembleModel(R, single, radius=radii, temperature=temps).simulate(1e-9, 1e-12, 5, random_state=1, implicit_solve=False)
+    assert len(calls) == 1 and calls[0]['n'] == R
+    assert calls[0]['radius'].shape == (R, 1) and np.array_equal(calls[0]['radius'][:, 0], [r[0] for r in radii])
+    assert np.array_equal(calls[0]['T'], temps)
+    del calls[:]
+    dimer = mp.Model([7e-9, 7e-9], [1e5, 1e5], [[0, 0, 1.0]] * 2, [[0, 0, 1.0]] * 2, [[0, 0, 0], [0, 0, 9e-9]], 4e5, 0.1, 330.0)
+    mp.EnsembleModel(R, dimer, temperature=temps).simulate(1e-9, 1e-12, 5, random_state=1, implicit_solve=False)
+    assert sorted(int(c['n']) for c in calls) == [1, 1, 1, 3] and all(np.ndim(c['T']) == 0 for c in calls)
