@@ -9,9 +9,12 @@ alpha=0.1, easy axis and initial moment along z) under a sinusoidal applied fiel
 (f=300 kHz, H0=20 kA/m), explicit Heun, in-kernel Philox noise.  One bench "step" = one pass
 of the hot path over that batch: every realisation is advanced by 100,000 Heun steps
 (dt=1e-12 s, i.e. 1e-7 s of the field cycle) with 101 zero-order-hold samples and the fused
-ensemble reduction — 1e11 particle-steps per pass per GPU.  N>1: every rank integrates its own
-1M realisations with disjoint Philox member indices (weak scaling) and one NCCL all-reduce
-combines the [S][4] ensemble sums per pass.
+ensemble reduction — 1e11 particle-steps per pass.  N>1 (one process per GPU): the 1M realisations
+are shared out by member index (`--scaling strong`, the default: BASELINE's ensemble is 1M in total;
+`--scaling weak` gives every GPU 1M), every member keeps its global Philox index, and ONE
+ncclAllReduce — issued by libmagpy_b200 itself on the integration stream, no torch on this arm —
+combines the [S][4] ensemble sums per pass.  The other scaling mode is measured too
+(config.other_scaling_mode).
 
 value  : whole-job particle-steps/s with inputs resident in HBM, timed with CUDA events on the
          launching stream (max over ranks).
@@ -237,7 +240,7 @@ def reference_arm(args):
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD['name'], 'sample': sample},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -249,26 +252,54 @@ def reference_arm(args):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def _make_plan(core, arr, seeds, R_local, offset, device, comm, gauss='f32p', t_end=None):
+    w = WORKLOAD
+    return core.EnsemblePlan(arr['radius'], arr['anisotropy'], arr['axis'], arr['m0'], arr['location'], w['Ms'],
+                             w['alpha'], w['T'], False, True, False, w['dt'], t_end or w['t_end'], w['S'], seeds,
+                             field_shape=w['field_shape'], field_amplitude=w['H0'], field_frequency=w['f'],
+                             device=device, stream_offset=offset, return_trajectories=False,
+                             return_sums=True, return_final=True, gauss=gauss, comm=comm)
+
+
+def _timed_passes(plan, comm, passes):
+    """`passes` passes of the hot path; (device ms incl. the all-reduce, integrate-kernel ms, last stats), each the
+    max over ranks of the per-rank CUDA-event sums (events on the library's launch stream)."""
+    t_dev = t_int = 0.0
+    st = None
+    for _ in range(passes):
+        plan.run()          # integration kernels + ensemble reduction + ONE ncclAllReduce, all on the plan's stream
+        st = plan.sync()
+        t_dev += st['device_ms']
+        t_int += st['integrate_ms']
+    tt = np.array([t_dev, t_int])
+    if comm is not None:
+        comm.allreduce(tt, 'max')
+    return float(tt[0]), float(tt[1]), st
+
+
 def ours(args):
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     import magpy_b200 as mp
     from magpy_b200 import core
+    from magpy_b200.sharding import shard_bounds
 
     if core.device_count() == 0:
         raise RuntimeError('bench.py needs a CUDA device: magpy_b200 has no CPU fallback')
+    # one process per GPU; the library's own NCCL communicator (no torch anywhere on this arm)
+    comm = core.Comm.from_env(local_rank) if world > 1 else None
     w = WORKLOAD
-    R = w['R']
+    strong = args.scaling == 'strong'
+    R_total = w['R'] if strong else w['R'] * world
+    seeds_all = member_seeds(R_total, w['random_state'])
+    lo, hi = shard_bounds(R_total, world, rank)
+    R = hi - lo
     arr = workload_arrays(R)
-    seeds_all = member_seeds(R * world, w['random_state'])
-    seeds = seeds_all[rank * R:(rank + 1) * R]
+
+    def barrier():
+        if comm is not None:
+            comm.barrier()
 
     # roofline denominator: the best FP64 rate measured on this device in this run.  DFMA and DMMA are the same
     # datapath (scripts/micro/dmma.cu); the DMMA chain reaches the nominal rate, the DFMA chain ~8 % less.
@@ -276,106 +307,89 @@ def ours(args):
     dmma_tflops = core.fp64_mma_peak(local_rank)
     peak_tflops = max(dfma_tflops, dmma_tflops)
 
-    plan = core.EnsemblePlan(arr['radius'], arr['anisotropy'], arr['axis'], arr['m0'], arr['location'], w['Ms'],
-                             w['alpha'], w['T'], False, True, False, w['dt'], w['t_end'], w['S'], seeds,
-                             field_shape=w['field_shape'], field_amplitude=w['H0'], field_frequency=w['f'],
-                             device=local_rank, stream_offset=rank * R, return_trajectories=False,
-                             return_sums=True, return_final=True, gauss='f32p')
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    sums_t = None
-    if dist is not None:
-        sums_t = torch.zeros(w['S'] * 4, dtype=torch.float64, device='cuda')
-        ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def one_pass():
-        """One pass of the hot path; returns (device ms incl. all-reduce, integrate-kernel ms, stats)."""
-        plan.run()
-        st = plan.sync()
-        ms = st['device_ms']
-        if dist is not None:
-            # the plan's [S][4] sums live in device memory: all-reduce them in place over NCCL
-            ptr, n = plan.sums_device_ptr()
-            view = torch.as_tensor(_DevView(ptr, n), device='cuda')
-            ar0.record()
-            dist.all_reduce(view)
-            ar1.record()
-            torch.cuda.synchronize()
-            ms += ar0.elapsed_time(ar1)
-        return ms, st['integrate_ms'], st
-
-    for _ in range(max(args.warmup, 0)):
-        one_pass()
+    plan = _make_plan(core, arr, seeds_all[lo:hi], R, lo, local_rank, comm)
+    _timed_passes(plan, comm, max(args.warmup, 0))
     launches0 = plan.sync()['kernel_launches']
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    t_dev = t_int = 0.0
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        ms, ims, st = one_pass()
-        t_dev += ms
-        t_int += ims
+    t_dev, t_int, st = _timed_passes(plan, comm, args.steps)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     gpu_launches = st['kernel_launches'] - launches0
     n_steps = st['steps_per_member']
-    ps_per_pass = R * w['N'] * n_steps
-
+    ps_per_pass = R_total * w['N'] * n_steps          # whole job, all ranks
     ms_per_step = t_dev / args.steps
-    if dist is not None:
-        tt = torch.tensor([ms_per_step, t_int / args.steps], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_per_step, int_ms = float(tt[0]), float(tt[1])
-    else:
-        int_ms = t_int / args.steps
-    value = world * ps_per_pass / (ms_per_step * 1e-3)
+    int_ms = t_int / args.steps
+    value = ps_per_pass / (ms_per_step * 1e-3)
     out = plan.fetch()
-    mean_mz = float(out['sums'][-1, 2] / (R * world) / w['Ms'] / w['N'])   # the plan's sums were all-reduced in place
+    mean_mz = float(out['sums'][-1, 2] / R_total / w['Ms'] / w['N'])   # the plan's sums were all-reduced in place
+    variant = st.get('kernel_variant', 0)
     del plan
+
+    # the other scaling mode, for the record (N > 1 only; at N = 1 they coincide)
+    other = None
+    if world > 1:
+        R2 = w['R'] if strong else -(-w['R'] // world)
+        off2 = rank * R2
+        seeds2 = member_seeds(R2 * world, w['random_state'])[off2:off2 + R2]
+        plan2 = _make_plan(core, workload_arrays(R2), seeds2, R2, off2, local_rank, comm)
+        _timed_passes(plan2, comm, 1)
+        barrier()
+        k2 = max(1, min(args.steps, 3))
+        t2, _, st2 = _timed_passes(plan2, comm, k2)
+        other = {'scaling': 'weak' if strong else 'strong', 'realisations_per_gpu': R2, 'ms_per_step': t2 / k2,
+                 'value': R2 * world * w['N'] * st2['steps_per_member'] / (t2 / k2 * 1e-3), 'unit': UNIT}
+        del plan2
+
+    # the other Gaussian transforms of the Philox stream on the same workload (N = 1 run of the default workload only)
+    rng_rates = None
+    if world == 1 and w['N'] == 1:
+        rng_rates = {}
+        for g, frac in (('f32', 0.2), ('f64', 0.05)):
+            p3 = _make_plan(core, arr, seeds_all[lo:hi], R, lo, local_rank, None, gauss=g, t_end=w['t_end'] * frac)
+            p3.run(); p3.sync(); p3.run()
+            s3 = p3.sync()
+            rng_rates[g] = s3['particle_steps'] / (s3['integrate_ms'] * 1e-3)
+            del p3
 
     # end to end through the public API with host buffers (H2D + D2H inside the timed region)
     base = mp.Model(arr['radius'], arr['anisotropy'], arr['axis'], arr['m0'], arr['location'], w['Ms'], w['alpha'],
                     w['T'], field_shape=w['field_shape'], field_frequency=w['f'], field_amplitude=w['H0'])
-    ens = mp.EnsembleModel(R, base)
+    ens = mp.EnsembleModel(R_total, base)
+    shard = (rank, world) if world > 1 else None
     e2e_passes = max(1, min(args.steps, 2))
-    ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'] + rank, implicit_solve=False, device=local_rank,
-                 stream_offset=rank * R, return_trajectories=False)   # warm-up
+    ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'], implicit_solve=False, device=local_rank,
+                 return_trajectories=False, shard=shard, comm=comm)   # warm-up
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for i in range(e2e_passes):
-        res = ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'] + rank, implicit_solve=False,
-                           device=local_rank, stream_offset=rank * R, return_trajectories=False)
+        res = ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'], implicit_solve=False,
+                           device=local_rank, return_trajectories=False, shard=shard, comm=comm)
         h2d += sum(s['h2d_bytes'] for s in res.stats)
         d2h += sum(s['d2h_bytes'] for s in res.stats)
-        if dist is not None:
-            s_t = torch.from_numpy(res._sums).cuda()
-            dist.all_reduce(s_t)
-            res._sums[...] = s_t.cpu().numpy()
+        final_mz = float(res.ensemble_magnetisation()[-1])        # the step's result, read on the host
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_passes
-    if dist is not None:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt[0])
-    e2e_value = world * ps_per_pass / e2e_s
+    tt = np.array([(time.perf_counter() - t0) / e2e_passes, float(h2d), float(d2h)])
+    if comm is not None:
+        e2e_t = comm.allreduce(tt[:1].copy(), 'max')
+        tot = comm.allreduce(tt[1:].copy(), 'sum')
+        tt = np.concatenate([e2e_t, tot])
+    e2e_s, h2d, d2h = float(tt[0]), int(tt[1]), int(tt[2])
+    e2e_value = ps_per_pass / e2e_s
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return
 
     W_ALG = w_alg(w['N'])
-    achieved = W_ALG * ps_per_pass / (int_ms * 1e-3) / 1e12
+    # the dominant kernel of a rank processes that rank's share of the pass
+    achieved = W_ALG * (ps_per_pass / world) / (int_ms * 1e-3) / 1e12
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'heun_single_traffic.json')
-    if w['N'] == 1 and os.path.exists(prof):
+    if w['N'] == 1 and world == 1 and os.path.exists(prof):
         try:
             traffic = json.load(open(prof)).get('dram_bytes_per_launch')
         except Exception:
@@ -393,37 +407,39 @@ def ours(args):
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': w['name'], 'realisations_per_gpu': R, 'particles': w['N'], 'heun_steps_per_pass': n_steps,
-                   'samples': w['S'], 'rng': 'Philox4x32-10 + fp32 Box-Muller in kernel, one Philox block per two steps (gauss=f32p)',
+        'config': {'workload': w['name'], 'realisations_total': R_total, 'realisations_per_gpu': -(-R_total // world),
+                   'particles': w['N'], 'heun_steps_per_pass': n_steps, 'samples': w['S'],
+                   'rng': 'Philox4x32-10 + fp32 Box-Muller in kernel, one Philox block per two steps (gauss=f32p)',
+                   'rng_other_modes_particle_steps_per_s': rng_rates,
+                   'collective': 'one ncclAllReduce(sum, fp64) of the [S][4] ensemble sums per pass, issued by '
+                                 'libmagpy_b200 on the integration stream' if world > 1 else 'none (one GPU)',
                    'l2': 'state is register resident; no input is re-read between passes (0 B/step steady-state HBM '
                          'traffic), so no L2 flush applies',
-                   'timing': 'CUDA events on the launching stream, max over ranks',
+                   'timing': 'CUDA events on the launching stream (integration + reduction + all-reduce), max over ranks',
+                   'kernel_variant': 'heun_single min-blocks %s' % variant if w['N'] == 1 else None,
+                   'other_scaling_mode': other,
                    'mean_mz_over_Ms_at_end': mean_mz, 'wall_s_timed_region': wall},
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
                      'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': traffic,
                      'kernel': st['kernel'] + '_kernel', 'kernel_ms_per_launch': int_ms,
                      'algorithmic_flop_per_particle_step': W_ALG,
-                     'peak_dfma_chain': dfma_tflops, 'peak_dmma_chain': dmma_tflops,
+                     'peak_dfma_chain': dfma_tflops, 'peak_dmma_chain': dmma_tflops, 'sm_clock_mhz_max': max_mhz,
                      'peak_source': 'measured in this run: the larger of the library\'s register-resident DFMA-chain and '
-                                    'DMMA.8x8x4-chain kernels (one FP64 datapath); MEASURED_PEAKS.json has no fp64 figure'},
+                                    'DMMA.8x8x4-chain kernels (one FP64 datapath); MEASURED_PEAKS.json has no fp64 figure',
+                     'peak_recompute': 'fp64_peak_kernel: SMs x 8 CTAs x 128 threads, 8192 iterations of 64 independent '
+                                       'DFMA per thread -> flop = threads x 8192 x 64 x 2; fp64_mma_peak_kernel: SMs x 256 '
+                                       'threads, 4000 iterations of 48 DMMA.8x8x4 per warp -> flop = warps x 4000 x 48 x 512; '
+                                       'nominal = SMs x 4 x 16 lanes x 2 x clock'},
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d // e2e_passes,
-                'd2h_bytes_per_step': d2h // e2e_passes, 'api': 'EnsembleModel.simulate', 'passes': e2e_passes},
+                'd2h_bytes_per_step': d2h // e2e_passes, 'api': 'EnsembleModel.simulate', 'passes': e2e_passes,
+                'mean_mz_over_Ms_at_end': final_mz / w['Ms'] / w['N']},
         'gpu_launches': int(gpu_launches),
         'clocks': clocks,
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
-
-
-class _DevView:
-    """Minimal __cuda_array_interface__ wrapper so torch can all-reduce the plan's sums in place."""
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<f8', 'data': (ptr, False), 'version': 2,
-                                         'strides': None}
 
 
 def main():
@@ -434,6 +450,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS),
                     help='c3 (default): the configuration the BASELINE metric is quoted on; c4: 64-particle clusters')
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'],
+                    help='strong (default): the workload\'s realisations are shared out over the GPUs (BASELINE: 1M in '
+                         'total); weak: every GPU takes the full count.  The other mode is measured too and reported in '
+                         'config.other_scaling_mode')
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = WORKLOADS[args.workload]

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MAGPY_B200_ABI_VERSION 3
+#define MAGPY_B200_ABI_VERSION 4
 
 /* status codes */
 #define MAGPY_B200_OK 0
@@ -30,6 +30,7 @@ extern "C" {
 #define MAGPY_B200_ERR_NO_DEVICE 2 /* no usable CUDA device / bad device index          */
 #define MAGPY_B200_ERR_CUDA 3      /* CUDA runtime error                                */
 #define MAGPY_B200_ERR_NOMEM 4     /* request does not fit device or host memory        */
+#define MAGPY_B200_ERR_COMM 5      /* NCCL / rendezvous error of the multi-GPU path      */
 
 /* field shapes: same numbering as `enum field::options` (include/field.hpp:95-97)
  * and `cpdef enum options` (magpy/core.pyx:38-42). */
@@ -59,6 +60,9 @@ typedef struct magpy_b200_stats {
     uint64_t h2d_bytes;            /* host->device bytes copied by this call                */
     uint64_t d2h_bytes;            /* device->host bytes copied by this call                */
     uint64_t kernel_family;        /* MAGPY_B200_KERNEL_*: which integration kernel ran (ABI v3) */
+    uint64_t kernel_variant;       /* heun_single: resident CTAs per SM asked of the register allocator — 1 (free: 6
+                                      CTAs of 128 threads) or 7 (when the shard fits one wave of 7 per SM but not
+                                      one of 6); 0 for the other kernels (ABI v4)                             */
 } magpy_b200_stats;
 
 /* integration kernels (magpy_b200/csrc): reported in magpy_b200_stats.kernel_family */
@@ -76,6 +80,8 @@ typedef struct magpy_b200_stats {
  * axes and initial magnetisation — replaces the joblib fan-out of
  * `EnsembleModel.simulate` (magpy/model.py:159-208) + one
  * `simulation::full_dynamics` call per member (lib/simulation.cpp:476-624). */
+typedef struct magpy_b200_comm magpy_b200_comm; /* opaque: one rank of a one-process-per-GPU job (NCCL) */
+
 typedef struct magpy_b200_ensemble {
     uint32_t abi_version;            /* = MAGPY_B200_ABI_VERSION                              */
     int32_t device;                  /* CUDA device ordinal                                   */
@@ -135,6 +141,27 @@ typedef struct magpy_b200_ensemble {
     /* Per-member temperatures (ABI v3): NULL, or [R] temperatures in K that replace `temperature` member by member.
      * Single-particle ensembles only, for the same reason (the temperature enters through sigma_i alone). */
     const double* member_temperature;
+    /* ---- ABI v4 ---- */
+    /* Global member indices (NULL, or [R]): word 1 of the Philox counter of member r is member_index[r] instead of
+     * stream_offset + r, so that a member keeps its noise stream however the ensemble is cut into parameter groups,
+     * shards and devices (values < 2^32). */
+    const uint64_t* member_index;
+    /* Per-member material parameters of single-particle ensembles (N = 1), each NULL or [R]; they replace
+     * anisotropy[0] / damping / field_amplitude member by member — the reference's
+     * `EnsembleModel(N, base, anisotropy=[...], damping=[...], field_amplitude=[...])` (magpy/model.py:146-156) in ONE
+     * launch.  Anisotropy and damping change the member's reduced time scale (lib/simulation.cpp:514-520), so every
+     * thread carries its own dt, sigma, field scale and zero-order-hold schedule (lib/simulation.cpp:342-355 evaluated per
+     * member on the device in the same fp64 arithmetic).  Heun and implicit midpoint, field shapes constant and sine
+     * (anisotropy / damping) or any shape (field amplitude); gauss_mode F32_PACKED or injected increments. */
+    const double* member_anisotropy;
+    const double* member_damping;
+    const double* member_field_amplitude;
+    /* Multi-GPU (one process per GPU): when set, the [S][4] ensemble sums are all-reduced over the communicator
+     * (ncclAllReduce, sum, fp64, in place on the device buffer, enqueued on the plan's stream after the last
+     * integration kernel) before they are returned: out_sums then holds the sums over ALL ranks' members.  Every rank
+     * of the communicator must make the matching call.  Replaces the gathering of pickled Results from the joblib
+     * workers (magpy/model.py:204-207). */
+    magpy_b200_comm* comm;
 } magpy_b200_ensemble;
 #define MAGPY_B200_NEWTON_REFERENCE 0
 #define MAGPY_B200_NEWTON_EXACT 1
@@ -192,6 +219,28 @@ int magpy_b200_plan_fetch(magpy_b200_plan* plan, double* out_time, double* out_f
 /* device address of the [S][4] ensemble-sum buffer (for an in-place NCCL all-reduce) */
 int magpy_b200_plan_sums_device_ptr(magpy_b200_plan* plan, void** dptr, size_t* n_doubles);
 int magpy_b200_plan_destroy(magpy_b200_plan* plan);
+
+/* ---- multi-GPU: one process per GPU, one collective -----------------------------------------
+ * The path shards by member index with no data-path exchange (magpy/model.py:204-207: independent members); the only
+ * collective is ONE all-reduce (sum, fp64) of the [S][4] ensemble sums per pass, issued by the library through NCCL
+ * (loaded with dlopen on first use; no link-time dependency).  A communicator is built either from an id the caller
+ * distributes itself (magpy_b200_comm_unique_id on rank 0 -> any out-of-band channel -> magpy_b200_comm_create on every
+ * rank: ncclGetUniqueId / ncclCommInitRank), or from the launcher's environment (RANK, WORLD_SIZE, LOCAL_RANK,
+ * MASTER_ADDR, MASTER_PORT as set by torchrun): rank 0 serves the id over TCP on MASTER_PORT + 1
+ * (MAGPY_B200_COMM_PORT overrides).  device < 0 = LOCAL_RANK. */
+#define MAGPY_B200_COMM_ID_BYTES 128
+#define MAGPY_B200_COMM_SUM 0
+#define MAGPY_B200_COMM_MAX 1
+int magpy_b200_comm_unique_id(uint8_t id[MAGPY_B200_COMM_ID_BYTES]);
+int magpy_b200_comm_create(const uint8_t id[MAGPY_B200_COMM_ID_BYTES], int rank, int world_size, int device,
+                           magpy_b200_comm** comm);
+int magpy_b200_comm_create_from_env(int device, magpy_b200_comm** comm);
+int magpy_b200_comm_rank(const magpy_b200_comm* comm, int* rank, int* world_size);
+/* all-reduce of a small HOST array (staged through the device, ncclAllReduce): job-wide maxima of timings, ensemble
+ * sums accumulated on the host over several parameter groups */
+int magpy_b200_comm_allreduce(magpy_b200_comm* comm, double* host_values, size_t n, int op);
+int magpy_b200_comm_barrier(magpy_b200_comm* comm);
+int magpy_b200_comm_destroy(magpy_b200_comm* comm);
 
 /* ---- host helpers that mirror reference arithmetic ---------------------------------- */
 /* SI -> reduced units (lib/simulation.cpp:498-549): out[0]=V_av [1]=K_av [2]=H_k

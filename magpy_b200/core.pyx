@@ -47,6 +47,7 @@ cdef extern from "magpy_b200.h" nogil:
         uint64_t h2d_bytes
         uint64_t d2h_bytes
         uint64_t kernel_family
+        uint64_t kernel_variant
 
     ctypedef struct magpy_b200_ensemble:
         uint32_t abi_version
@@ -87,9 +88,26 @@ cdef extern from "magpy_b200.h" nogil:
         uint32_t implicit_newton
         uint64_t radius_stride
         const double* member_temperature
+        const uint64_t* member_index
+        const double* member_anisotropy
+        const double* member_damping
+        const double* member_field_amplitude
+        magpy_b200_comm* comm
 
     ctypedef struct magpy_b200_plan:
         pass
+
+    ctypedef struct magpy_b200_comm:
+        pass
+
+    int MAGPY_B200_ERR_COMM
+    int magpy_b200_comm_unique_id(unsigned char* id)
+    int magpy_b200_comm_create(const unsigned char* id, int rank, int world_size, int device, magpy_b200_comm** comm)
+    int magpy_b200_comm_create_from_env(int device, magpy_b200_comm** comm)
+    int magpy_b200_comm_rank(const magpy_b200_comm* comm, int* rank, int* world_size)
+    int magpy_b200_comm_allreduce(magpy_b200_comm* comm, double* host_values, size_t n, int op)
+    int magpy_b200_comm_barrier(magpy_b200_comm* comm)
+    int magpy_b200_comm_destroy(magpy_b200_comm* comm)
 
     int magpy_b200_abi_version()
     const char* magpy_b200_last_error()
@@ -136,6 +154,8 @@ cdef _raise(int rc):
         raise ValueError(msg)
     if rc == MAGPY_B200_ERR_NOMEM:
         raise MemoryError(msg)
+    if rc == MAGPY_B200_ERR_COMM:
+        raise ConnectionError(msg)
     raise RuntimeError(msg)
 
 
@@ -156,7 +176,90 @@ cdef dict _stats_dict(magpy_b200_stats* st):
         'h2d_bytes': st.h2d_bytes,
         'd2h_bytes': st.d2h_bytes,
         'kernel': _KERNEL_NAMES.get(st.kernel_family, 'unknown'),
+        'kernel_variant': st.kernel_variant,
     }
+
+
+cdef class Comm:
+    """One rank of a one-process-per-GPU job: the library's NCCL communicator (include/magpy_b200.h, multi-GPU section).
+
+    `Comm.from_env(device=-1)` follows the launcher's environment (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_ADDR,
+    MASTER_PORT — torchrun's contract); `Comm(id, rank, world_size, device)` takes an id from `Comm.unique_id()` that the
+    caller distributed itself.  Pass it as `comm=` to `simulate_ensemble` / `EnsemblePlan` /
+    `EnsembleModel.simulate(shard=...)`: the ensemble sums are then all-reduced on the device (ONE ncclAllReduce per
+    pass)."""
+    cdef magpy_b200_comm* c
+    cdef readonly int rank, world_size
+
+    def __cinit__(self):
+        self.c = NULL
+
+    def __init__(self, bytes id=None, int rank=0, int world_size=1, int device=0):
+        cdef const unsigned char* p = NULL
+        if id is not None:
+            if len(id) != 128:
+                raise ValueError('id must be the 128 bytes of Comm.unique_id()')
+            p = <const unsigned char*> id
+        cdef int rc
+        with nogil:
+            rc = magpy_b200_comm_create(p, rank, world_size, device, &self.c)
+        if rc != 0:
+            self.c = NULL
+            _raise(rc)
+        self.rank, self.world_size = rank, world_size
+
+    @staticmethod
+    def unique_id():
+        cdef unsigned char buf[128]
+        cdef int rc = magpy_b200_comm_unique_id(buf)
+        if rc != 0:
+            _raise(rc)
+        return bytes(buf[:128])
+
+    @staticmethod
+    def from_env(int device=-1):
+        cdef Comm self = Comm.__new__(Comm)
+        cdef int rc
+        with nogil:
+            rc = magpy_b200_comm_create_from_env(device, &self.c)
+        if rc != 0:
+            self.c = NULL
+            _raise(rc)
+        magpy_b200_comm_rank(self.c, &self.rank, &self.world_size)
+        return self
+
+    def __dealloc__(self):
+        if self.c != NULL:
+            magpy_b200_comm_destroy(self.c)
+            self.c = NULL
+
+    def allreduce(self, values, str op='sum'):
+        """In-place all-reduce of a small host float64 array over all ranks ('sum' or 'max')."""
+        cdef np.ndarray[double, ndim=1, mode='c'] v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+        cdef int code = {'sum': 0, 'max': 1}[op]
+        cdef size_t n = v.shape[0]
+        cdef int rc
+        cdef double* p = &v[0] if n else NULL
+        with nogil:
+            rc = magpy_b200_comm_allreduce(self.c, p, n, code)
+        if rc != 0:
+            _raise(rc)
+        out = np.asarray(values)
+        if isinstance(values, np.ndarray):
+            values[...] = v.reshape(values.shape)
+            return values
+        return v.reshape(out.shape)
+
+    def allreduce_sums(self, sums):
+        """Sum the [S][4] ensemble sums over all ranks (host array)."""
+        return self.allreduce(sums, 'sum')
+
+    def barrier(self):
+        cdef int rc
+        with nogil:
+            rc = magpy_b200_comm_barrier(self.c)
+        if rc != 0:
+            _raise(rc)
 
 
 cpdef get_KB():
@@ -259,28 +362,34 @@ cdef class _EnsembleArgs:
 
 
 cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
-                               double magnetisation, double damping, temperature, bint renorm,
+                               double magnetisation, damping, temperature, bint renorm,
                                bint interactions, bint use_implicit, double time_step, double end_time,
-                               max_samples, seeds, str field_shape, double field_amplitude,
+                               max_samples, seeds, str field_shape, field_amplitude,
                                double field_frequency, double implicit_tol, int device, stream_offset,
                                bint return_trajectories, bint return_sums, bint return_final, str gauss,
-                               injected_dw, int noise_coarsen_log2=0, str implicit_newton='reference'):
+                               injected_dw, int noise_coarsen_log2=0, str implicit_newton='reference',
+                               member_index=None, Comm comm=None):
     cdef _EnsembleArgs e = _EnsembleArgs()
     # radius: (N,) shared by all members, or (R, N) per member (single-particle ensembles: a size distribution)
     rad = np.ascontiguousarray(radius, dtype=np.float64)
     cdef bint member_radii = rad.ndim == 2
     cdef np.ndarray[double, ndim=1, mode='c'] c_radius = rad.reshape(-1)
     cdef size_t N = rad.shape[1] if member_radii else c_radius.shape[0]
-    cdef np.ndarray[double, ndim=1, mode='c'] c_anis = np.ascontiguousarray(anisotropy, dtype=np.float64).reshape(-1)
+    # anisotropy: (N,) shared, or (R, 1) per member (single-particle ensembles: an anisotropy distribution)
+    anis = np.ascontiguousarray(anisotropy, dtype=np.float64)
+    cdef bint member_anis = anis.ndim == 2
+    cdef np.ndarray[double, ndim=1, mode='c'] c_anis = anis.reshape(-1)
     cdef np.ndarray[double, ndim=2, mode='c'] c_loc = np.ascontiguousarray(location, dtype=np.float64).reshape(-1, 3)
-    if N == 0 or c_anis.shape[0] != N or c_loc.shape[0] != N:
-        raise ValueError('radius, anisotropy and location must describe the same number of particles')
     cdef np.ndarray[np.int64_t, ndim=1, mode='c'] c_seeds = np.ascontiguousarray(seeds, dtype=np.int64).reshape(-1)
     cdef size_t R = c_seeds.shape[0]
     if R == 0:
         raise ValueError('seeds must hold one seed per ensemble member')
+    if N == 0 or (not member_anis and c_anis.shape[0] != N) or c_loc.shape[0] != N:
+        raise ValueError('radius, anisotropy and location must describe the same number of particles')
     if member_radii and (rad.shape[0] != R or N != 1):
         raise ValueError('per-member radii need shape (R, 1): supported for single-particle ensembles only')
+    if member_anis and (anis.shape[0] != R or anis.shape[1] != 1 or N != 1):
+        raise ValueError('per-member anisotropy needs shape (R, 1): supported for single-particle ensembles only')
     if int(max_samples) < 2:
         raise ValueError('max_samples must be >= 2')
     cdef size_t S = int(max_samples)
@@ -302,13 +411,44 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
     e.a.radius = &c_radius[0]
     e.a.radius_stride = N if member_radii else 0
     e.a.anisotropy = &c_anis[0]
+    if member_anis:
+        e.a.member_anisotropy = &c_anis[0]
     e.a.location = &c_loc[0, 0]
     e.a.anisotropy_axis = &c_ax[0]
     e.a.axis_stride = 3 * N if ax.ndim == 3 else 0
     e.a.magnetisation_direction = &c_m0[0]
     e.a.m0_stride = 3 * N if m0.ndim == 3 else 0
     e.a.magnetisation = magnetisation
-    e.a.damping = damping
+    # damping / field_amplitude: scalars, or one value per member (single-particle ensembles)
+    cdef np.ndarray[double, ndim=1, mode='c'] c_damp, c_famp
+    if np.ndim(damping) == 0:
+        e.a.damping = float(damping)
+    else:
+        c_damp = np.ascontiguousarray(damping, dtype=np.float64).reshape(-1)
+        if c_damp.shape[0] != R or N != 1:
+            raise ValueError('per-member damping needs one value per member: supported for single-particle ensembles only')
+        e.keep.append(c_damp)
+        e.a.damping = c_damp[0]
+        e.a.member_damping = &c_damp[0]
+    if np.ndim(field_amplitude) == 0:
+        e.a.field_amplitude = float(field_amplitude)
+    else:
+        c_famp = np.ascontiguousarray(field_amplitude, dtype=np.float64).reshape(-1)
+        if c_famp.shape[0] != R or N != 1:
+            raise ValueError('per-member field amplitudes need one value per member: supported for single-particle ensembles only')
+        e.keep.append(c_famp)
+        e.a.field_amplitude = c_famp[0]
+        e.a.member_field_amplitude = &c_famp[0]
+    cdef np.ndarray[np.uint64_t, ndim=1, mode='c'] c_midx
+    if member_index is not None:
+        c_midx = np.ascontiguousarray(member_index, dtype=np.uint64).reshape(-1)
+        if c_midx.shape[0] != R:
+            raise ValueError('member_index must hold one global index per member')
+        e.keep.append(c_midx)
+        e.a.member_index = <const uint64_t*> &c_midx[0]
+    if comm is not None:
+        e.keep.append(comm)
+        e.a.comm = comm.c
     # temperature: a scalar, or one value per member (single-particle ensembles: a temperature sweep in one launch)
     cdef np.ndarray[double, ndim=1, mode='c'] c_temp
     if np.ndim(temperature) == 0:
@@ -328,7 +468,6 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
     e.a.end_time = end_time
     e.a.max_samples = S
     e.a.field_shape = _FIELD_LOOKUP[field_shape]
-    e.a.field_amplitude = field_amplitude
     e.a.field_frequency = field_frequency
     e.a.seeds = <const int64_t*> &c_seeds[0]
     e.a.stream_offset = int(stream_offset)
@@ -370,12 +509,12 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
 
 
 def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
-                      double magnetisation, double damping, temperature, bint renorm, bint interactions,
+                      double magnetisation, damping, temperature, bint renorm, bint interactions,
                       bint use_implicit, double time_step, double end_time, max_samples, seeds,
-                      str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
+                      str field_shape='constant', field_amplitude=0.0, double field_frequency=0.0,
                       double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=True,
                       bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None, devices=None,
-                      int noise_coarsen_log2=0, str implicit_newton='reference'):
+                      int noise_coarsen_log2=0, str implicit_newton='reference', member_index=None, Comm comm=None):
     """Integrate R = len(seeds) independent members of one cluster in a single call.
 
     `devices` (list of CUDA ordinals, or 'all') shards the members over several GPUs of this box from this one
@@ -385,7 +524,10 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
     normalised sum of the 2^L increments the L = 0 stream gives to steps s 2^L ... (s+1) 2^L - 1, so runs with
     time_step * 2^L see the same Brownian paths (convergence studies, test/convergence/task5.cpp:150-158).
 
-    `anisotropy_axis` and `magnetisation_direction` are (N,3) (shared) or (R,N,3).
+    `anisotropy_axis` and `magnetisation_direction` are (N,3) (shared) or (R,N,3).  Single-particle ensembles also
+    take per-member `radius` (R,1), `anisotropy` (R,1), `temperature` (R,), `damping` (R,) and `field_amplitude` (R,).
+    `member_index` (R,) gives the members' global indices (word 1 of their Philox counters) when they are not the
+    contiguous range starting at `stream_offset`.  `comm` (a `Comm`) all-reduces the sums over all ranks on the device.
     Returns a dict with 'time' [S], 'field' [S], 'trajectories' [R,N,3,S] | None,
     'sums' [S,4] | None (sum over members of cluster Mx,My,Mz and Mz^2), 'final' [R,N,3] | None
     and 'stats'.  `injected_dw` (R, steps, 3N) replaces the Philox stream by caller-supplied
@@ -394,7 +536,8 @@ def simulate_ensemble(radius, anisotropy, anisotropy_axis, magnetisation_directi
                                        magnetisation, damping, temperature, renorm, interactions, use_implicit,
                                        time_step, end_time, max_samples, seeds, field_shape, field_amplitude,
                                        field_frequency, implicit_tol, device, stream_offset, return_trajectories,
-                                       return_sums, return_final, gauss, injected_dw, noise_coarsen_log2, implicit_newton)
+                                       return_sums, return_final, gauss, injected_dw, noise_coarsen_log2, implicit_newton,
+                                       member_index, comm)
     cdef magpy_b200_stats st
     cdef int rc
     cdef np.ndarray[int, ndim=1, mode='c'] c_dev
@@ -432,17 +575,17 @@ cdef class EnsemblePlan:
         self.plan = NULL
 
     def __init__(self, radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
-                 double magnetisation, double damping, temperature, bint renorm, bint interactions,
+                 double magnetisation, damping, temperature, bint renorm, bint interactions,
                  bint use_implicit, double time_step, double end_time, max_samples, seeds,
-                 str field_shape='constant', double field_amplitude=0.0, double field_frequency=0.0,
+                 str field_shape='constant', field_amplitude=0.0, double field_frequency=0.0,
                  double implicit_tol=1e-9, int device=0, stream_offset=0, bint return_trajectories=False,
                  bint return_sums=True, bint return_final=True, str gauss='f32p', injected_dw=None,
-                 str implicit_newton='reference'):
+                 str implicit_newton='reference', member_index=None, Comm comm=None):
         self.e = _build_args(radius, anisotropy, anisotropy_axis, magnetisation_direction, location,
                              magnetisation, damping, temperature, renorm, interactions, use_implicit,
                              time_step, end_time, max_samples, seeds, field_shape, field_amplitude,
                              field_frequency, implicit_tol, device, stream_offset, return_trajectories,
-                             return_sums, return_final, gauss, injected_dw, 0, implicit_newton)
+                             return_sums, return_final, gauss, injected_dw, 0, implicit_newton, member_index, comm)
         cdef int rc
         with nogil:
             rc = magpy_b200_plan_create(&self.e.a, &self.plan)

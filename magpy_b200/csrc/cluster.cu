@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(512) heun_cluster_kernel(const __grid_constant
     const double alpha = P.alpha, dt = P.dt;
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const uint32_t member = member_id(P, r);
     const bool renorm = P.renorm != 0, inter = P.interactions != 0;
     // consume the packed noise stream two steps per Philox block when few particles are owned; with many
     // owned particles the dipolar sum dwarfs the generator and the carry registers are worth more
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
     const double alpha = P.alpha, dt = P.dt, clampA = P.clampA, sqrt_dt = P.sqrt_dt;
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const uint32_t member = member_id(P, r);
     const bool renorm = P.renorm != 0, exact = P.newton_exact != 0;
     NewtonCount nc{0ull, 0ull, 0ull};
 

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
                     for (int q = 0; q < NQ; ++q) {
                         const uint64_t rq = member(q), seed = (uint64_t)__ldg(P.seeds + rq);
                         float g6[6];
-                        philox_gauss6_f32((uint32_t)seed, (uint32_t)(seed >> 32), j >> 1, pid, (uint32_t)(rq + P.stream_offset),
+                        philox_gauss6_f32((uint32_t)seed, (uint32_t)(seed >> 32), j >> 1, pid, member_id(P, rq),
                                           bm, g6);
                         cw[q] = odd ? Inc{g6[3], g6[4], g6[5]} : Inc{g6[0], g6[1], g6[2]};
                         carry[q][0] = g6[3]; carry[q][1] = g6[4]; carry[q][2] = g6[5];
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(512, 1) heun_cluster_mma_kernel(const __grid_c
                 for (int q = 0; q < NQ; ++q) {
                     const uint64_t rq = member(q), seed = (uint64_t)__ldg(P.seeds + rq);
                     const V3 w = draw_scaled<NOISE>(P, (uint32_t)seed, (uint32_t)(seed >> 32), j, pid,
-                                                    (uint32_t)(rq + P.stream_offset), rq, csig, bm);
+                                                    member_id(P, rq), rq, csig, bm);
                     cw[q] = Inc{w.x, w.y, w.z};
                 }
             }

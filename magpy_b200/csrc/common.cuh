@@ -56,6 +56,7 @@ struct RunParams {
     uint64_t axis_cs, axis_rs;  // component stride, member stride
     const int64_t* seeds;       // [R]
     uint64_t stream_offset;
+    const uint32_t* member_idx; // [R] global member index of the Philox counter, or nullptr: stream_offset + r
     uint32_t philox_m0, philox_m1;  // the two Philox multipliers, passed at run time for the split multiply of rng.cuh
     uint32_t coarsen_log2;      // NOISE_PHILOX_COARSE: step s sums the packed stream's fine steps s 2^L .. (s+1) 2^L - 1
     double* state;              // [n][R]
@@ -77,6 +78,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Philox counter word 1: the member's GLOBAL index in the ensemble — does not depend on how the ensemble is cut into
+// parameter groups, shards or devices (explicit list), or stream_offset + local index for a contiguous slice
+__device__ __forceinline__ uint32_t member_id(const RunParams& P, uint64_t r) {
+    return P.member_idx ? __ldg(P.member_idx + r) : (uint32_t)(r + P.stream_offset);
 }
 
 // unit-variance draws (implicit kernels clamp them before scaling, lib/integrators.cpp:598-602)

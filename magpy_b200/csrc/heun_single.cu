@@ -45,12 +45,11 @@ __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V
 #ifndef MB_PHILOX_SPLIT
 #define MB_PHILOX_SPLIT 0   // leading Philox rounds whose wide multiplies are issued as IMAD.HI + IMAD (tuning knob, rng.cuh)
 #endif
-#ifndef MB_K1_MIN_BLOCKS
-#define MB_K1_MIN_BLOCKS 1   // resident CTAs per SM the register allocation must allow (tuning knob)
-#endif
-
-template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool RENORM>
-__global__ void __launch_bounds__(SINGLE_THREADS, MB_K1_MIN_BLOCKS) heun_single_kernel(const __grid_constant__ RunParams P) {
+// MINB = resident CTAs per SM the register allocation must allow.  1: ptxas is free (76 registers, 6 CTAs = 24 warps
+// per SM); 7: at most 72 registers (66 used, no spills).  The host picks 7 when the shard fits in one wave of 7 CTAs per
+// SM but not in one of 6 (magpy_b200.cu: choose_k1_variant; measured in profiles/r02_probe_k1_variants.log).
+template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool RENORM, int MINB>
+__global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
     const bool live = r_raw < P.R;
@@ -67,7 +66,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1_MIN_BLOCKS) heun_single_
     const float bm_scale = scale_to_bm(c);
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const uint32_t member = member_id(P, r);
 
     // one Heun step from the scaled increment cw; `tp` = this step's entry of the field table
     auto advance = [&](const V3& cw, const double2* tp) {
@@ -148,34 +147,57 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1_MIN_BLOCKS) heun_single_
     }
 }
 
-template <int NOISE, bool TAB, bool AXIS_Z>
+template <int NOISE, bool TAB, bool AXIS_Z, int MINB>
 static void launch_hs2(bool renorm, dim3 g, dim3 b, cudaStream_t s, const RunParams& P) {
-    if (renorm) heun_single_kernel<NOISE, TAB, AXIS_Z, true><<<g, b, 0, s>>>(P);
-    else heun_single_kernel<NOISE, TAB, AXIS_Z, false><<<g, b, 0, s>>>(P);
+    if (renorm) heun_single_kernel<NOISE, TAB, AXIS_Z, true, MINB><<<g, b, 0, s>>>(P);
+    else heun_single_kernel<NOISE, TAB, AXIS_Z, false, MINB><<<g, b, 0, s>>>(P);
 }
 
-template <int NOISE>
+template <int NOISE, int MINB>
 static void launch_hs(bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
     const dim3 g(grid), b(SINGLE_THREADS);
     const bool renorm = P.renorm != 0;
     if (tab) {
-        if (axis_z) launch_hs2<NOISE, true, true>(renorm, g, b, s, P);
-        else launch_hs2<NOISE, true, false>(renorm, g, b, s, P);
+        if (axis_z) launch_hs2<NOISE, true, true, MINB>(renorm, g, b, s, P);
+        else launch_hs2<NOISE, true, false, MINB>(renorm, g, b, s, P);
     } else {
-        if (axis_z) launch_hs2<NOISE, false, true>(renorm, g, b, s, P);
-        else launch_hs2<NOISE, false, false>(renorm, g, b, s, P);
+        if (axis_z) launch_hs2<NOISE, false, true, MINB>(renorm, g, b, s, P);
+        else launch_hs2<NOISE, false, false, MINB>(renorm, g, b, s, P);
     }
 }
 
-cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
+// min_blocks = 1 or 7 (production noise mode only; the other modes have the one free-allocation instantiation)
+cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, int min_blocks, unsigned grid, cudaStream_t s,
+                               const RunParams& P) {
     switch (noise) {
-        case NOISE_PHILOX_F32: launch_hs<NOISE_PHILOX_F32>(tab, axis_z, grid, s, P); break;
-        case NOISE_PHILOX_F64: launch_hs<NOISE_PHILOX_F64>(tab, axis_z, grid, s, P); break;
-        case NOISE_INJECTED: launch_hs<NOISE_INJECTED>(tab, axis_z, grid, s, P); break;
-        case NOISE_PHILOX_COARSE: launch_hs<NOISE_PHILOX_COARSE>(tab, axis_z, grid, s, P); break;
-        default: launch_hs<NOISE_PHILOX_PACKED>(tab, axis_z, grid, s, P); break;
+        case NOISE_PHILOX_F32: launch_hs<NOISE_PHILOX_F32, 1>(tab, axis_z, grid, s, P); break;
+        case NOISE_PHILOX_F64: launch_hs<NOISE_PHILOX_F64, 1>(tab, axis_z, grid, s, P); break;
+        case NOISE_INJECTED: launch_hs<NOISE_INJECTED, 1>(tab, axis_z, grid, s, P); break;
+        case NOISE_PHILOX_COARSE: launch_hs<NOISE_PHILOX_COARSE, 1>(tab, axis_z, grid, s, P); break;
+        default:
+            if (min_blocks == 7) launch_hs<NOISE_PHILOX_PACKED, 7>(tab, axis_z, grid, s, P);
+            else launch_hs<NOISE_PHILOX_PACKED, 1>(tab, axis_z, grid, s, P);
+            break;
     }
     return cudaGetLastError();
+}
+
+// resident CTAs per SM of the production instantiation <PACKED, tab, axis_z, renorm, min_blocks> on the current device
+int heun_single_resident_ctas(bool tab, bool axis_z, bool renorm, int min_blocks) {
+    int n = 0;
+    auto q = [&](auto kernel) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, SINGLE_THREADS, 0); };
+#define MB_Q(T, A, RN) \
+    (min_blocks == 7 ? q(heun_single_kernel<NOISE_PHILOX_PACKED, T, A, RN, 7>) \
+                     : q(heun_single_kernel<NOISE_PHILOX_PACKED, T, A, RN, 1>))
+    if (tab) {
+        if (axis_z) { if (renorm) MB_Q(true, true, true); else MB_Q(true, true, false); }
+        else { if (renorm) MB_Q(true, false, true); else MB_Q(true, false, false); }
+    } else {
+        if (axis_z) { if (renorm) MB_Q(false, true, true); else MB_Q(false, true, false); }
+        else { if (renorm) MB_Q(false, false, true); else MB_Q(false, false, false); }
+    }
+#undef MB_Q
+    return n;
 }
 
 }  // namespace mb

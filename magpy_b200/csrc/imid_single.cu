@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
     const double kred = P.k_red[0], sr = P.sig[r * P.sig_rs];   // per-member sigma when the radii differ
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const uint32_t member = member_id(P, r);
     const bool renorm = P.renorm != 0;
     NewtonCount nc{0ull, 0ull, 0ull};
 

@@ -9,7 +9,10 @@ namespace mb {
 struct RunParams;
 
 // noise: NOISE_PHILOX_F32 | NOISE_PHILOX_F64 | NOISE_INJECTED | NOISE_PHILOX_PACKED; tab: applied field from field_tab
-cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P);
+// min_blocks: register-allocation variant of the production (packed-noise) instantiation: 1 (free) or 7 CTAs per SM
+cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, int min_blocks, unsigned grid, cudaStream_t s,
+                               const RunParams& P);
+int heun_single_resident_ctas(bool tab, bool axis_z, bool renorm, int min_blocks);
 cudaError_t launch_imid_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P);
 cudaError_t launch_heun_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
 cudaError_t launch_imid_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);

@@ -18,13 +18,9 @@
 #include "../../include/magpy_b200.h"
 #include "common.cuh"
 #include "launch.h"
+#include "host_util.h"
 
-namespace {
-
-// include/constants.hpp:10-12, digit for digit (MU0 is the reference's truncated value)
-constexpr double kKB = 1.38064852e-23;
-constexpr double kMU0 = 1.25663706e-6;
-constexpr double kGYROMAG = 1.76086e11;
+namespace mbh {
 
 thread_local std::string g_error;
 
@@ -38,14 +34,6 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define CU_TRY(expr)                                                                                  \
-    do {                                                                                              \
-        cudaError_t e__ = (expr);                                                                     \
-        if (e__ != cudaSuccess)                                                                       \
-            return fail(e__ == cudaErrorMemoryAllocation ? MAGPY_B200_ERR_NOMEM : MAGPY_B200_ERR_CUDA, \
-                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);  \
-    } while (0)
-
 int select_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -56,9 +44,30 @@ int select_device(int device) {
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
     if (device < 0 || device >= n) return fail(MAGPY_B200_ERR_NO_DEVICE, "device %d out of range [0,%d)", device, n);
-    CU_TRY(cudaSetDevice(device));
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(MAGPY_B200_ERR_CUDA, "cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
     return MAGPY_B200_OK;
 }
+
+}  // namespace mbh
+
+namespace {
+
+// include/constants.hpp:10-12, digit for digit (MU0 is the reference's truncated value)
+constexpr double kKB = 1.38064852e-23;
+constexpr double kMU0 = 1.25663706e-6;
+constexpr double kGYROMAG = 1.76086e11;
+
+using mbh::fail;
+using mbh::select_device;
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(e__ == cudaErrorMemoryAllocation ? MAGPY_B200_ERR_NOMEM : MAGPY_B200_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);  \
+    } while (0)
 
 // ---- reference host arithmetic --------------------------------------------------------
 struct Reduced {
@@ -193,6 +202,7 @@ struct magpy_b200_plan {
     int layout = 0;        // Heun cluster kernel: see cluster.cu
     bool use_table = false;
     bool axis_z = false;   // N = 1 and one shared easy axis exactly along +z: specialised Heun kernel
+    int k1_min_blocks = 1; // K1: register-allocation variant (resident CTAs per SM asked of ptxas), see choose_k1_variant
     bool small = false;    // few particles: one thread per cluster, all moments in registers
     bool split = false;    //   ... implicit, one lane per particle (imid_split_kernel)
     bool mma = false;      // Heun cluster kernel on the FP64 MMA path (cluster_mma.cu)
@@ -205,6 +215,8 @@ struct magpy_b200_plan {
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
     DevBuf<double> d_state0, d_state, d_axis, d_kred, d_sig, d_dip, d_dmat, d_vred, d_traj, d_sums, d_partial, d_tab, d_dW, d_stage;
     DevBuf<int64_t> d_seeds;
+    DevBuf<uint32_t> d_member_idx;
+    magpy_b200_comm* comm = nullptr;   // all-reduce the sums over this communicator at the end of every run
     DevBuf<uint64_t> d_target;
     DevBuf<unsigned long long> d_newton;
     uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -217,7 +229,7 @@ struct magpy_b200_plan {
         d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
         d_dmat.release(); d_vred.release();
         d_traj.release(); d_sums.release(); d_partial.release(); d_tab.release(); d_dW.release(); d_stage.release();
-        d_seeds.release(); d_target.release(); d_newton.release();
+        d_seeds.release(); d_member_idx.release(); d_target.release(); d_newton.release();
         if (stream) cudaStreamSynchronize(stream);
         for (auto e : ev_k) cudaEventDestroy(e);
         if (ev_begin) cudaEventDestroy(ev_begin);
@@ -250,7 +262,7 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
     const bool tab = pl->use_table;
     if (pl->N == 1) {
         if (pl->implicit) LAUNCH_TRY(mb::launch_imid_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
-        else LAUNCH_TRY(mb::launch_heun_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
+        else LAUNCH_TRY(mb::launch_heun_single(noise, tab, pl->axis_z, pl->k1_min_blocks, pl->grid, pl->stream, P));
     } else if (pl->small) {
         if (pl->split) LAUNCH_TRY(mb::launch_imid_split(noise, tab, pl->N, pl->grid, pl->stream, P));
         else if (pl->implicit) LAUNCH_TRY(mb::launch_imid_small(noise, tab, pl->N, pl->grid, pl->stream, P));
@@ -314,12 +326,42 @@ int validate(const magpy_b200_ensemble* a) {
     }
     if (a->implicit_newton != MAGPY_B200_NEWTON_REFERENCE && a->implicit_newton != MAGPY_B200_NEWTON_EXACT)
         return fail(MAGPY_B200_ERR_BAD_ARG, "implicit_newton must be MAGPY_B200_NEWTON_REFERENCE or MAGPY_B200_NEWTON_EXACT");
+    if (a->member_index)
+        for (uint64_t r = 0; r < a->n_members; ++r)
+            if (a->member_index[r] > 0xFFFFFFFFull) return fail(MAGPY_B200_ERR_BAD_ARG, "member_index[%llu] must be < 2^32", (unsigned long long)r);
+    if (a->comm && mbh::comm_device(a->comm) != a->device)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "the communicator was created for device %d, the ensemble runs on device %d",
+                    mbh::comm_device(a->comm), a->device);
     if (a->use_implicit) {
         if (a->n_particles > 64) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 64 particles per cluster");
     } else if (a->n_particles > 128) {
         return fail(MAGPY_B200_ERR_BAD_ARG, "Heun supports at most 128 particles per cluster");
     }
     return MAGPY_B200_OK;
+}
+
+// K1 (heun_single.cu) is bound by the FP64-side issue time of a warp-step (~151 cycles per sub-partition): a wave with k
+// CTAs per SM takes k issue times per step, and a lone warp is hardly faster than that (155 cycles).  With ptxas left
+// alone the kernel takes 76 registers = 6 resident CTAs per SM (888 per device).  Measured over shard sizes
+// (profiles/r02_probe_k1_variants.log): a shard slightly larger than one wave does NOT pay a whole extra wave — its few
+// tail CTAs run one per SM (1M members over 8 GPUs = 977 CTAs: 92 % of the large-ensemble rate) — but as the tail grows
+// towards one CTA on every SM the block scheduler doubles some SMs up (1036 CTAs: 86 %).  The 7-CTA instantiation
+// (66 registers, no spills) holds up to 1036 CTAs in ONE wave at 97 %; an 8-CTA one (62 registers) was measured too and
+// never beats two waves of 6, so it is not built.  MAGPY_B200_K1_MIN_BLOCKS=1|7 overrides.
+void choose_k1_variant(magpy_b200_plan* pl, bool renorm) {
+    pl->k1_min_blocks = 1;
+    if (pl->N != 1 || pl->implicit || plan_noise(pl) != mb::NOISE_PHILOX_PACKED) return;
+    if (const char* env = std::getenv("MAGPY_B200_K1_MIN_BLOCKS")) {
+        const int v = std::atoi(env);
+        if (v == 1 || v == 7) { pl->k1_min_blocks = v; return; }
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    const int free_ctas = mb::heun_single_resident_ctas(pl->use_table, pl->axis_z, renorm, 1);
+    const int tight_ctas = mb::heun_single_resident_ctas(pl->use_table, pl->axis_z, renorm, 7);
+    if (free_ctas > 0 && tight_ctas > free_ctas && pl->grid > (unsigned)(sms * free_ctas) &&
+        pl->grid <= (unsigned)(sms * tight_ctas))
+        pl->k1_min_blocks = 7;
 }
 
 // K2m (cluster_mma.cu) applies to Heun clusters of 8..128 interacting particles (above 64 the packed matrix stays in
@@ -474,6 +516,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     pl->use_table = a->field_shape != MAGPY_B200_FIELD_CONSTANT;
     pl->axis_z = N == 1 && a->axis_stride == 0 && a->anisotropy_axis[0] == 0.0 && a->anisotropy_axis[1] == 0.0 &&
                  a->anisotropy_axis[2] == 1.0;
+    choose_k1_variant(pl, a->renorm != 0);
 
     // chunking: bound the field table / injected-noise window and the partial-sum buffer
     uint64_t max_steps = 4ull << 20;
@@ -573,6 +616,16 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     }
     CU_TRY(cudaMemcpyAsync(pl->d_seeds.p, seeds, R * 8, cudaMemcpyHostToDevice, pl->stream));
     pl->h2d += R * 8;
+    std::vector<uint32_t> member_idx;
+    if (a->member_index) {
+        member_idx.resize(R);
+        for (uint64_t r = 0; r < R; ++r) member_idx[r] = (uint32_t)a->member_index[r];
+        CU_TRY(pl->d_member_idx.alloc(R, pl->stream));
+        CU_TRY(cudaMemcpyAsync(pl->d_member_idx.p, member_idx.data(), R * 4, cudaMemcpyHostToDevice, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->h2d += R * 4;
+    }
+    pl->comm = a->comm;
 
     // per-member arrays arrive [R][n]; the device wants [n][R]
     {
@@ -702,6 +755,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.axis_rs = a->axis_stride ? 1 : 0;
     P.seeds = pl->d_seeds.p;
     P.stream_offset = a->stream_offset;
+    P.member_idx = pl->d_member_idx.p;
     P.coarsen_log2 = a->noise_coarsen_log2;
     P.philox_m0 = 0xD2511F53u;
     P.philox_m1 = 0xCD9E8D57u;
@@ -742,6 +796,10 @@ int plan_run(magpy_b200_plan* pl) {
         }
         ++ci;
     }
+    if (pl->comm) {   // the one collective of the multi-GPU path: sums over all ranks' members, in place, on this stream
+        int rc = mbh::comm_allreduce_device(pl->comm, pl->d_sums.p, pl->S * 4, MAGPY_B200_COMM_SUM, pl->stream);
+        if (rc) return rc;
+    }
     CU_TRY(cudaEventRecord(pl->ev_end, pl->stream));
     pl->ran = true;
     return MAGPY_B200_OK;
@@ -762,6 +820,7 @@ int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
                         : pl->small ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SMALL : MAGPY_B200_KERNEL_HEUN_SMALL)
                         : pl->mma   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA
                                     : (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER : MAGPY_B200_KERNEL_HEUN_CLUSTER);
+    st->kernel_variant = (pl->N == 1 && !pl->implicit) ? (uint64_t)pl->k1_min_blocks : 0;
     if (pl->ran) {
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, pl->ev_begin, pl->ev_end));
@@ -836,7 +895,7 @@ int plan_fetch(magpy_b200_plan* pl, double* out_time, double* out_field, double*
 extern "C" {
 
 int magpy_b200_abi_version(void) { return MAGPY_B200_ABI_VERSION; }
-const char* magpy_b200_last_error(void) { return g_error.c_str(); }
+const char* magpy_b200_last_error(void) { return mbh::g_error.c_str(); }
 
 int magpy_b200_device_count(int* count) {
     if (!count) return fail(MAGPY_B200_ERR_BAD_ARG, "count is NULL");
@@ -959,6 +1018,8 @@ int magpy_b200_simulate_ensemble_multi(const magpy_b200_ensemble* args, const in
                                        magpy_b200_stats* stats) {
     if (!args) return fail(MAGPY_B200_ERR_BAD_ARG, "args is NULL");
     if (!devices || n_devices < 1) return fail(MAGPY_B200_ERR_BAD_ARG, "devices must list at least one CUDA device");
+    if (args->comm && n_devices > 1)
+        return fail(MAGPY_B200_ERR_BAD_ARG, "a communicator belongs to one device: use either `comm` (one process per GPU) or a device list");
     if (n_devices == 1) {
         magpy_b200_ensemble one = *args;
         one.device = devices[0];
@@ -983,6 +1044,10 @@ int magpy_b200_simulate_ensemble_multi(const magpy_b200_ensemble* args, const in
             if (a.m0_stride) a.magnetisation_direction += lo * a.m0_stride;
             if (a.radius_stride) a.radius += lo * a.radius_stride;
             if (a.member_temperature) a.member_temperature += lo;
+            if (a.member_index) a.member_index += lo;
+            if (a.member_anisotropy) a.member_anisotropy += lo;
+            if (a.member_damping) a.member_damping += lo;
+            if (a.member_field_amplitude) a.member_field_amplitude += lo;
             if (a.injected_dw) a.injected_dw += lo * a.injected_steps * n;
             if (a.out_trajectories) a.out_trajectories += lo * n * S;
             if (a.out_final) a.out_final += lo * n;
@@ -1017,6 +1082,7 @@ int magpy_b200_simulate_ensemble_multi(const magpy_b200_ensemble* args, const in
             total.h2d_bytes += st.h2d_bytes;
             total.d2h_bytes += st.d2h_bytes;
             total.kernel_family = st.kernel_family;
+            total.kernel_variant = st.kernel_variant;
         }
         if (!rc && args->out_sums) {   // fixed device order: deterministic for a given device list
             std::fill_n(args->out_sums, S * 4, 0.0);

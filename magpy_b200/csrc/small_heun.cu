@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) heun_small_kernel(const __grid_
     }
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const uint32_t member = member_id(P, r);
 
     // one Heun step of the whole cluster from the scaled increments cw (same fused form as K1:
     // f(m,g) = -m x (g + alpha m x g), predictor/corrector adds folded into the last cross product)

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
     }
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const uint32_t member = member_id(P, r);
     NewtonCount nc{0ull, 0ull, 0ull};
 
     uint64_t j = P.j0;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_split_kernel(const __grid_
     const V3 qu = quirk_u(N, p, e0, P.k_red[0]);
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    const uint32_t member = (uint32_t)(r + P.stream_offset);
+    const uint32_t member = member_id(P, r);
     NewtonCount nc{0ull, 0ull, 0ull};
 
     // effective field of the own particle from the cluster's moments (own = x, the others by shuffle)

@@ -111,7 +111,8 @@ class EnsembleModel:
 
     def simulate(self, end_time, time_step, max_samples, random_state, renorm=False, interactions=True,
                  n_jobs=1, implicit_solve=True, implicit_tol=1e-9, device=0, stream_offset=0,
-                 return_trajectories=None, gauss='f32p', shard=None, devices=None, implicit_newton='reference'):
+                 return_trajectories=None, gauss='f32p', shard=None, devices=None, implicit_newton='reference',
+                 comm=None):
         """Simulate every member; arguments up to `implicit_tol` as magpy/model.py:159-208.
 
         `n_jobs` is accepted and ignored (the ensemble runs as one device launch).
@@ -129,8 +130,14 @@ class EnsembleModel:
                 exact Jacobian of the midpoint residual (~3 iterations, several times faster): the same scheme solved to
                 a tighter residual, so paths differ from the reference's at the 1e-9 level per step.
             shard ((rank, world_size)|None): integrate only this rank's contiguous slice of the
-                members (magpy_b200.sharding.shard_bounds) and all-reduce the ensemble sums over the
-                initialised torch.distributed group; per-member outputs then cover the local slice.
+                members (magpy_b200.sharding.shard_bounds) and all-reduce the ensemble sums over `comm`;
+                per-member outputs then cover the local slice.
+            comm (core.Comm|None): the communicator of a sharded run (one process per GPU).  None = the one built
+                from the launcher's environment (`sharding.world_comm`, torchrun's RANK / WORLD_SIZE / MASTER_*);
+                a sharded run over more than one rank without a communicator raises.  With a `core.Comm` and a
+                single parameter group the all-reduce runs on the device inside the library call (one
+                ncclAllReduce); any other object needs an `allreduce_sums(ndarray)` method and is applied to the
+                host sums.
         """
         R = self.ensemble_size
         seeds = self._member_seeds(random_state)
@@ -140,6 +147,11 @@ class EnsembleModel:
             lo, hi = shard_bounds(R, shard[1], shard[0])
             if hi == lo:
                 raise ValueError('ensemble of %d members cannot be sharded over %d ranks' % (R, shard[1]))
+            from .sharding import resolve_comm
+            comm = resolve_comm(shard, comm, device)
+        elif comm is not None:
+            raise ValueError('comm= needs shard=(rank, world_size)')
+        device_comm = comm if isinstance(comm, core.Comm) else None
         base = self.base_model_params
         N = int(np.asarray(base['radius']).reshape(-1).shape[0])
         if return_trajectories is None:
@@ -194,6 +206,7 @@ class EnsembleModel:
                 consume(out, idx)
             del pending[:]
         stats = []
+        reduced_on_device = False
         for idx in groups:
             first = int(idx[0])
             params = dict(base, **{k: self._overrides[k][first] for k in other_keys})
@@ -216,8 +229,17 @@ class EnsembleModel:
                     params['damping'], temperature, renorm, interactions, implicit_solve, time_step,
                     end_time, S, seeds[lo:hi] if single else seeds[idx], params['field_shape'],
                     params['field_amplitude'], params['field_frequency'], implicit_tol)
-            kwargs = dict(device=device, stream_offset=int(stream_offset) + first, return_trajectories=return_trajectories,
+            kwargs = dict(device=device, return_trajectories=return_trajectories,
                           return_sums=True, return_final=True, gauss=gauss, implicit_newton=implicit_newton)
+            if single:
+                kwargs['stream_offset'] = int(stream_offset) + lo   # contiguous slice: global index = offset + position
+                if device_comm is not None and devices is None:
+                    kwargs['comm'] = device_comm                   # sums all-reduced on the device, inside the call
+                    reduced_on_device = True
+            else:
+                # a parameter group is a scattered subset: every member keeps its GLOBAL index in the Philox counter,
+                # whatever the grouping or the sharding
+                kwargs['member_index'] = np.asarray(idx, dtype=np.uint64) + np.uint64(int(stream_offset))
             if single or devices is not None:
                 consume(core.simulate_ensemble(*args, devices=devices, **kwargs), idx)
             else:
@@ -228,9 +250,8 @@ class EnsembleModel:
                     flush()
         flush()
         time, field, traj, final, sums = state['time'], state['field'], state['traj'], state['final'], state['sums']
-        if shard is not None:
-            from .sharding import allreduce_sums
-            allreduce_sums(sums)
+        if comm is not None and not reduced_on_device:
+            comm.allreduce_sums(sums)
         member_fields = None
         if len(group_fields) > 1 and any(not np.array_equal(f, group_fields[0]) for f in group_fields[1:]):
             member_fields = (np.stack(group_fields), group_of)   # members see different fields: keep each one's own

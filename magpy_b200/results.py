@@ -71,6 +71,9 @@ def load_results(fname):
     return Results(arr['time'], arr['field'], {0: arr['mx']}, {0: arr['my']}, {0: arr['mz']}, 1)
 
 
+_trapezoid = getattr(np, 'trapezoid', None) or np.trapz   # NumPy >= 2.0 / 1.x (the reference: scipy.integrate.trapz)
+
+
 class _LazyResults:
     """Sequence of per-member ``Results`` views over one [R, N, 3, S] array.  `member_fields` = (fields [G, S],
     group index of every member [R]) when the members do not all see the same applied field (an ensemble whose
@@ -189,7 +192,7 @@ class EnsembleResults:
         mask = before_mask & after_mask
         if mask is True:
             mask = np.ones(len(self.time), dtype=bool)
-        return -get_mu0() * np.trapezoid(self.field[mask], self.ensemble_magnetisation()[mask])
+        return -get_mu0() * _trapezoid(self.field[mask], self.ensemble_magnetisation()[mask])
 
     def final_cycle_energy_dissipated(self, field_frequency):
         """Energy dissipated during the last field period (magpy/results.py:193-217)."""

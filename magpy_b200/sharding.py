@@ -2,9 +2,12 @@
 
 Members are independent (magpy/model.py:204-207), so the path shards by member index with no
 data-path exchange; the only collective is one all-reduce (sum, fp64) of the [S][4] ensemble
-sums.  Member `i` keeps its seed and its Philox member index whatever the number of ranks, so
-results do not depend on the GPU count (up to fp64 summation order)."""
-import numpy as np
+sums, issued by the native library through NCCL (`core.Comm`, include/magpy_b200.h).  Member `i`
+keeps its seed and its Philox member index whatever the number of ranks, so results do not depend
+on the GPU count (up to fp64 summation order)."""
+from . import core
+
+_WORLD = None
 
 
 def shard_bounds(n_members, world_size, rank):
@@ -16,19 +19,30 @@ def shard_bounds(n_members, world_size, rank):
     return lo, min(lo + per, n_members)
 
 
-def allreduce_sums(sums, group=None):
-    """Sum the [S][4] ensemble sums over all ranks (no-op without an initialised process group)."""
+def world_comm(device=-1):
+    """The process-wide communicator built from the launcher's environment (RANK, WORLD_SIZE, LOCAL_RANK,
+    MASTER_ADDR, MASTER_PORT — what torchrun sets); created on first use.  device < 0 = LOCAL_RANK."""
+    global _WORLD
+    if _WORLD is None:
+        _WORLD = core.Comm.from_env(device)
+    return _WORLD
+
+
+def resolve_comm(shard, comm, device):
+    """The communicator a sharded call must use: the one given, else the environment's; never a silent no-op — a
+    sharded run whose sums are not reduced would report partial sums against the global member count."""
+    rank, world = shard
+    if comm is not None:
+        return comm
+    if world == 1:
+        return None
     try:
-        import torch
-        import torch.distributed as dist
-    except ImportError:      # single process, torch absent
-        return sums
-    if not (dist.is_available() and dist.is_initialized()):
-        return sums
-    on_gpu = dist.get_backend(group) == 'nccl'
-    t = torch.from_numpy(np.ascontiguousarray(sums))
-    if on_gpu:
-        t = t.cuda()
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    sums[...] = t.cpu().numpy()
-    return sums
+        comm = world_comm(device)
+    except (ConnectionError, RuntimeError) as exc:
+        raise RuntimeError('EnsembleModel.simulate(shard=(%d, %d)) needs a communicator to sum the ensemble over the '
+                           'ranks: pass comm=, or launch one process per GPU with RANK / WORLD_SIZE / MASTER_ADDR / '
+                           'MASTER_PORT set (%s)' % (rank, world, exc)) from exc
+    if (comm.rank, comm.world_size) != (rank, world):
+        raise ValueError('shard=(%d, %d) does not match the communicator (rank %d of %d)' %
+                         (rank, world, comm.rank, comm.world_size))
+    return comm

@@ -257,7 +257,8 @@ def test_ensemble_model_seeds_and_grouping(monkeypatch):
         idx = [i for i, t in enumerate(temps) if t == c['T']]
         assert np.array_equal(c['seeds'], want[idx])
         assert np.array_equal(c['axis'], axes[idx])
-        assert c['kw']['stream_offset'] == idx[0]
+        # every member keeps its GLOBAL index in the Philox counter, whatever the grouping
+        assert np.array_equal(c['kw']['member_index'], idx) and 'stream_offset' not in c['kw']
     assert np.array_equal(res.final_state_array()[:, 0, 0], temps)
     assert np.allclose(res.ensemble_magnetisation(), 1.0)
     with pytest.raises(TypeError):
@@ -325,6 +326,15 @@ rank, world = int(sys.argv[1]), int(sys.argv[2])
 dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=rank, world_size=world)
 orc = ol.load_oracle()
 
+class GlooComm:
+    # CPU stand-in for core.Comm (the library's NCCL communicator): same duck type, gloo underneath
+    rank, world_size = rank, world
+    def allreduce_sums(self, sums):
+        import torch
+        t = torch.from_numpy(sums)
+        dist.all_reduce(t)
+        return sums
+
 def oracle_backed(radius, anisotropy, axis, m0, location, Ms, alpha, T, renorm, inter, impl, dt, t_end, S, seeds, shape,
                   H0, f, tol, **kw):
     # stand-in for the device call (no GPU in this test): the CPU oracle, member by member
@@ -337,13 +347,21 @@ def oracle_backed(radius, anisotropy, axis, m0, location, Ms, alpha, T, renorm, 
     M = tr.sum(axis=1)
     sums = np.stack([M[:, 0].sum(0), M[:, 1].sum(0), M[:, 2].sum(0), (M[:, 2] ** 2).sum(0)], axis=1)
     return dict(N=c.N, R=len(seeds), time=t, field=fl, trajectories=tr, sums=sums, final=tr[..., -1],
-                stats=dict(offset=kw['stream_offset']))
+                stats=dict(offset=kw.get('stream_offset'), member_index=kw.get('member_index')))
+
+class OraclePlan:
+    def __init__(self, *a, **kw):
+        self.out = oracle_backed(*a, **kw)
+    def run(self): pass
+    def sync(self): return self.out['stats']
+    def fetch(self): return dict(self.out)
+model_mod.core.EnsemblePlan = OraclePlan
 
 model_mod.core.simulate_ensemble = oracle_backed
 base = mp.Model([7e-9, 7e-9], [1e5, 1e5], [[0, 0, 1.0]] * 2, [[0, 0, 1.0]] * 2, [[0, 0, 0], [0, 0, 9e-9]], 4e5, 0.1, 330.0,
                 field_shape='sine', field_frequency=5e9, field_amplitude=1e4)
 ens = mp.EnsembleModel(9, base)
-res = ens.simulate(5e-11, 1e-12, 11, random_state=3, implicit_solve=False, shard=(rank, world))
+res = ens.simulate(5e-11, 1e-12, 11, random_state=3, implicit_solve=False, shard=(rank, world), comm=GlooComm())
 full = ens.simulate(5e-11, 1e-12, 11, random_state=3, implicit_solve=False)
 lo, hi = mp.sharding.shard_bounds(9, world, rank)
 assert res.stats[0]['offset'] == lo
@@ -352,6 +370,24 @@ assert np.allclose(res.final_state_array(), full.final_state_array()[lo:hi], rto
 assert np.allclose(res.ensemble_magnetisation('z'), full.ensemble_magnetisation('z'), rtol=1e-13)
 assert np.allclose(res.ensemble_magnetisation_stderr(), full.ensemble_magnetisation_stderr(), rtol=1e-9)
 assert np.isclose(res.energy_dissipated(), full.energy_dissipated(), rtol=1e-10)
+# a sharded run over several ranks without a communicator must not silently return partial sums (ADVICE r1)
+for k in ('RANK', 'WORLD_SIZE'):
+    os.environ.pop(k, None)
+try:
+    ens.simulate(5e-11, 1e-12, 11, random_state=3, implicit_solve=False, shard=(rank, world))
+    raise SystemExit('sharded run without a communicator did not raise')
+except RuntimeError as exc:
+    assert 'communicator' in str(exc)
+# grouped override (two temperatures, interleaved) + sharding: every member keeps its global Philox index
+temps = [300.0, 330.0] * 4 + [300.0]
+ens2 = mp.EnsembleModel(9, base, temperature=temps)
+res2 = ens2.simulate(5e-11, 1e-12, 11, random_state=3, implicit_solve=False, shard=(rank, world), comm=GlooComm())
+full2 = ens2.simulate(5e-11, 1e-12, 11, random_state=3, implicit_solve=False)
+seen = np.sort(np.concatenate([st['member_index'] for st in res2.stats]))
+assert np.array_equal(seen, np.arange(lo, hi)), seen
+assert np.array_equal(np.sort(np.concatenate([st['member_index'] for st in full2.stats])), np.arange(9))
+assert np.allclose(res2.final_state_array(), full2.final_state_array()[lo:hi], rtol=0, atol=0)
+assert np.allclose(res2.ensemble_magnetisation('z'), full2.ensemble_magnetisation('z'), rtol=1e-13)
 dist.destroy_process_group()
 print('rank', rank, 'ok')
 '''
