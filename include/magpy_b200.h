@@ -155,7 +155,8 @@ typedef struct magpy_b200_ensemble {
      * (anisotropy / damping) or any shape (field amplitude); gauss_mode F32_PACKED or injected increments. */
     const double* member_anisotropy;
     const double* member_damping;
-    const double* member_field_amplitude;
+    const double* member_field_amplitude;   /* when set, out_field is the waveform for an amplitude of 1 A/m (member r saw
+                                               member_field_amplitude[r] times it) */
     /* Multi-GPU (one process per GPU): when set, the [S][4] ensemble sums are all-reduced over the communicator
      * (ncclAllReduce, sum, fp64, in place on the device buffer, enqueued on the plan's stream after the last
      * integration kernel) before they are returned: out_sums then holds the sums over ALL ranks' members.  Every rank
@@ -276,6 +277,12 @@ int magpy_b200_philox_words(int device, const uint32_t ctr[4], const uint32_t ke
 /* the n Gaussian draws member `member` / particle `particle` consumes at `step` (3 values) */
 int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t particle, uint64_t first_step,
                          uint64_t n_steps, int gauss_mode, double* out /* [n_steps][3] */);
+/* Statistics of the Gaussian stream accumulated on the device (for tests at 1e9+ draws against lib/rng.cpp:14-24's
+ * N(0,1)): n_members threads (members first_member ...) x n_steps steps x 3 draws, consumed exactly as the integration
+ * kernels do.  hist[4096]: counts in bins of width 1/256 over [-8, 8); angle_hist[1024]: direction of the (x, y) pairs
+ * that come from one Box-Muller pair, over one revolution (bin b = directions [b, b + 1) 2 pi / 1024 - pi 2^-18); moments[5] = {sum z, sum z^2, sum z^3, sum z^4, max |z|}. */
+int magpy_b200_gaussian_stats(int device, int64_t seed, uint64_t first_member, uint64_t n_members, uint64_t n_steps,
+                              int gauss_mode, uint64_t* hist, uint64_t* angle_hist, double* moments);
 /* sustained FP64 FMA rate of the device (TFLOP/s), measured with a register-resident
  * DFMA chain kernel — the roofline denominator for the integration kernels */
 int magpy_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz);

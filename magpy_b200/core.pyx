@@ -132,6 +132,7 @@ cdef extern from "magpy_b200.h" nogil:
     int magpy_b200_schedule(double, double, size_t, uint64_t*)
     int magpy_b200_philox_words(int, const uint32_t*, const uint32_t*, uint32_t*)
     int magpy_b200_gaussians(int, int64_t, uint64_t, uint32_t, uint64_t, uint64_t, int, double*)
+    int magpy_b200_gaussian_stats(int, int64_t, uint64_t, uint64_t, uint64_t, int, uint64_t*, uint64_t*, double*)
     int magpy_b200_fp64_peak(int, double*, double*)
     int magpy_b200_fp64_mma_peak(int, double*)
     int magpy_b200_simulate_dom(int, size_t, const double*, const double*, const double*, double, double, double, double,
@@ -683,6 +684,27 @@ def gaussians(seed, member, particle, first_step, n_steps, str gauss='f32p', int
     if rc != 0:
         _raise(rc)
     return out
+
+
+def gaussian_stats(seed, n_members, n_steps, str gauss='f32p', first_member=0, int device=0):
+    """Histograms and moments of 3 * n_members * n_steps draws of the in-kernel Gaussian stream, accumulated on the device:
+    {'n', 'hist' (4096 bins of width 1/256 over [-8, 8)), 'edges', 'angle_hist' (1024 bins over [-pi, pi)), 'n_angles',
+    'sum', 'sum2', 'sum3', 'sum4', 'max_abs'}."""
+    cdef np.ndarray[np.uint64_t, ndim=1] hist = np.zeros(4096, dtype=np.uint64)
+    cdef np.ndarray[np.uint64_t, ndim=1] ang = np.zeros(1024, dtype=np.uint64)
+    cdef np.ndarray[double, ndim=1] mom = np.zeros(5)
+    cdef int64_t c_seed = int(seed)
+    cdef uint64_t c_first = int(first_member), c_n = int(n_members), c_steps = int(n_steps)
+    cdef int code = _GAUSS_LOOKUP[gauss]
+    cdef int rc
+    with nogil:
+        rc = magpy_b200_gaussian_stats(device, c_seed, c_first, c_n, c_steps, code, <uint64_t*> &hist[0],
+                                       <uint64_t*> &ang[0], &mom[0])
+    if rc != 0:
+        _raise(rc)
+    return {'n': 3 * int(n_members) * int(n_steps), 'hist': hist, 'edges': np.arange(4097) / 256.0 - 8.0,
+            'angle_hist': ang, 'n_angles': int(ang.sum()), 'sum': mom[0], 'sum2': mom[1], 'sum3': mom[2], 'sum4': mom[3],
+            'max_abs': mom[4]}
 
 
 def fp64_peak(int device=0):

@@ -57,6 +57,14 @@ struct RunParams {
     const int64_t* seeds;       // [R]
     uint64_t stream_offset;
     const uint32_t* member_idx; // [R] global member index of the Philox counter, or nullptr: stream_offset + r
+    // per-member material parameters (N = 1, `MP` instantiations of the single-particle kernels): every thread carries
+    // its own reduced time scale, hence its own dt, noise amplitude, field scale and zero-order-hold schedule
+    const double* mp_alpha;     // [R] damping
+    const double* mp_dt;        // [R] reduced time step dt * tau_r
+    const double* mp_h0;        // [R] reduced field amplitude H0_r / H_k,r (the field table holds the unit waveform)
+    const double* mp_Ts;        // [R] reduced sampling interval T_r / (S - 1)
+    uint32_t* member_j;         // [R] state index reached by each member (carried between the launches of a run)
+    uint64_t tab_j0;            // step index of field-table row 0 in the MP instantiations (j0 minus a margin)
     uint32_t philox_m0, philox_m1;  // the two Philox multipliers, passed at run time for the split multiply of rng.cuh
     uint32_t coarsen_log2;      // NOISE_PHILOX_COARSE: step s sums the packed stream's fine steps s 2^L .. (s+1) 2^L - 1
     double* state;              // [n][R]
@@ -159,6 +167,21 @@ constexpr int CL_LANES = 32;
 __device__ __forceinline__ void renormalise(V3& m) {
     const double inv = rsqrt(dot(m, m));
     m.x *= inv; m.y *= inv; m.z *= inv;
+}
+
+// State index stored by sample k >= 1 of ONE member: the zero-order-hold schedule of lib/simulation.cpp:342-355 in the
+// member's own reduced units — the smallest step count s with fl(s * dt) > fl(k * Ts), minus one (the state before the
+// step that breaches the sampling time).  Same fp64 operations as build_schedule on the host (magpy_b200.cu); the
+// products are formed with __dmul_rn so that no FMA contraction changes a comparison at an exact tie (Ts / dt an
+// integer is the common case).
+__device__ __forceinline__ uint64_t member_target(const uint32_t k, const double dt, const double Ts) {
+    if (k == 0) return 0;
+    const double lim = __dmul_rn((double)k, Ts);
+    const double est = floor(__ddiv_rn(lim, dt));
+    uint64_t s = est > 2.0 ? (uint64_t)est - 2 : 0;
+    while (__dmul_rn((double)s, dt) <= lim) ++s;
+    while (s > 0 && __dmul_rn((double)(s - 1), dt) > lim) --s;
+    return s - 1;
 }
 
 struct NewtonCount {

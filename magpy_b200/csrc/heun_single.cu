@@ -12,6 +12,8 @@ namespace mb {
 // With u = g + alpha (m x g) the LLG increment is f(m,g) = -m x u, so the predictor
 // x~ = m + f(m,g) and the corrector m' = (m + x~)/2 + f(x~,g~)/2 are accumulated directly in the
 // FMAs of the second cross product (no separate adds, and f1 is never materialised).
+// `dt` only multiplies the applied field here (the anisotropy term carries it in edt = k dt e): the MP instantiations
+// pass h0_r dt_r with the unit waveform in hz0 / hz1.
 template <bool AXIS_Z>
 __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V3& edt, const double alpha,
                                                const double dt, const V3& cw, const double hz0, const double hz1) {
@@ -48,7 +50,9 @@ __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V
 // MINB = resident CTAs per SM the register allocation must allow.  1: ptxas is free (76 registers, 6 CTAs = 24 warps
 // per SM); 7: at most 72 registers (66 used, no spills).  The host picks 7 when the shard fits in one wave of 7 CTAs per
 // SM but not in one of 6 (magpy_b200.cu: choose_k1_variant; measured in profiles/r02_probe_k1_variants.log).
-template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool RENORM, int MINB>
+// MP = per-member material parameters (anisotropy, damping, field amplitude next to radius / temperature): alpha, dt,
+// the noise amplitude, the field scale and the sampling schedule are per-thread values (RunParams::mp_*).
+template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool RENORM, int MINB, bool MP = false>
 __global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
@@ -59,10 +63,12 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const
     V3 e{0.0, 0.0, 1.0};
     if (!AXIS_Z)
         e = V3{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
-    const double alpha = P.alpha, dt = P.dt;
+    const double alpha = MP ? P.mp_alpha[r] : P.alpha, dt = MP ? P.mp_dt[r] : P.dt;
     const double kdt = P.k_red[0] * dt;
     const V3 edt{e.x * kdt, e.y * kdt, e.z * kdt};
-    const double c = P.sig[r * P.sig_rs] * P.sqrt_dt;   // per-member sigma when the radii differ between members
+    const double c = P.sig[r * P.sig_rs] * (MP ? sqrt(dt) : P.sqrt_dt);   // per-member sigma when the radii differ between members
+    const double mp_h0 = MP ? P.mp_h0[r] : 0.0, mp_Ts = MP ? P.mp_Ts[r] : 0.0;
+    const double hdt = MP ? mp_h0 * dt : dt;            // multiplies the applied field (MP: unit waveform in the table)
     const float bm_scale = scale_to_bm(c);
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
@@ -70,18 +76,19 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const
 
     // one Heun step from the scaled increment cw; `tp` = this step's entry of the field table
     auto advance = [&](const V3& cw, const double2* tp) {
-        double hz0 = P.h_const, hz1 = P.h_const;
+        double hz0 = MP ? 1.0 : P.h_const, hz1 = hz0;
         if (FIELD_TAB) {
             const double2 h = __ldg(tp);
             hz0 = h.x; hz1 = h.y;
         }
-        m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
+        m = heun_single_step<AXIS_Z>(m, e, edt, alpha, hdt, cw, hz0, hz1);
         if (RENORM) renormalise(m);
     };
 
     // All loop state of the inner loops is 32-bit (a launch covers at most 2^32 steps and the Philox
     // counter word is the low 32 bits of the step / step-pair index anyway) plus one table pointer.
-    uint64_t j = P.j0;
+    uint64_t j = MP ? (uint64_t)P.member_j[r] : P.j0;
+    const uint64_t tab0 = MP ? P.tab_j0 : P.j0;
     const double2* tab = reinterpret_cast<const double2*>(P.field_tab);
     // Packed noise: `g` holds the six increments of Philox block `gblk` (steps 2 gblk and 2 gblk + 1) while
     // `have` is set.  The pair loop is software pipelined — the block of the NEXT step pair is generated inside
@@ -99,16 +106,20 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const
         }
     };
     for (uint32_t k = P.k0; k <= P.k1; ++k) {
-        const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+        // MP: every member stops at ITS OWN state index of sample k; a launch that records samples ends on the last of
+        // them, a pure-advance launch (k0 == k1) never steps past the member's next sample
+        const uint64_t tgt = !MP ? ((k < P.k1) ? P.target[k] : P.j1)
+                             : (k < P.k1) ? member_target(k, dt, mp_Ts)
+                             : (P.k1 > P.k0) ? j : min(P.j1, member_target(P.k0, dt, mp_Ts));
         if (NOISE == NOISE_PHILOX_PACKED) {
             if ((j & 1) && j < tgt) {          // odd step: second half of its block
                 need((uint32_t)(j >> 1));
-                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tab + (j - P.j0));
+                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tab + (j - tab0));
                 ++j;
             }
-            const uint32_t pairs = (uint32_t)((tgt - j) >> 1);
+            const uint32_t pairs = (!MP || j < tgt) ? (uint32_t)((tgt - j) >> 1) : 0u;   // MP: a member may already be past P.j1
             uint32_t blk = (uint32_t)(j >> 1);
-            const double2* tp = tab + (j - P.j0);
+            const double2* tp = tab + (j - tab0);
             if (pairs != 0) need(blk);
             for (uint32_t i = pairs; i != 0; --i, tp += 2) {
                 float gn[6];
@@ -122,11 +133,11 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const
             j += 2ull * pairs;
             if (j < tgt) {                     // one more (even) step before the sample: first half of its block
                 need((uint32_t)(j >> 1));
-                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tab + (j - P.j0));
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tab + (j - tab0));
                 ++j;
             }
         } else {
-            const double2* tp = tab + (j - P.j0);
+            const double2* tp = tab + (j - tab0);
 #pragma unroll 2
             for (; j < tgt; ++j, ++tp) advance(draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, c, bm_scale), tp);
         }
@@ -144,6 +155,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const
     }
     if (live) {
         P.state[r] = m.x; P.state[P.R + r] = m.y; P.state[2 * P.R + r] = m.z;
+        if (MP) P.member_j[r] = (uint32_t)j;
     }
 }
 
@@ -166,9 +178,27 @@ static void launch_hs(bool tab, bool axis_z, unsigned grid, cudaStream_t s, cons
     }
 }
 
+// per-member material parameters: general-axis arithmetic, packed Philox or injected increments
+template <int NOISE>
+static void launch_hs_mp(bool tab, dim3 g, dim3 b, cudaStream_t s, const RunParams& P) {
+    const bool renorm = P.renorm != 0;
+    if (tab) {
+        if (renorm) heun_single_kernel<NOISE, true, false, true, 1, true><<<g, b, 0, s>>>(P);
+        else heun_single_kernel<NOISE, true, false, false, 1, true><<<g, b, 0, s>>>(P);
+    } else {
+        if (renorm) heun_single_kernel<NOISE, false, false, true, 1, true><<<g, b, 0, s>>>(P);
+        else heun_single_kernel<NOISE, false, false, false, 1, true><<<g, b, 0, s>>>(P);
+    }
+}
+
 // min_blocks = 1 or 7 (production noise mode only; the other modes have the one free-allocation instantiation)
 cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, int min_blocks, unsigned grid, cudaStream_t s,
                                const RunParams& P) {
+    if (P.mp_dt != nullptr) {
+        if (noise == NOISE_INJECTED) launch_hs_mp<NOISE_INJECTED>(tab, dim3(grid), dim3(SINGLE_THREADS), s, P);
+        else launch_hs_mp<NOISE_PHILOX_PACKED>(tab, dim3(grid), dim3(SINGLE_THREADS), s, P);
+        return cudaGetLastError();
+    }
     switch (noise) {
         case NOISE_PHILOX_F32: launch_hs<NOISE_PHILOX_F32, 1>(tab, axis_z, grid, s, P); break;
         case NOISE_PHILOX_F64: launch_hs<NOISE_PHILOX_F64, 1>(tab, axis_z, grid, s, P); break;

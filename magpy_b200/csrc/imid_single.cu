@@ -74,7 +74,9 @@ __device__ __forceinline__ V3 imid_single_step(const V3& x0, const V3& e, const 
     return V3{2 * X.x - x0.x, 2 * X.y - x0.y, 2 * X.z - x0.z};
 }
 
-template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool EXACT>
+// MP = per-member material parameters (see heun_single.cu): alpha, dt, the clamp, the field scale and the sampling
+// schedule are per-thread values.
+template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool EXACT, bool MP = false>
 __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
@@ -89,18 +91,28 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
     const uint32_t member = member_id(P, r);
     const bool renorm = P.renorm != 0;
     NewtonCount nc{0ull, 0ull, 0ull};
+    const double alpha = MP ? P.mp_alpha[r] : P.alpha, dt = MP ? P.mp_dt[r] : P.dt;
+    const double sqrt_dt = MP ? sqrt(dt) : P.sqrt_dt;
+    const double clampA = MP ? sqrt(2 * 1000.0 * fabs(log(dt))) : P.clampA;   // lib/integrators.cpp:598-599
+    const double mp_h0 = MP ? P.mp_h0[r] : 1.0, mp_Ts = MP ? P.mp_Ts[r] : 0.0;
 
-    uint64_t j = P.j0;
+    uint64_t j = MP ? (uint64_t)P.member_j[r] : P.j0;
+    const uint64_t tab0 = MP ? P.tab_j0 : P.j0;
     for (uint32_t k = P.k0; k <= P.k1; ++k) {
-        const uint64_t tgt = (k < P.k1) ? P.target[k] : P.j1;
+        // MP: every member stops at ITS OWN state index of sample k; a launch that records samples ends on the last of
+        // them, a pure-advance launch (k0 == k1) never steps past the member's next sample
+        const uint64_t tgt = !MP ? ((k < P.k1) ? P.target[k] : P.j1)
+                             : (k < P.k1) ? member_target(k, dt, mp_Ts)
+                             : (P.k1 > P.k0) ? j : min(P.j1, member_target(P.k0, dt, mp_Ts));
         for (; j < tgt; ++j) {
             const V3 w = draw_noise<NOISE>(P, key0, key1, j, 0u, member, r);
-            double hz0 = P.h_const, hz1 = P.h_const;
+            double hz0 = MP ? mp_h0 : P.h_const, hz1 = hz0;
             if (FIELD_TAB) {
-                const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - P.j0));
+                const double2 h = __ldg(reinterpret_cast<const double2*>(P.field_tab) + (j - tab0));
                 hz0 = h.x; hz1 = h.y;
+                if (MP) { hz0 *= mp_h0; hz1 *= mp_h0; }   // the table holds the unit waveform
             }
-            m = imid_single_step<AXIS_Z, EXACT>(m, e, kred, P.alpha, sr, P.dt, P.clampA, P.sqrt_dt, P.eps, w, hz0, hz1, nc);
+            m = imid_single_step<AXIS_Z, EXACT>(m, e, kred, alpha, sr, dt, clampA, sqrt_dt, P.eps, w, hz0, hz1, nc);
             if (renorm) renormalise(m);
         }
         if (k < P.k1) {
@@ -117,8 +129,21 @@ __global__ void __launch_bounds__(SINGLE_THREADS) imid_single_kernel(const __gri
     }
     if (live) {
         P.state[r] = m.x; P.state[P.R + r] = m.y; P.state[2 * P.R + r] = m.z;
+        if (MP) P.member_j[r] = (uint32_t)j;
     }
     newton_flush(P, nc, live);
+}
+
+template <int NOISE>
+static void launch_is_mp(bool tab, unsigned grid, cudaStream_t s, const RunParams& P) {
+    const dim3 g(grid), b(SINGLE_THREADS);
+    if (P.newton_exact) {
+        if (tab) imid_single_kernel<NOISE, true, false, true, true><<<g, b, 0, s>>>(P);
+        else imid_single_kernel<NOISE, false, false, true, true><<<g, b, 0, s>>>(P);
+    } else {
+        if (tab) imid_single_kernel<NOISE, true, false, false, true><<<g, b, 0, s>>>(P);
+        else imid_single_kernel<NOISE, false, false, false, true><<<g, b, 0, s>>>(P);
+    }
 }
 
 template <int NOISE>
@@ -137,6 +162,11 @@ static void launch_is(bool tab, bool axis_z, unsigned grid, cudaStream_t s, cons
 }
 
 cudaError_t launch_imid_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
+    if (P.mp_dt != nullptr) {   // per-member material parameters
+        if (noise == NOISE_INJECTED) launch_is_mp<NOISE_INJECTED>(tab, grid, s, P);
+        else launch_is_mp<NOISE_PHILOX_PACKED>(tab, grid, s, P);
+        return cudaGetLastError();
+    }
     switch (noise) {
         case NOISE_PHILOX_F32: launch_is<NOISE_PHILOX_F32>(tab, axis_z, grid, s, P); break;
         case NOISE_PHILOX_F64: launch_is<NOISE_PHILOX_F64>(tab, axis_z, grid, s, P); break;

@@ -43,6 +43,10 @@ cudaError_t launch_philox_words(const uint32_t ctr[4], const uint32_t key[2], ui
 cudaError_t launch_gaussians(int noise, uint64_t seed, uint32_t member, uint32_t particle, uint64_t first_step,
                              uint64_t n_steps, double* out);
 
+// histogram [4096] of the draws over [-8, 8), histogram [1024] of the Box-Muller pair angles, {sum z, z^2, z^3, z^4, max |z|}
+cudaError_t launch_gauss_stats(int noise, uint64_t seed, uint64_t first_member, uint64_t n_members, uint64_t n_steps,
+                               unsigned long long* hist, unsigned long long* angle_hist, double* moments);
+
 // discrete-orientation model (dom.cu): one thread per batch item
 struct DomBatch {
     uint64_t n, S;

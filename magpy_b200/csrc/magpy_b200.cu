@@ -179,6 +179,10 @@ struct Chunk {
     uint32_t k0, k1;
 };
 
+// per-member schedules (MP kernels) differ from the shared one by a step at most (exact ties of k Ts against s dt):
+// the field table of a launch covers this many extra steps on either side
+constexpr uint64_t kMpMargin = 4;
+
 }  // namespace
 
 struct magpy_b200_plan {
@@ -215,7 +219,9 @@ struct magpy_b200_plan {
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
     DevBuf<double> d_state0, d_state, d_axis, d_kred, d_sig, d_dip, d_dmat, d_vred, d_traj, d_sums, d_partial, d_tab, d_dW, d_stage;
     DevBuf<int64_t> d_seeds;
-    DevBuf<uint32_t> d_member_idx;
+    DevBuf<uint32_t> d_member_idx, d_member_j;
+    DevBuf<double> d_mp;            // per-member material parameters: alpha | dt | h0 | Ts, [4][R]
+    bool mp = false;                // per-member anisotropy / damping / field amplitude (N = 1): MP kernel instantiations
     magpy_b200_comm* comm = nullptr;   // all-reduce the sums over this communicator at the end of every run
     DevBuf<uint64_t> d_target;
     DevBuf<unsigned long long> d_newton;
@@ -223,13 +229,14 @@ struct magpy_b200_plan {
     uint64_t max_chunk_steps = 0;
     uint32_t max_chunk_samples = 0;
     bool ran = false;
+    bool unit_field = false;   // per-member field amplitudes: out_field is the waveform for 1 A/m
 
     ~magpy_b200_plan() {
         cudaSetDevice(device);
         d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
         d_dmat.release(); d_vred.release();
         d_traj.release(); d_sums.release(); d_partial.release(); d_tab.release(); d_dW.release(); d_stage.release();
-        d_seeds.release(); d_member_idx.release(); d_target.release(); d_newton.release();
+        d_seeds.release(); d_member_idx.release(); d_member_j.release(); d_mp.release(); d_target.release(); d_newton.release();
         if (stream) cudaStreamSynchronize(stream);
         for (auto e : ev_k) cudaEventDestroy(e);
         if (ev_begin) cudaEventDestroy(ev_begin);
@@ -326,6 +333,17 @@ int validate(const magpy_b200_ensemble* a) {
     }
     if (a->implicit_newton != MAGPY_B200_NEWTON_REFERENCE && a->implicit_newton != MAGPY_B200_NEWTON_EXACT)
         return fail(MAGPY_B200_ERR_BAD_ARG, "implicit_newton must be MAGPY_B200_NEWTON_REFERENCE or MAGPY_B200_NEWTON_EXACT");
+    if (a->member_anisotropy || a->member_damping || a->member_field_amplitude) {
+        if (a->n_particles != 1)
+            return fail(MAGPY_B200_ERR_BAD_ARG, "per-member anisotropy / damping / field amplitude are supported for single-particle ensembles only");
+        if (!a->injected_dw && a->gauss_mode != MAGPY_B200_GAUSS_F32_PACKED)
+            return fail(MAGPY_B200_ERR_BAD_ARG, "per-member anisotropy / damping / field amplitude need gauss_mode F32_PACKED (or injected increments)");
+        if (a->noise_coarsen_log2 > 0)
+            return fail(MAGPY_B200_ERR_BAD_ARG, "per-member material parameters cannot be combined with noise_coarsen_log2");
+        if ((a->member_anisotropy || a->member_damping) && a->field_shape == MAGPY_B200_FIELD_SQUARE)
+            return fail(MAGPY_B200_ERR_BAD_ARG, "per-member anisotropy / damping change the member's time scale: the square "
+                        "wave's switching instants would need per-member evaluation (use one ensemble per value)");
+    }
     if (a->member_index)
         for (uint64_t r = 0; r < a->n_members; ++r)
             if (a->member_index[r] > 0xFFFFFFFFull) return fail(MAGPY_B200_ERR_BAD_ARG, "member_index[%llu] must be < 2^32", (unsigned long long)r);
@@ -581,14 +599,15 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     CU_TRY(pl->d_state0.alloc(n * R, pl->stream));
     CU_TRY(pl->d_state.alloc(n * R, pl->stream));
     CU_TRY(pl->d_kred.alloc(N, pl->stream));
-    const bool member_radii = a->radius_stride != 0 || a->member_temperature != nullptr;   // N = 1: sigma per member
-    CU_TRY(pl->d_sig.alloc(member_radii ? R : N, pl->stream));
+    pl->mp = a->member_anisotropy || a->member_damping || a->member_field_amplitude;
+    const bool member_radii = !pl->mp && (a->radius_stride != 0 || a->member_temperature != nullptr);   // N = 1: sigma per member
+    CU_TRY(pl->d_sig.alloc((member_radii || pl->mp) ? R : N, pl->stream));
     CU_TRY(pl->d_seeds.alloc(R, pl->stream));
     CU_TRY(pl->d_target.alloc(pl->S, pl->stream));
     CU_TRY(pl->d_sums.alloc(pl->S * 4, pl->stream));
     CU_TRY(pl->d_partial.alloc((size_t)4 * pl->max_chunk_samples * pl->grid, pl->stream));
     CU_TRY(pl->d_newton.alloc(3, pl->stream));
-    if (pl->use_table) CU_TRY(pl->d_tab.alloc(2 * std::max<uint64_t>(1, pl->max_chunk_steps), pl->stream));
+    if (pl->use_table) CU_TRY(pl->d_tab.alloc(2 * (std::max<uint64_t>(1, pl->max_chunk_steps) + 2 * kMpMargin), pl->stream));
     CU_TRY(cudaMemcpyAsync(pl->d_kred.p, rd.k_red.data(), N * 8, cudaMemcpyHostToDevice, pl->stream));
     std::vector<double> member_sigma;
     if (member_radii) {
@@ -603,8 +622,40 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         CU_TRY(cudaMemcpyAsync(pl->d_sig.p, member_sigma.data(), R * 8, cudaMemcpyHostToDevice, pl->stream));
         CU_TRY(cudaStreamSynchronize(pl->stream));
         pl->h2d += R * 8;
-    } else {
+    } else if (!pl->mp) {
         CU_TRY(cudaMemcpyAsync(pl->d_sig.p, rd.sigma.data(), N * 8, cudaMemcpyHostToDevice, pl->stream));
+    }
+    std::vector<double> mp_host;
+    if (pl->mp) {
+        // lib/simulation.cpp:498-549 member by member (N = 1: V_av = V, K_av = K, k_red = v_red = 1), same evaluation
+        // order as reduce_units: rows alpha | dt_red | h0 | sampling interval, and sigma into d_sig
+        mp_host.resize(4 * R);
+        member_sigma.resize(R);
+        for (uint64_t r = 0; r < R; ++r) {
+            const double rad = a->radius[a->radius_stride ? r : 0];
+            const double K = a->member_anisotropy ? a->member_anisotropy[r] : a->anisotropy[0];
+            const double al = a->member_damping ? a->member_damping[r] : a->damping;
+            const double T = a->member_temperature ? a->member_temperature[r] : a->temperature;
+            const double H0 = a->member_field_amplitude ? a->member_field_amplitude[r] : a->field_amplitude;
+            const double vol = 4.0 / 3.0 * M_PI * rad * rad * rad;
+            const double K_av = K / 1;
+            const double H_k = 2 * K_av / kMU0 / a->magnetisation;
+            const double tau = kGYROMAG * kMU0 * H_k / (1 + al * al);
+            const double dtr = a->time_step * tau, Tr = a->end_time * tau;
+            if (!(dtr > 0.0) || !std::isfinite(dtr) || !std::isfinite(Tr))
+                return fail(MAGPY_B200_ERR_BAD_ARG, "member %llu: non-finite reduced time step", (unsigned long long)r);
+            mp_host[r] = al;
+            mp_host[R + r] = dtr;
+            mp_host[2 * R + r] = H0 / H_k;
+            mp_host[3 * R + r] = Tr / (pl->S - 1);
+            member_sigma[r] = std::sqrt(al * kKB * T / (K_av * vol) / (1 + al * al));
+        }
+        CU_TRY(pl->d_mp.alloc(4 * R, pl->stream));
+        CU_TRY(pl->d_member_j.alloc(R, pl->stream));
+        CU_TRY(cudaMemcpyAsync(pl->d_mp.p, mp_host.data(), 4 * R * 8, cudaMemcpyHostToDevice, pl->stream));
+        CU_TRY(cudaMemcpyAsync(pl->d_sig.p, member_sigma.data(), R * 8, cudaMemcpyHostToDevice, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->h2d += 5 * R * 8;
     }
     CU_TRY(cudaMemcpyAsync(pl->d_target.p, pl->target.data(), pl->S * 8, cudaMemcpyHostToDevice, pl->stream));
     pl->h2d += N * 16 + pl->S * 8;
@@ -626,6 +677,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         pl->h2d += R * 4;
     }
     pl->comm = a->comm;
+    pl->unit_field = a->member_field_amplitude != nullptr;
 
     // per-member arrays arrive [R][n]; the device wants [n][R]
     {
@@ -741,7 +793,14 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.h_const = rd.h0;
     P.k_red = pl->d_kred.p;
     P.sig = pl->d_sig.p;
-    P.sig_rs = (a->radius_stride != 0 || a->member_temperature != nullptr) ? 1 : 0;
+    P.sig_rs = (pl->mp || a->radius_stride != 0 || a->member_temperature != nullptr) ? 1 : 0;
+    if (pl->mp) {
+        P.mp_alpha = pl->d_mp.p;
+        P.mp_dt = pl->d_mp.p + R;
+        P.mp_h0 = pl->d_mp.p + 2 * R;
+        P.mp_Ts = pl->d_mp.p + 3 * R;
+        P.member_j = pl->d_member_j.p;
+    }
     P.dip = pl->d_dip.p;
     P.dmat = pl->d_dmat.p;
     P.v_red = pl->d_vred.p;
@@ -777,13 +836,19 @@ int plan_run(magpy_b200_plan* pl) {
     CU_TRY(cudaMemcpyAsync(pl->d_state.p, pl->d_state0.p, nR * 8, cudaMemcpyDeviceToDevice, pl->stream));
     CU_TRY(cudaMemsetAsync(pl->d_newton.p, 0, 3 * sizeof(unsigned long long), pl->stream));
     CU_TRY(cudaMemsetAsync(pl->d_sums.p, 0, pl->S * 4 * 8, pl->stream));
+    if (pl->mp) CU_TRY(cudaMemsetAsync(pl->d_member_j.p, 0, pl->R * 4, pl->stream));
     const double second = pl->implicit ? pl->red.dt / 2 : pl->red.dt;
     size_t ci = 0;
     for (const Chunk& c : pl->chunks) {
         mb::RunParams P = pl->base;
         P.j0 = c.j0; P.j1 = c.j1; P.k0 = c.k0; P.k1 = c.k1;
         const uint64_t ns = c.j1 - c.j0;
-        if (pl->use_table && ns > 0) {
+        if (pl->mp) {   // unit waveform, a margin of steps on either side (per-member schedules)
+            P.tab_j0 = c.j0 > kMpMargin ? c.j0 - kMpMargin : 0;
+            if (pl->use_table)
+                LAUNCH_TRY(mb::launch_field_table(pl->d_tab.p, P.tab_j0, c.j1 + kMpMargin - P.tab_j0, pl->red.dt, second,
+                                                  pl->field_shape, 1.0, pl->red.f, pl->stream));
+        } else if (pl->use_table && ns > 0) {
             LAUNCH_TRY(mb::launch_field_table(pl->d_tab.p, c.j0, ns, pl->red.dt, second, pl->field_shape, pl->red.h0,
                                               pl->red.f, pl->stream));
         }
@@ -851,7 +916,8 @@ int plan_fetch(magpy_b200_plan* pl, double* out_time, double* out_field, double*
         for (uint64_t k = 0; k < S; ++k) out_time[k] = ((double)(unsigned int)k * Ts) / rd.tau;
     if (out_field)
         for (uint64_t k = 0; k < S; ++k)
-            out_field[k] = applied_field(pl->field_shape, (double)(unsigned int)k * Ts, rd.h0, rd.f) * rd.H_k;
+            out_field[k] = pl->unit_field ? applied_field(pl->field_shape, (double)(unsigned int)k * Ts, 1.0, rd.f)
+                                          : applied_field(pl->field_shape, (double)(unsigned int)k * Ts, rd.h0, rd.f) * rd.H_k;
     if (out_sums) {
         CU_TRY(cudaMemcpyAsync(out_sums, pl->d_sums.p, S * 4 * 8, cudaMemcpyDeviceToHost, pl->stream));
         CU_TRY(cudaStreamSynchronize(pl->stream));
@@ -1158,6 +1224,29 @@ int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t par
                       : gauss_mode == MAGPY_B200_GAUSS_F32 ? mb::NOISE_PHILOX_F32 : mb::NOISE_PHILOX_PACKED;
     CU_TRY(mb::launch_gaussians(noise, (uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p));
     CU_TRY(cudaMemcpy(out, d.p, 3 * n_steps * 8, cudaMemcpyDeviceToHost));
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_gaussian_stats(int device, int64_t seed, uint64_t first_member, uint64_t n_members, uint64_t n_steps,
+                              int gauss_mode, uint64_t* hist, uint64_t* angle_hist, double* moments) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (!hist || !angle_hist || !moments || n_members == 0 || n_steps == 0) return fail(MAGPY_B200_ERR_BAD_ARG, "bad arguments");
+    if (n_members > 0x7FFFFFFFull) return fail(MAGPY_B200_ERR_BAD_ARG, "n_members too large");
+    DevBuf<unsigned long long> d_h, d_a;
+    DevBuf<double> d_m;
+    CU_TRY(d_h.alloc(4096));
+    CU_TRY(d_a.alloc(1024));
+    CU_TRY(d_m.alloc(5));
+    CU_TRY(cudaMemset(d_h.p, 0, 4096 * 8));
+    CU_TRY(cudaMemset(d_a.p, 0, 1024 * 8));
+    CU_TRY(cudaMemset(d_m.p, 0, 5 * 8));
+    const int noise = gauss_mode == MAGPY_B200_GAUSS_F64 ? mb::NOISE_PHILOX_F64
+                      : gauss_mode == MAGPY_B200_GAUSS_F32 ? mb::NOISE_PHILOX_F32 : mb::NOISE_PHILOX_PACKED;
+    CU_TRY(mb::launch_gauss_stats(noise, (uint64_t)seed, first_member, n_members, n_steps, d_h.p, d_a.p, d_m.p));
+    CU_TRY(cudaMemcpy(hist, d_h.p, 4096 * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(angle_hist, d_a.p, 1024 * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(moments, d_m.p, 5 * 8, cudaMemcpyDeviceToHost));
     return MAGPY_B200_OK;
 }
 

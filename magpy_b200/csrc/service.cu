@@ -181,6 +181,75 @@ __global__ void gaussians_kernel(uint64_t seed, uint32_t member, uint32_t partic
     out[3 * i] = g.x; out[3 * i + 1] = g.y; out[3 * i + 2] = g.z;
 }
 
+// Moments and histograms of the Gaussian stream, accumulated on the device so that the statistical tests can look at
+// 1e9+ draws (tail probabilities, Kolmogorov-Smirnov, uniformity of the Box-Muller angle): thread = member, loop over
+// steps, 3 draws per step exactly as the integration kernels consume them.
+constexpr int GS_BINS = 4096, GS_ANGLE_BINS = 1024;
+template <int GAUSS_MODE>
+__global__ void __launch_bounds__(256) gauss_stats_kernel(uint64_t seed, uint64_t first_member, uint64_t n_members,
+                                                          uint64_t n_steps, unsigned long long* hist,
+                                                          unsigned long long* angle_hist, double* moments) {
+    __shared__ unsigned int sh[GS_BINS], sa[GS_ANGLE_BINS];
+    __shared__ double red[8 * 5];
+    for (int i = threadIdx.x; i < GS_BINS; i += blockDim.x) sh[i] = 0;
+    for (int i = threadIdx.x; i < GS_ANGLE_BINS; i += blockDim.x) sa[i] = 0;
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s1 = 0, s2 = 0, s3 = 0, s4 = 0, mx = 0;
+    if (t < n_members) {
+        const uint32_t member = (uint32_t)(first_member + t);
+        for (uint64_t step = 1; step <= n_steps; ++step) {
+            const Gauss3 g = philox_gauss3<GAUSS_MODE>((uint32_t)seed, (uint32_t)(seed >> 32), step, 0u, member);
+            const double v[3] = {g.x, g.y, g.z};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const double z = v[q], z2 = z * z;
+                s1 += z; s2 += z2; s3 += z2 * z; s4 += z2 * z2;
+                mx = fmax(mx, fabs(z));
+                int b = (int)floor((z + 8.0) * 256.0);
+                b = b < 0 ? 0 : (b >= GS_BINS ? GS_BINS - 1 : b);
+                atomicAdd(&sh[b], 1u);
+            }
+            // (x, y) of one Box-Muller pair: every step in the 32-bit / fp64 modes, the even (0-based) steps of the packed one
+            if (GAUSS_MODE != 3 || ((step - 1) & 1) == 0) {
+                // fraction of a revolution, shifted by half a step of the packed mode's 2^18-direction grid so that no grid
+                // direction sits on a bin edge (every bin then holds exactly 256 of them)
+                double a = atan2(g.y, g.x) * 0.15915494309189535;
+                a = a - floor(a) + 1.9073486328125e-06;
+                const int b = ((int)(a * GS_ANGLE_BINS)) & (GS_ANGLE_BINS - 1);
+                atomicAdd(&sa[b], 1u);
+            }
+        }
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3); s4 = warp_sum(s4);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp * 5] = s1; red[warp * 5 + 1] = s2; red[warp * 5 + 2] = s3; red[warp * 5 + 3] = s4; red[warp * 5 + 4] = mx; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double a = 0;
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) a += red[w * 5 + threadIdx.x];
+        atomicAdd(moments + threadIdx.x, a);
+    } else if (threadIdx.x == 4) {
+        double a = 0;
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) a = fmax(a, red[w * 5 + 4]);
+        // max of non-negative doubles = max of their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(moments + 4), (unsigned long long)__double_as_longlong(a));
+    }
+    for (int i = threadIdx.x; i < GS_BINS; i += blockDim.x) if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+    for (int i = threadIdx.x; i < GS_ANGLE_BINS; i += blockDim.x) if (sa[i]) atomicAdd(angle_hist + i, (unsigned long long)sa[i]);
+}
+
+cudaError_t launch_gauss_stats(int noise, uint64_t seed, uint64_t first_member, uint64_t n_members, uint64_t n_steps,
+                               unsigned long long* hist, unsigned long long* angle_hist, double* moments) {
+    const unsigned g = (unsigned)((n_members + 255) / 256);
+    if (noise == NOISE_PHILOX_PACKED) gauss_stats_kernel<NOISE_PHILOX_PACKED><<<g, 256>>>(seed, first_member, n_members, n_steps, hist, angle_hist, moments);
+    else if (noise == NOISE_PHILOX_F64) gauss_stats_kernel<NOISE_PHILOX_F64><<<g, 256>>>(seed, first_member, n_members, n_steps, hist, angle_hist, moments);
+    else gauss_stats_kernel<NOISE_PHILOX_F32><<<g, 256>>>(seed, first_member, n_members, n_steps, hist, angle_hist, moments);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_field_table(double* tab, uint64_t j0, uint64_t n_steps, double dt, double second_offset, int shape,
                                double h0, double f_red, cudaStream_t s) {
     field_table_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, s>>>(tab, j0, n_steps, dt, second_offset, shape, h0, f_red);

@@ -157,9 +157,17 @@ class EnsembleModel:
         if return_trajectories is None:
             return_trajectories = (hi - lo) * N * 3 * int(max_samples) * 8 <= _TRAJ_BYTES_AUTO
 
-        # per-member radii / temperatures of single-particle members go to the device as arrays too (one launch for a size
-        # distribution or a temperature sweep)
-        fast = _PER_MEMBER_FAST + (('radius', 'temperature') if N == 1 else ())
+        # per-member radii / temperatures / anisotropy constants / damping / field amplitudes of single-particle members go
+        # to the device as arrays too (one launch for a size or anisotropy distribution, a temperature or amplitude sweep).
+        # Anisotropy and damping change the member's time scale; the library evaluates each member's own schedule but not
+        # a square wave's switching instants per member, so with a square field they fall back to one group per value.
+        fast = _PER_MEMBER_FAST
+        if N == 1:
+            fast += ('radius', 'temperature')
+            if gauss == 'f32p':      # the per-member-parameter kernels exist for the production noise mode
+                fast += ('field_amplitude',)
+                if base['field_shape'] != 'square' and 'field_shape' not in self._overrides:
+                    fast += ('anisotropy', 'damping')
         other_keys = [k for k in self._overrides if k not in fast]
         if other_keys:
             groups = {}
@@ -180,13 +188,20 @@ class EnsembleModel:
         sums = np.zeros((S, 4))
         state = dict(time=None, field=None, traj=traj, final=final, sums=sums)
         group_fields, group_of = [], np.zeros(hi - lo, dtype=np.int64)   # the applied field each member saw
+        member_amp = None
+        if N == 1 and 'field_amplitude' in self._overrides and 'field_amplitude' in fast:
+            # the library returns the waveform for 1 A/m; member i saw field_amplitude[i] times it
+            member_amp = np.asarray([self._overrides['field_amplitude'][i] for i in range(lo, hi)], dtype=np.float64)
         pending = []
 
         def consume(out, idx):
             if state['time'] is None:
                 state['time'], state['field'] = out['time'], out['field']
+                if member_amp is not None:   # the ensemble-level field is member 0's, as the reference's results[0].field
+                    state['field'] = out['field'] * member_amp[idx[0] - lo]
             if single:
                 state['traj'], state['final'], state['sums'] = out['trajectories'], out['final'], out['sums']
+                group_fields.append(out['field'])
             else:
                 if return_trajectories:
                     state['traj'][idx - lo] = out['trajectories']
@@ -224,11 +239,17 @@ class EnsembleModel:
             temperature = params['temperature']
             if N == 1 and 'temperature' in self._overrides:
                 temperature = np.asarray([self._overrides['temperature'][i] for i in idx], dtype=np.float64)
-            args = (radius, params['anisotropy'], member_array('anisotropy_axis'),
+
+            def member_scalar(key, column=False):
+                if key in self._overrides and key in fast:
+                    v = np.asarray([np.asarray(self._overrides[key][i], dtype=np.float64).reshape(-1)[0] for i in idx])
+                    return np.ascontiguousarray(v.reshape(len(idx), 1) if column else v)
+                return params[key]
+            args = (radius, member_scalar('anisotropy', True), member_array('anisotropy_axis'),
                     member_array('magnetisation_direction'), params['location'], params['magnetisation'],
-                    params['damping'], temperature, renorm, interactions, implicit_solve, time_step,
+                    member_scalar('damping'), temperature, renorm, interactions, implicit_solve, time_step,
                     end_time, S, seeds[lo:hi] if single else seeds[idx], params['field_shape'],
-                    params['field_amplitude'], params['field_frequency'], implicit_tol)
+                    member_scalar('field_amplitude'), params['field_frequency'], implicit_tol)
             kwargs = dict(device=device, return_trajectories=return_trajectories,
                           return_sums=True, return_final=True, gauss=gauss, implicit_newton=implicit_newton)
             if single:
@@ -253,8 +274,10 @@ class EnsembleModel:
         if comm is not None and not reduced_on_device:
             comm.allreduce_sums(sums)
         member_fields = None
-        if len(group_fields) > 1 and any(not np.array_equal(f, group_fields[0]) for f in group_fields[1:]):
-            member_fields = (np.stack(group_fields), group_of)   # members see different fields: keep each one's own
+        if member_amp is not None:
+            member_fields = (np.stack(group_fields), group_of, member_amp)
+        elif len(group_fields) > 1 and any(not np.array_equal(f, group_fields[0]) for f in group_fields[1:]):
+            member_fields = (np.stack(group_fields), group_of, None)   # members see different fields: keep each one's own
         return EnsembleResults.from_arrays(time, field, R, trajectories=traj, sums=sums, final=final, stats=stats,
                                            member_fields=member_fields)
 

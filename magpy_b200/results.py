@@ -76,7 +76,7 @@ _trapezoid = getattr(np, 'trapezoid', None) or np.trapz   # NumPy >= 2.0 / 1.x (
 
 class _LazyResults:
     """Sequence of per-member ``Results`` views over one [R, N, 3, S] array.  `member_fields` = (fields [G, S],
-    group index of every member [R]) when the members do not all see the same applied field (an ensemble whose
+    group index of every member [R], per-member amplitude [R] or None) when the members do not all see the same applied field (an ensemble whose
     members differ in field amplitude / frequency / shape): member i then reports its own field, as the reference's
     per-member ``Results`` do."""
     def __init__(self, time, field, traj, member_fields=None):
@@ -97,8 +97,10 @@ class _LazyResults:
         N = block.shape[0]
         field = self._field
         if self._member_fields is not None:
-            fields, group_of = self._member_fields
+            fields, group_of, scale = self._member_fields
             field = fields[group_of[i]]
+            if scale is not None:      # per-member field amplitudes: `fields` holds the waveform for 1 A/m
+                field = field * scale[i]
         return Results(self._time, field,
                        {p: block[p, 0] for p in range(N)},
                        {p: block[p, 1] for p in range(N)},

@@ -113,6 +113,28 @@ int ref_simulate(size_t N, const double* radius, const double* anisotropy, const
     return 0;
 }
 
+// simulation::full_dynamics followed by the reference's own simulation::save_results (lib/simulation.cpp:38-63) for
+// particle `particle`: writes prefix.mx / .my / .mz / .field / .time — the on-disk format magpy_b200.results.load_results
+// must read.
+int ref_simulate_and_save(size_t N, const double* radius, const double* anisotropy, const double* axis,
+                          const double* m0, const double* location, double Ms, double alpha, double T,
+                          int renorm, int interactions, int use_implicit, double eps, double dt, double t_end,
+                          size_t S, long seed, int field_shape, double H0, double f, size_t particle,
+                          const char* prefix) {
+    if (openblas_set_num_threads) openblas_set_num_threads(1);
+    try {
+        std::vector<double> r(radius, radius + N), k(anisotropy, anisotropy + N);
+        auto res = simulation::full_dynamics(r, k, to_d3(axis, N), to_d3(m0, N), to_d3(location, N), Ms,
+                                             alpha, T, renorm != 0, interactions != 0, use_implicit != 0,
+                                             eps, dt, t_end, S, seed, (field::options)field_shape, H0, f);
+        if (particle >= res.size()) return 2;
+        simulation::save_results(std::string(prefix), res[particle]);
+    } catch (const std::exception&) {
+        return 1;
+    }
+    return 0;
+}
+
 // Ensemble of R independent calls of the unmodified SI full_dynamics, one per
 // seed, spread over host threads by an OpenMP pragma that is OURS (best-case
 // CPU harness).  Per-member m0/axis are optional

@@ -133,7 +133,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  *         with a ~1e-5 tolerance); mode 1: fp64 Box-Muller from 53-bit uniforms, two blocks;
  * mode 2: packed fp32 Box-Muller — ONE block, counter word 0 = (step-1)>>1, key word 0 =
  *         particle | 2<<24, feeds the two steps 2b+1, 2b+2: the 128 bits w0:w1:w2:w3 are cut
- *         into three (24-bit radius field of which the top 23 bits are used, 18-bit angle)
+ *         into three (24-bit radius field of which the top 22 bits are used as cell midpoints, 18-bit angle)
  *         pairs -> six draws, the first three for the odd `step` (1-based), the last three
  *         for the even one. */
 static float u32_to_float_rz(uint32_t x) { /* cvt.rz.f32.u32 */
@@ -145,7 +145,7 @@ static float u32_to_float_rz(uint32_t x) { /* cvt.rz.f32.u32 */
 }
 
 static void bm_pair_packed(uint32_t r23, uint32_t a18, float* c, float* s) {
-    const float u = 2.0f - (1.0f + (float)r23 * 1.1920928955078125e-07f);       /* 1 - k 2^-23, in (0, 1] */
+    const float u = 2.0f - (1.0f + (float)(r23 | 1u) * 1.1920928955078125e-07f); /* (k + 1/2) 2^-22: cell midpoints */
     const float r = sqrtf(log2f(u) * -1.3862943611198906f);
     const float a = (1.0f + (float)a18 * 3.814697265625e-06f) * 6.283185307179586f; /* 2 pi (1 + k 2^-18) */
     *c = r * cosf(a);

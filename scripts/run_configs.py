@@ -4,7 +4,7 @@
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 scripts/run_configs.py
 
 Under torchrun every rank integrates its contiguous slice of the members (magpy_b200.sharding) and the
-ensemble sums are all-reduced once (NCCL).  Times are the library's CUDA-event device times, max over ranks.
+ensemble sums are all-reduced once (ncclAllReduce issued by libmagpy_b200).  Times are the library's CUDA-event device times, max over ranks.
 """
 import json
 import os
@@ -19,15 +19,10 @@ sys.path.insert(0, ROOT)
 rank = int(os.environ.get('RANK', '0'))
 local_rank = int(os.environ.get('LOCAL_RANK', '0'))
 world = int(os.environ.get('WORLD_SIZE', '1'))
-dist = None
-if world > 1:
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
 import magpy_b200 as mp  # noqa: E402
-from magpy_b200 import geometry  # noqa: E402
+from magpy_b200 import core, geometry  # noqa: E402
+
+comm = core.Comm.from_env(local_rank) if world > 1 else None   # the library's own NCCL communicator
 
 
 ONLY = [a for a in sys.argv[1:] if a.startswith('C')]   # e.g. `run_configs.py C4` runs config 4 alone
@@ -42,14 +37,12 @@ def run(name, model, R, end_time, time_step, S, implicit, traj=False, **kw):
     for _ in range(2):   # first pass warms the context / memory pool
         t0 = time.perf_counter()
         out = ens.simulate(end_time, time_step, S, 1001, implicit_solve=implicit, device=local_rank, shard=shard,
-                           return_trajectories=traj, **kw)
+                           comm=comm, return_trajectories=traj, **kw)
         wall = time.perf_counter() - t0
     st = out.stats[0]
     ms = st['device_ms']
-    if dist is not None:
-        t = torch.tensor([ms, wall], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, wall = float(t[0]), float(t[1])
+    if comm is not None:
+        ms, wall = comm.allreduce(np.array([ms, wall]), 'max')
     N = len(np.atleast_1d(model.radius))
     total = R * N * st['steps_per_member']
     if rank == 0:
@@ -81,5 +74,5 @@ run('C4 64-particle clusters Heun 100k x 10000 steps', cluster, 100000, 1e-10, 1
 single = mp.Model([12e-9], [4e4], [[0, 0, 1.0]], [[1.0, 0, 0]], [[0, 0, 0]], 4e5, 0.1, 300.0)
 run('C5 single implicit 1M x 1000 steps', single, 1000000, 1e-9, 1e-12, 101, True)
 
-if dist is not None:
-    dist.destroy_process_group()
+if comm is not None:
+    comm.barrier()

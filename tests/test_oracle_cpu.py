@@ -361,3 +361,34 @@ def test_dom_oracle_matches_compiled_reference_live(orc):
         b = ol.dom_simulate(ref, reference=True, **kw)
         assert np.array_equal(a[0], b[0]) and np.allclose(a[1], b[1], rtol=1e-15, atol=0)
         assert np.abs(a[2] - b[2]).max() <= 1e-13
+
+
+def test_load_results_reads_files_written_by_the_reference(tmp_path):
+    """`magpy_b200.results.load_results` reads what the reference's own
+    `simulation::save_results` (lib/simulation.cpp:38-63, include/io.hpp:12-27) writes — the committed golden files
+    (tests/golden/reference_saved.*, generator make_golden_saved_results.py) and, when the compiled reference is
+    present, a file it writes live; and `save_results` writes byte-identical files back."""
+    import sys
+    from magpy_b200.results import load_results, save_results
+    golden = os.path.join(HERE, 'golden')
+    sys.path.insert(0, golden)
+    import make_golden_saved_results as mg
+    orc = ol.load_oracle()
+    c = ol.make_case(**mg.CASE)
+    t, fl, m, _, _ = ol.oracle_simulate(orc, c, seed=mg.SEED)
+    prefixes = [os.path.join(golden, 'reference_saved')]
+    ref = ol.load_reference()
+    if ref is not None:
+        ref.ref_simulate_and_save.restype = C.c_int
+        mg.write(str(tmp_path / 'live'), ref)
+        prefixes.append(str(tmp_path / 'live'))
+    for prefix in prefixes:
+        res = load_results(prefix)
+        assert res.N == 1 and len(res.time) == c.S
+        # bit-for-bit the trajectory of particle 1 of the reference run (the oracle is pinned to it bitwise)
+        assert np.array_equal(res.time, t) and np.array_equal(res.field, fl)
+        assert np.array_equal(res.x[0], m[mg.PARTICLE, 0]) and np.array_equal(res.y[0], m[mg.PARTICLE, 1])
+        assert np.array_equal(res.z[0], m[mg.PARTICLE, 2])
+        save_results(str(tmp_path / 'again'), res)
+        for suffix in ('mx', 'my', 'mz', 'field', 'time'):
+            assert open('%s.%s' % (prefix, suffix), 'rb').read() == open(str(tmp_path / 'again') + '.' + suffix, 'rb').read()

@@ -320,6 +320,76 @@ def test_per_member_radii_single_particle(orc, core, implicit):
     assert len(ens_t.simulate(base.t_end, base.dt, base.S, 1001, implicit_solve=implicit).stats) == 1
 
 
+@pytest.mark.parametrize('implicit', [False, True])
+@pytest.mark.parametrize('shape', ['sine', 'constant'])
+def test_per_member_material_parameters_single_particle(orc, core, implicit, shape):
+    """Anisotropy, damping, field amplitude (next to radius and temperature) per member in ONE launch — the
+    reference's `EnsembleModel(N, base, anisotropy=[...], damping=[...], ...)` (magpy/model.py:146-156).  Anisotropy
+    and damping change the member's reduced time scale, so every thread runs its own dt, noise amplitude and
+    zero-order-hold schedule; each member is checked against the oracle run with its own parameters and the reference's
+    Wiener stream of its seed.  t_end / dt / (S - 1) is an integer here: every sampling time is an exact tie of the
+    schedule, where the members' step counts differ by rounding alone (the reference's per-member outcome is the bar)."""
+    rng = np.random.default_rng(11)
+    R = 48
+    K = rng.uniform(2e4, 9e4, R)
+    al = rng.uniform(0.05, 0.5, R)
+    H0 = rng.uniform(0.0, 3e4, R)
+    rad = rng.uniform(5e-9, 9e-9, R)
+    T = rng.uniform(150.0, 400.0, R)
+    seeds = np.arange(1, R + 1) * 41
+    base = ol.make_case(N=1, dt=1e-13 if not implicit else 1e-12, t_end=2.4e-11 if not implicit else 1.12e-10, S=17,
+                        implicit=implicit, field_shape=shape, H0=1.5e4, f=5e9, axis=[[0.6, 0, 0.8]], m0=[[0, 0, 1.0]])
+    cases = [ol.Case(dict(base, radius=np.array([rad[i]]), anisotropy=np.array([K[i]]), alpha=float(al[i]), H0=float(H0[i]),
+                          T=float(T[i]))) for i in range(R)]
+    steps = np.array([ol.steps_executed(orc, c) for c in cases])
+    assert len(set(steps.tolist())) > 1, 'the members should not all share one schedule (exact ties)'
+    n_max = int(steps.max()) + 2
+    dW = np.stack([ol.mt_normal(orc, int(s), n_max * 3).reshape(n_max, 3) for s in seeds])
+    ref, newton = [], []
+    for c, s in zip(cases, seeds):
+        t, fl, m, it, fails = ol.oracle_simulate(orc, c, seed=int(s))
+        ref.append(m); newton.append(it)
+    ref = np.stack(ref)
+    out = core.simulate_ensemble(rad.reshape(R, 1), K.reshape(R, 1), base.axis, base.m0, base.location, base.Ms, al, T,
+                                 False, True, implicit, base.dt, base.t_end, base.S, seeds, field_shape=shape,
+                                 field_amplitude=H0, field_frequency=base.f, injected_dw=dW)
+    err = np.abs(out['trajectories'] - ref).max(axis=(1, 2, 3)) / base.Ms
+    assert err.max() <= TOL, (err.argmax(), err.max())
+    assert out['stats']['kernel_launches'] < 12
+    assert np.array_equal(out['final'], out['trajectories'][..., -1])      # no member steps past its own last sample
+    if implicit:   # identical iteration counts (the product skips each member's last, never-sampled step)
+        assert out['stats']['newton_iterations'] == sum(n[0] - n[2] for n in newton)
+    # the field every member saw: unit waveform times its amplitude
+    if shape == 'sine':
+        assert np.allclose(out['field'] * H0[3], ol.oracle_simulate(orc, cases[3], seed=1)[1], rtol=1e-12, atol=1e-9)
+    # each parameter alone also rides on the per-member arrays
+    for kw in (dict(anisotropy=K[:8].reshape(8, 1)), dict(damping=al[:8]), dict(field_amplitude=H0[:8])):
+        a = dict(anisotropy=base.anisotropy, damping=base.alpha, field_amplitude=base.H0)
+        a.update(kw)
+        one = core.simulate_ensemble(base.radius, a['anisotropy'], base.axis, base.m0, base.location, base.Ms, a['damping'],
+                                     base.T, False, True, implicit, base.dt, base.t_end, base.S, seeds[:8], field_shape=shape,
+                                     field_amplitude=a['field_amplitude'], field_frequency=base.f, injected_dw=dW[:8])
+        i = 5
+        ci = ol.Case(dict(base, anisotropy=np.array([K[i]]) if 'anisotropy' in kw else base.anisotropy,
+                          alpha=float(al[i]) if 'damping' in kw else base.alpha,
+                          H0=float(H0[i]) if 'field_amplitude' in kw else base.H0))
+        want = ol.oracle_simulate(orc, ci, seed=int(seeds[i]))[2]
+        assert np.abs(one['trajectories'][i] - want).max() / base.Ms <= TOL, list(kw)
+    # through the public API: one device call for the whole distribution, Philox noise
+    import magpy_b200 as mp
+    model = mp.Model(np.array([7e-9]), base.anisotropy, base.axis, base.m0, base.location, base.Ms, base.alpha, base.T,
+                     field_shape=shape, field_frequency=base.f, field_amplitude=base.H0)
+    ens = mp.EnsembleModel(R, model, anisotropy=[np.array([k]) for k in K], damping=list(al), field_amplitude=list(H0),
+                           radius=[np.array([r]) for r in rad])
+    res = ens.simulate(base.t_end, base.dt, base.S, 1001, implicit_solve=implicit)
+    assert len(res.stats) == 1
+    assert np.allclose(res.results[7].field, res.results[0].field * (H0[7] / H0[0]) if shape == 'sine' else H0[7])
+    with pytest.raises(ValueError):     # the square wave's switching instants depend on the member's time scale
+        core.simulate_ensemble(base.radius, K.reshape(R, 1), base.axis, base.m0, base.location, base.Ms, base.alpha, base.T,
+                               False, True, implicit, base.dt, base.t_end, base.S, seeds, field_shape='square',
+                               field_amplitude=1e4, field_frequency=base.f)
+
+
 def test_single_simulate_api_and_schedule_edges(orc, core):
     """core.simulate keeps the reference's dict; sampling finer than the time step repeats states."""
     c = ol.make_case(N=2, dt=1e-12, t_end=1e-11, S=40, implicit=False)    # Ts < dt: zero-order hold repeats
