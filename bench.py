@@ -182,6 +182,47 @@ def load_cpu_reference():
     return 'port', cores, run
 
 
+def _joblib_member(seed, w, arr):
+    """One ensemble member the way the reference runs it: one `simulation::full_dynamics` call (magpy/core.pyx:149-185)
+    in a worker process, the result dict pickled back to the parent (magpy/model.py:204-207)."""
+    import ctypes as C
+    lib = _joblib_member.lib = getattr(_joblib_member, 'lib', None) or C.CDLL(os.path.join(ROOT, 'oracle', '_ref', 'libmagpy_ref.so'))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    N, S = w['N'], w['S']
+    t, fl, m = np.zeros(S), np.zeros(S), np.zeros((N, 3, S))
+    rc = lib.ref_simulate(C.c_size_t(N), P(arr['radius']), P(arr['anisotropy']), P(arr['axis']), P(arr['m0']), P(arr['location']),
+                          C.c_double(w['Ms']), C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0),
+                          C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(S), C.c_long(int(seed)),
+                          C.c_int({'sine': 0, 'square': 1, 'constant': 2}[w['field_shape']]), C.c_double(w['H0']),
+                          C.c_double(w['f']), P(t), P(fl), P(m))
+    if rc != 0:
+        raise RuntimeError('reference full_dynamics failed')
+    return {'N': N, 'time': t, 'field': fl, 'x': {i: m[i, 0] for i in range(N)}, 'y': {i: m[i, 1] for i in range(N)},
+            'z': {i: m[i, 2] for i in range(N)}}
+
+
+def cpu_sample_joblib(cores, n_steps, target_seconds):
+    """BASELINE.md section 3 baseline (i), the reference's NATIVE fan-out: a joblib (loky) process pool with one
+    `full_dynamics` call per member and the per-member results pickled back, warm pool (first batch discarded), timed
+    from the parent.  The member function is the compiled, unmodified reference; the reference's own Python package
+    cannot travel to the GPU box, so the pool is driven from here (scripts/reference_native_baseline.py runs the real
+    `magpy.EnsembleModel.simulate(n_jobs=...)` in the build container for comparison)."""
+    from joblib import Parallel, delayed
+    w, arr = WORKLOAD, workload_arrays(1)
+    seeds = member_seeds(1 << 16, w['random_state'])
+    with Parallel(n_jobs=cores) as pool:
+        pool(delayed(_joblib_member)(s, w, arr) for s in seeds[:cores])          # spawns and warms the workers (discarded)
+        t0 = time.perf_counter()
+        pool(delayed(_joblib_member)(s, w, arr) for s in seeds[:2 * cores])      # calibration
+        per_member = (time.perf_counter() - t0) / 2
+        n = int(max(cores, min(len(seeds), cores * max(1, round(target_seconds / max(per_member, 1e-3))))))
+        t0 = time.perf_counter()
+        res = pool(delayed(_joblib_member)(s, w, arr) for s in seeds[:n])
+        el = time.perf_counter() - t0
+    mz = np.mean([r['z'][0][-1] for r in res])
+    return w['N'] * n * n_steps / el, n, el, float(mz)
+
+
 def _host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -399,9 +440,20 @@ def ours(args):
         if world > 1:
             raise RuntimeError('timed at N=1 only (see the N=1 line and --impl reference)')
         kind, cores, run = load_cpu_reference()
-        v, n, el = cpu_sample(run, cores, n_steps + 1, 12.0)
+        v, n, el = cpu_sample(run, cores, n_steps + 1, 10.0)
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind,
-               'sample': '%d realisations x %d Heun steps of the same workload in %.1f s' % (n, n_steps + 1, el)}
+               'sample': '%d realisations x %d Heun steps of the same workload in %.1f s' % (n, n_steps + 1, el),
+               'fanout': 'OpenMP pragma in our harness around the unmodified full_dynamics (BASELINE.md section 3, baseline ii)'}
+        if kind == 'reference':
+            try:   # baseline (i): the reference's native joblib process pool; `value` stays the larger of the two
+                vj, nj, elj, _ = cpu_sample_joblib(cores, n_steps + 1, 8.0)
+                cpu['joblib'] = {'value': vj, 'unit': UNIT, 'cores': cores,
+                                 'sample': '%d realisations x %d Heun steps in %.1f s, warm loky pool, results pickled '
+                                           'back per member (magpy/model.py:204-207)' % (nj, n_steps + 1, elj)}
+                if vj > cpu['value']:
+                    cpu['value'], cpu['fanout'] = vj, 'joblib process pool (baseline i)'
+            except Exception as exc:
+                cpu['joblib'] = {'value': None, 'error': str(exc)}
     except Exception as exc:   # the baseline is reported, never required for the GPU number
         cpu = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'unavailable', 'sample': str(exc)}
 

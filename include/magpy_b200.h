@@ -63,6 +63,11 @@ typedef struct magpy_b200_stats {
     uint64_t kernel_variant;       /* heun_single: resident CTAs per SM asked of the register allocator — 1 (free: 6
                                       CTAs of 128 threads) or 7 (when the shard fits one wave of 7 per SM but not
                                       one of 6); 0 for the other kernels (ABI v4)                             */
+    /* host wall-clock of the blocking entry points (magpy_b200_simulate_ensemble[_multi]), ms (ABI v4): */
+    double host_setup_ms;          /* plan creation: validation, schedule, allocations, uploads             */
+    double host_run_ms;            /* launch + wait for the device                                          */
+    double host_fetch_ms;          /* layout kernels + device->host copies into the caller's arrays         */
+    double host_total_ms;          /* the whole call, including the release of the plan                     */
 } magpy_b200_stats;
 
 /* integration kernels (magpy_b200/csrc): reported in magpy_b200_stats.kernel_family */
@@ -176,6 +181,18 @@ int magpy_b200_device_count(int* count);
 /* Device buffers of finished calls stay cached in the device's stream-ordered memory pool so
  * that repeated calls do not pay cudaMalloc/cudaFree again; this returns them to the driver. */
 int magpy_b200_release_cached_memory(int device);
+
+/* Page-locked host buffers for OUTPUT arrays.  A device->host copy into pageable memory that has never been touched (a
+ * fresh numpy.empty, a fresh std::vector) runs at ~5 GB/s on the B200 box: the driver stages it and every 4 KB page
+ * faults on first write (profiles/r02_probe_e2e_small.log: 24 MB in 5.5 ms, 2.5 GB in 510 ms).  Into these buffers the
+ * same copy is one DMA transfer at PCIe speed.  Freed blocks stay in a size-bucketed cache (at most
+ * MAGPY_B200_PINNED_CACHE_MB, default 8192) so that repeated calls do not pay the pinning again;
+ * magpy_b200_host_cache_release returns them to the system.  The Cython layer allocates the trajectory / final-state
+ * arrays it returns from here (numpy arrays that own their block).  Replaces the element-wise copies into fresh numpy
+ * arrays of magpy/core.pyx:186-203. */
+int magpy_b200_host_alloc(size_t bytes, void** ptr);
+int magpy_b200_host_free(void* ptr);
+int magpy_b200_host_cache_release(void);
 
 /* physical constants exactly as include/constants.hpp:10-12 (replaces
  * core.get_KB / get_mu0 / get_gamma, magpy/core.pyx:29-34) */

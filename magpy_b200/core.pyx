@@ -48,6 +48,10 @@ cdef extern from "magpy_b200.h" nogil:
         uint64_t d2h_bytes
         uint64_t kernel_family
         uint64_t kernel_variant
+        double host_setup_ms
+        double host_run_ms
+        double host_fetch_ms
+        double host_total_ms
 
     ctypedef struct magpy_b200_ensemble:
         uint32_t abi_version
@@ -101,6 +105,9 @@ cdef extern from "magpy_b200.h" nogil:
         pass
 
     int MAGPY_B200_ERR_COMM
+    int magpy_b200_host_alloc(size_t bytes, void** ptr)
+    int magpy_b200_host_free(void* ptr)
+    int magpy_b200_host_cache_release()
     int magpy_b200_comm_unique_id(unsigned char* id)
     int magpy_b200_comm_create(const unsigned char* id, int rank, int world_size, int device, magpy_b200_comm** comm)
     int magpy_b200_comm_create_from_env(int device, magpy_b200_comm** comm)
@@ -137,6 +144,57 @@ cdef extern from "magpy_b200.h" nogil:
     int magpy_b200_fp64_mma_peak(int, double*)
     int magpy_b200_simulate_dom(int, size_t, const double*, const double*, const double*, double, double, double, double,
                                 double, size_t, int, double, double, size_t, double*, double*, double*, uint64_t*)
+
+
+cdef extern from "Python.h":
+    void Py_INCREF(object)
+
+
+cdef class _PinnedBlock:
+    """Owner of one page-locked host block (magpy_b200_host_alloc); returns it to the library's cache when the numpy
+    array built on it is garbage collected."""
+    cdef void* p
+
+    def __cinit__(self):
+        self.p = NULL
+
+    def __dealloc__(self):
+        if self.p != NULL:
+            magpy_b200_host_free(self.p)
+            self.p = NULL
+
+
+import os as _os
+_PINNED_MIN_BYTES = 1 << 20
+
+
+cdef object _output_array(tuple shape):
+    """float64 output array for a device->host copy: page-locked (one DMA transfer, no first-touch page faults) when it
+    is large enough to matter and pinned memory is available, else a plain numpy.empty.  MAGPY_B200_PINNED_OUTPUTS=0
+    switches the pinned path off."""
+    cdef size_t n = 8
+    for d in shape:
+        n *= <size_t> d
+    if n < _PINNED_MIN_BYTES or _os.environ.get('MAGPY_B200_PINNED_OUTPUTS', '1') == '0':
+        return np.empty(shape)
+    cdef void* p = NULL
+    if magpy_b200_host_alloc(n, &p) != 0 or p == NULL:
+        return np.empty(shape)
+    cdef _PinnedBlock blk = _PinnedBlock()
+    blk.p = p
+    cdef np.npy_intp dims[8]
+    cdef int nd = len(shape)
+    for i in range(nd):
+        dims[i] = shape[i]
+    cdef np.ndarray arr = np.PyArray_SimpleNewFromData(nd, dims, np.NPY_FLOAT64, p)
+    Py_INCREF(blk)
+    np.PyArray_SetBaseObject(arr, blk)
+    return arr
+
+
+def release_pinned_cache():
+    """Return the cached page-locked output blocks to the system."""
+    magpy_b200_host_cache_release()
 
 
 # field::options numbering (include/field.hpp:95-97, magpy/core.pyx:38-42)
@@ -178,6 +236,8 @@ cdef dict _stats_dict(magpy_b200_stats* st):
         'd2h_bytes': st.d2h_bytes,
         'kernel': _KERNEL_NAMES.get(st.kernel_family, 'unknown'),
         'kernel_variant': st.kernel_variant,
+        'host_setup_ms': st.host_setup_ms, 'host_run_ms': st.host_run_ms, 'host_fetch_ms': st.host_fetch_ms,
+        'host_total_ms': st.host_total_ms,
     }
 
 
@@ -495,7 +555,7 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
     e.a.out_time = &o_time[0]
     e.a.out_field = &o_field[0]
     if return_trajectories:
-        o_traj = np.empty((R, N, 3, S))
+        o_traj = _output_array((R, N, 3, S))
         e.trajectories = o_traj
         e.a.out_trajectories = &o_traj[0, 0, 0, 0]
     if return_sums:
@@ -503,7 +563,7 @@ cdef _EnsembleArgs _build_args(radius, anisotropy, anisotropy_axis, magnetisatio
         e.sums = o_sums
         e.a.out_sums = &o_sums[0, 0]
     if return_final:
-        o_final = np.empty((R, N, 3))
+        o_final = _output_array((R, N, 3))
         e.final = o_final
         e.a.out_final = &o_final[0, 0, 0]
     return e

@@ -162,10 +162,16 @@ __device__ __forceinline__ void cta_partial_sums(double v0, double v1, double v2
 constexpr int SINGLE_THREADS = 128;
 constexpr int CL_LANES = 32;
 
-// m / |m| (lib/simulation.cpp:379-387).  rsqrt() is MUFU.RSQ64H plus Newton steps, branch free and
-// accurate to 1 ulp; the literal 1/sqrt() costs a DSQRT and a DDIV with their slow-path calls.
+// m / |m| (lib/simulation.cpp:379-387).  After a step from a unit vector |m|^2 = 1 + d with a tiny d (Heun: ~|f|^4 / 4,
+// 6e-7 at the bench's step), so 1 / sqrt(1 + d) = 1 - d/2 + 3 d^2/8 - 5 d^3/16 to < 1.1e-15 for |d| < 2.5e-4: four
+// dependent FMAs instead of MUFU.RSQ64H + Newton steps + the fix-up code of rsqrt() (K1 with renorm: 2.05e11 -> see
+// profiles/r02_probe_renorm.log).  Anything further from 1 (first step of an unnormalised start, huge steps) takes
+// rsqrt(), which is branch free and accurate to 1 ulp; the literal 1/sqrt() costs a DSQRT and a DDIV with their
+// slow-path calls.
 __device__ __forceinline__ void renormalise(V3& m) {
-    const double inv = rsqrt(dot(m, m));
+    const double d = dot(m, m) - 1.0;
+    double inv = fma(d, fma(d, fma(d, -0.3125, 0.375), -0.5), 1.0);
+    if (fabs(d) >= 2.5e-4) inv = rsqrt(d + 1.0);
     m.x *= inv; m.y *= inv; m.z *= inv;
 }
 

@@ -6,11 +6,15 @@
 // and drives the kernels through the launchers of launch.h.  No CPU integration path exists here: without a
 // CUDA device every compute entry point fails with MAGPY_B200_ERR_NO_DEVICE.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <new>
 #include <string>
 #include <vector>
@@ -1013,6 +1017,95 @@ int magpy_b200_release_cached_memory(int device) {
     return MAGPY_B200_OK;
 }
 
+// ---- pinned host buffers for output arrays (cached by size) ----------------------------------------------------
+namespace {
+struct PinnedCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;     // rounded size -> block
+    std::unordered_map<void*, size_t> live;       // blocks handed out
+    size_t cached_bytes = 0;
+    size_t limit() const {
+        if (const char* env = std::getenv("MAGPY_B200_PINNED_CACHE_MB")) return (size_t)std::max(0ll, std::atoll(env)) << 20;
+        return (size_t)8192 << 20;
+    }
+} g_pinned;
+size_t pinned_round(size_t bytes) {
+    // 64 KiB granules up to 16 MiB, then 1/8 of the leading power of two: a freed block serves every request within 12.5 %
+    size_t g = 64 << 10;
+    while ((g << 3) < bytes) g <<= 1;
+    return (bytes + g - 1) / g * g;
+}
+}  // namespace
+
+int magpy_b200_host_alloc(size_t bytes, void** ptr) {
+    if (!ptr || bytes == 0) return fail(MAGPY_B200_ERR_BAD_ARG, "bad arguments");
+    *ptr = nullptr;
+    const size_t want = pinned_round(bytes);
+    {
+        std::lock_guard<std::mutex> lock(g_pinned.mu);
+        auto it = g_pinned.free_blocks.find(want);
+        if (it != g_pinned.free_blocks.end()) {
+            *ptr = it->second;
+            g_pinned.cached_bytes -= want;
+            g_pinned.free_blocks.erase(it);
+            g_pinned.live[*ptr] = want;
+            return MAGPY_B200_OK;
+        }
+    }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MAGPY_B200_ERR_NO_DEVICE, "no CUDA device available: no page-locked memory");
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+    if (e != cudaSuccess) {   // give the cache back and try once more
+        cudaGetLastError();
+        magpy_b200_host_cache_release();
+        e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MAGPY_B200_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lock(g_pinned.mu);
+    g_pinned.live[p] = want;
+    *ptr = p;
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_host_free(void* ptr) {
+    if (!ptr) return MAGPY_B200_OK;
+    size_t size = 0;
+    bool keep = false;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned.mu);
+        auto it = g_pinned.live.find(ptr);
+        if (it == g_pinned.live.end()) return fail(MAGPY_B200_ERR_BAD_ARG, "pointer was not returned by magpy_b200_host_alloc");
+        size = it->second;
+        g_pinned.live.erase(it);
+        if (g_pinned.cached_bytes + size <= g_pinned.limit()) {
+            g_pinned.free_blocks.emplace(size, ptr);
+            g_pinned.cached_bytes += size;
+            keep = true;
+        }
+    }
+    if (!keep) cudaFreeHost(ptr);
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_host_cache_release(void) {
+    std::vector<void*> blocks;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned.mu);
+        for (auto& kv : g_pinned.free_blocks) blocks.push_back(kv.second);
+        g_pinned.free_blocks.clear();
+        g_pinned.cached_bytes = 0;
+    }
+    for (void* p : blocks) cudaFreeHost(p);
+    return MAGPY_B200_OK;
+}
+
 int magpy_b200_plan_create(const magpy_b200_ensemble* args, magpy_b200_plan** plan) {
     if (!plan) return fail(MAGPY_B200_ERR_BAD_ARG, "plan is NULL");
     *plan = nullptr;
@@ -1067,16 +1160,30 @@ int magpy_b200_plan_destroy(magpy_b200_plan* plan) {
 }
 
 int magpy_b200_simulate_ensemble(const magpy_b200_ensemble* args, magpy_b200_stats* stats) {
+    using clk = std::chrono::steady_clock;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = clk::now();
     magpy_b200_plan* pl = nullptr;
     int rc = magpy_b200_plan_create(args, &pl);
     if (rc) return rc;
+    const auto t1 = clk::now();
     rc = plan_run(pl);
     if (!rc) rc = plan_sync(pl, nullptr);
+    const auto t2 = clk::now();
     if (!rc)
         rc = magpy_b200_plan_fetch(pl, args->out_time, args->out_field, args->out_trajectories, args->out_sums,
                                    args->out_final);
-    if (!rc) rc = plan_sync(pl, stats);
+    const auto t3 = clk::now();
+    magpy_b200_stats st;
+    if (!rc) rc = plan_sync(pl, &st);
     delete pl;
+    if (!rc && stats) {
+        st.host_setup_ms = ms(t0, t1);
+        st.host_run_ms = ms(t1, t2);
+        st.host_fetch_ms = ms(t2, t3);
+        st.host_total_ms = ms(t0, clk::now());
+        *stats = st;
+    }
     return rc;
 }
 
