@@ -79,6 +79,9 @@ typedef struct magpy_b200_stats {
 #define MAGPY_B200_KERNEL_IMID_CLUSTER 6     /* cluster.cu                                                   */
 #define MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA 7 /* cluster_mma.cu: dipolar field as a matrix product (DMMA)     */
 #define MAGPY_B200_KERNEL_IMID_SPLIT 8       /* small_imid.cu: one lane per particle (small ensembles, N = 2, 4) */
+#define MAGPY_B200_KERNEL_HEUN_CLUSTER_BIG 10 /* cluster_big.cu: Heun beyond 128 particles, moments in global memory      */
+#define MAGPY_B200_KERNEL_IMID_CLUSTER_MMA 9 /* cluster_mma_imid.cu: implicit midpoint, dipolar field of every quasi-Newton
+                                                iteration as a matrix product (DMMA), 8..128 particles             */
 
 /* One ensemble of `n_members` independent clusters that share geometry and material
  * (radius, anisotropy, location, Ms, damping, T, field) and may differ in anisotropy
@@ -294,6 +297,10 @@ int magpy_b200_philox_words(int device, const uint32_t ctr[4], const uint32_t ke
 /* the n Gaussian draws member `member` / particle `particle` consumes at `step` (3 values) */
 int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t particle, uint64_t first_step,
                          uint64_t n_steps, int gauss_mode, double* out /* [n_steps][3] */);
+/* the 3x3 solve of one particle's quasi-Newton update as the implicit kernels run it (adjugate / Cramer's rule in
+ * registers instead of dgesv's pivoted elimination, lib/optimisation.cpp:134): n systems A[n][9] (row major) x = b[n][3];
+ * ok[i] = 0 where the determinant is exactly zero (dgesv's info > 0) */
+int magpy_b200_solve3(int device, size_t n, const double* A, const double* b, double* x, int* ok);
 /* Statistics of the Gaussian stream accumulated on the device (for tests at 1e9+ draws against lib/rng.cpp:14-24's
  * N(0,1)): n_members threads (members first_member ...) x n_steps steps x 3 draws, consumed exactly as the integration
  * kernels do.  hist[4096]: counts in bins of width 1/256 over [-8, 8); angle_hist[1024]: direction of the (x, y) pairs

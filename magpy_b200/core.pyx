@@ -139,6 +139,7 @@ cdef extern from "magpy_b200.h" nogil:
     int magpy_b200_schedule(double, double, size_t, uint64_t*)
     int magpy_b200_philox_words(int, const uint32_t*, const uint32_t*, uint32_t*)
     int magpy_b200_gaussians(int, int64_t, uint64_t, uint32_t, uint64_t, uint64_t, int, double*)
+    int magpy_b200_solve3(int, size_t, const double*, const double*, double*, int*)
     int magpy_b200_gaussian_stats(int, int64_t, uint64_t, uint64_t, uint64_t, int, uint64_t*, uint64_t*, double*)
     int magpy_b200_fp64_peak(int, double*, double*)
     int magpy_b200_fp64_mma_peak(int, double*)
@@ -219,7 +220,7 @@ cdef _raise(int rc):
 
 
 _KERNEL_NAMES = {1: 'heun_single', 2: 'imid_single', 3: 'heun_small', 4: 'imid_small', 5: 'heun_cluster',
-                 6: 'imid_cluster', 7: 'heun_cluster_mma', 8: 'imid_split'}
+                 6: 'imid_cluster', 7: 'heun_cluster_mma', 8: 'imid_split', 9: 'imid_cluster_mma', 10: 'heun_cluster_big'}
 
 
 cdef dict _stats_dict(magpy_b200_stats* st):
@@ -744,6 +745,21 @@ def gaussians(seed, member, particle, first_step, n_steps, str gauss='f32p', int
     if rc != 0:
         _raise(rc)
     return out
+
+
+def solve3(A, b, int device=0):
+    """The implicit kernels' in-register 3x3 solve (adjugate) on the device: A (n, 3, 3), b (n, 3) -> x (n, 3), ok (n,)."""
+    cdef np.ndarray[double, ndim=1, mode='c'] cA = np.ascontiguousarray(A, dtype=np.float64).reshape(-1)
+    cdef np.ndarray[double, ndim=1, mode='c'] cb = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
+    cdef size_t n = cb.shape[0] // 3
+    if cA.shape[0] != 9 * n or n == 0:
+        raise ValueError('A must be (n, 3, 3) and b (n, 3)')
+    cdef np.ndarray[double, ndim=2] x = np.empty((n, 3))
+    cdef np.ndarray[int, ndim=1] ok = np.empty(n, dtype=np.intc)
+    cdef int rc = magpy_b200_solve3(device, n, &cA[0], &cb[0], &x[0, 0], <int*> &ok[0])
+    if rc != 0:
+        _raise(rc)
+    return x, ok.astype(bool)
 
 
 def gaussian_stats(seed, n_members, n_steps, str gauss='f32p', first_member=0, int device=0):

@@ -24,6 +24,11 @@ cudaError_t launch_heun_cluster(int noise, bool tab, int np, int layout, dim3 gr
 // two launches: `full_ctas` CTAs with a full set of members (whole waves), then `tail_ctas` CTAs of the partial last wave
 cudaError_t launch_heun_cluster_mma(int noise, bool tab, bool one_buf, unsigned full_ctas, unsigned tail_ctas, unsigned threads,
                                     size_t smem, cudaStream_t s, const RunParams& P);
+// cluster_big.cu: Heun for any cluster size (moments in global memory); CTA = 32 members x 16 particle slots
+cudaError_t launch_heun_cluster_big(int noise, bool tab, unsigned grid, cudaStream_t s, const RunParams& P);
+// K4m (cluster_mma_imid.cu): threads = 32 * G * column tiles of 8 members
+cudaError_t launch_imid_cluster_mma(int noise, bool tab, unsigned grid, unsigned threads, size_t smem, cudaStream_t s,
+                                    const RunParams& P);
 cudaError_t launch_imid_cluster(int noise, bool tab, int np, dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                 const RunParams& P);
 
@@ -43,6 +48,7 @@ cudaError_t launch_philox_words(const uint32_t ctr[4], const uint32_t key[2], ui
 cudaError_t launch_gaussians(int noise, uint64_t seed, uint32_t member, uint32_t particle, uint64_t first_step,
                              uint64_t n_steps, double* out);
 
+cudaError_t launch_solve3(const double* A, const double* b, double* x, int* ok, uint64_t n);
 // histogram [4096] of the draws over [-8, 8), histogram [1024] of the Box-Muller pair angles, {sum z, z^2, z^3, z^4, max |z|}
 cudaError_t launch_gauss_stats(int noise, uint64_t seed, uint64_t first_member, uint64_t n_members, uint64_t n_steps,
                                unsigned long long* hist, unsigned long long* angle_hist, double* moments);

@@ -214,6 +214,8 @@ struct magpy_b200_plan {
     bool small = false;    // few particles: one thread per cluster, all moments in registers
     bool split = false;    //   ... implicit, one lane per particle (imid_split_kernel)
     bool mma = false;      // Heun cluster kernel on the FP64 MMA path (cluster_mma.cu)
+    bool imid_mma = false; // implicit cluster kernel on the FP64 MMA path (cluster_mma_imid.cu)
+    bool big = false;      // Heun beyond 128 particles: moments in global memory (cluster_big.cu)
     bool one_buf = false;  //   ... with one shared-memory moment buffer
     uint32_t G = 0;        //   ... particle groups of 8
     uint32_t mma_full = 0, mma_tail = 0;   //   ... member distribution over CTAs (see choose_mma)
@@ -221,6 +223,7 @@ struct magpy_b200_plan {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
+    DevBuf<double> d_state_t;
     DevBuf<double> d_state0, d_state, d_axis, d_kred, d_sig, d_dip, d_dmat, d_vred, d_traj, d_sums, d_partial, d_tab, d_dW, d_stage;
     DevBuf<int64_t> d_seeds;
     DevBuf<uint32_t> d_member_idx, d_member_j;
@@ -237,7 +240,7 @@ struct magpy_b200_plan {
 
     ~magpy_b200_plan() {
         cudaSetDevice(device);
-        d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
+        d_state_t.release(); d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
         d_dmat.release(); d_vred.release();
         d_traj.release(); d_sums.release(); d_partial.release(); d_tab.release(); d_dW.release(); d_stage.release();
         d_seeds.release(); d_member_idx.release(); d_member_j.release(); d_mp.release(); d_target.release(); d_newton.release();
@@ -282,6 +285,10 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
         LAUNCH_TRY(mb::launch_heun_cluster_mma(noise, tab, pl->one_buf, pl->mma_full, pl->grid - pl->mma_full, pl->block.x, pl->smem,
                                                pl->stream, P));
         if (pl->mma_full > 0 && pl->grid > pl->mma_full) pl->launches++;   // whole waves + partial last wave
+    } else if (pl->big) {
+        LAUNCH_TRY(mb::launch_heun_cluster_big(noise, tab, pl->grid, pl->stream, P));
+    } else if (pl->imid_mma) {
+        LAUNCH_TRY(mb::launch_imid_cluster_mma(noise, tab, pl->grid, pl->block.x, pl->smem, pl->stream, P));
     } else if (pl->implicit) {
         LAUNCH_TRY(mb::launch_imid_cluster(noise, tab, pl->np, dim3(pl->grid), pl->block, pl->smem, pl->stream, P));
     } else {
@@ -293,12 +300,16 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
 int launch_transpose(magpy_b200_plan* pl, const double* in, double* out, uint64_t batches, uint64_t rows,
                      uint64_t cols, uint64_t in_bs, uint64_t in_rs, uint64_t out_bs, uint64_t out_rs,
                      double scale) {
-    // batches go through gridDim.z in slices of 65535
-    if ((rows + 31) / 32 > 65535) return fail(MAGPY_B200_ERR_BAD_ARG, "transpose rows too large");
+    // batches go through gridDim.z and row tiles through gridDim.y, both in slices of 65535
+    const uint64_t row_slice = 65535ull * 32;
     for (uint64_t b0 = 0; b0 < batches; b0 += 65535) {
         const uint64_t nb = std::min<uint64_t>(65535, batches - b0);
-        LAUNCH_TRY(mb::launch_transpose(in + b0 * in_bs, out + b0 * out_bs, rows, cols, nb, in_bs, in_rs, out_bs, out_rs,
-                                        scale, pl->stream));
+        for (uint64_t r0 = 0; r0 < rows; r0 += row_slice) {
+            const uint64_t nr = std::min<uint64_t>(row_slice, rows - r0);
+            // element (b, row, col): in[b in_bs + row in_rs + col] -> out[b out_bs + col out_rs + row]
+            LAUNCH_TRY(mb::launch_transpose(in + b0 * in_bs + r0 * in_rs, out + b0 * out_bs + r0, nr, cols, nb, in_bs, in_rs,
+                                            out_bs, out_rs, scale, pl->stream));
+        }
     }
     return MAGPY_B200_OK;
 }
@@ -355,9 +366,9 @@ int validate(const magpy_b200_ensemble* a) {
         return fail(MAGPY_B200_ERR_BAD_ARG, "the communicator was created for device %d, the ensemble runs on device %d",
                     mbh::comm_device(a->comm), a->device);
     if (a->use_implicit) {
-        if (a->n_particles > 64) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 64 particles per cluster");
-    } else if (a->n_particles > 128) {
-        return fail(MAGPY_B200_ERR_BAD_ARG, "Heun supports at most 128 particles per cluster");
+        if (a->n_particles > 128) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 128 particles per cluster");
+    } else if (a->n_particles > 2048) {
+        return fail(MAGPY_B200_ERR_BAD_ARG, "Heun supports at most 2048 particles per cluster");
     }
     return MAGPY_B200_OK;
 }
@@ -438,6 +449,42 @@ bool choose_mma(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     return true;
 }
 
+// K4m (cluster_mma_imid.cu): implicit midpoint for clusters of 8..128 particles.  One warp per (particle group of 8, column
+// tile of 8 members): G * CT <= 16 warps; the packed matrix in shared memory up to 64 particles, in global memory / L2
+// above; ONE moment buffer.  MAGPY_B200_CLUSTER_KERNEL=simt keeps the scalar kernel (cluster.cu, <= 64 particles).
+bool choose_imid_mma(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
+    const uint32_t N = pl->N;
+    if (!pl->implicit || N < 8 || N > 128) return false;
+    const char* force = std::getenv("MAGPY_B200_CLUSTER_KERNEL");
+    if (force && std::strcmp(force, "simt") == 0 && N <= 40) return false;
+    // measured (profiles/r02_probe_imid_cluster.log): 8 particles 1.67e9 vs 1.96e9 particle-steps/s for the scalar kernel,
+    // 16: 1.35e9 vs 1.33e9, 32: 1.03e9 vs 0.89e9; 64 and more only fit here
+    if (!(force && std::strcmp(force, "mma") == 0) && N <= 16) return false;
+    (void)a;
+    const uint32_t G = (N + 7) / 8;
+    pl->mma_dglobal = N > 64;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    // column tiles per CTA: as many as 16 warps allow, fewer when the ensemble is too small to give every SM a CTA
+    uint32_t CT = std::min<uint32_t>(15, std::max<uint32_t>(1, 16 / G));   // one named barrier (1..15) per column tile
+    const uint64_t tiles = (pl->R + 7) / 8;
+    CT = (uint32_t)std::min<uint64_t>(CT, std::max<uint64_t>(1, tiles / (uint64_t)sms));
+    const size_t cap = 227 * 1024;
+    for (; CT >= 1; --CT) {
+        const size_t MB = 8 * CT, LD = MB + 4;
+        const size_t dmat = pl->mma_dglobal ? 0 : (size_t)G * (G + 1) / 2 * 576 * 8;
+        pl->smem = dmat + (size_t)24 * G * LD * 8 + (size_t)3 * G * MB * 8;
+        if (pl->smem <= cap) break;
+    }
+    if (CT == 0) return false;
+    pl->imid_mma = true;
+    pl->G = G;
+    pl->np = 1;
+    pl->block = dim3(32 * G * CT);
+    pl->grid = (unsigned)((pl->R + 8 * CT - 1) / (8 * CT));
+    return true;
+}
+
 int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     int rc = validate(a);
     if (rc) return rc;
@@ -504,8 +551,17 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
                 pl->grid = (unsigned)((R * N + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
             }
         }
+    } else if (!pl->implicit && N > 128) {
+        // cluster_big.cu: any cluster size, moments in global memory
+        pl->big = true;
+        pl->np = 1;
+        pl->block = dim3(mb::CL_LANES, 16);
+        pl->grid = (unsigned)((R + mb::CL_LANES - 1) / mb::CL_LANES);
+        pl->smem = 0;
     } else if (choose_mma(a, pl)) {
         // cluster_mma.cu: dipolar field as a matrix product on DMMA; geometry set by choose_mma
+    } else if (choose_imid_mma(a, pl)) {
+        // cluster_mma_imid.cu: the same product inside every quasi-Newton iteration
     } else {
         const uint32_t max_slots = pl->implicit ? 8 : 16;
         // >= 2 own particles per thread reuse every shared-memory moment read of the dipolar sum; the implicit kernel's
@@ -602,6 +658,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     // uploads
     CU_TRY(pl->d_state0.alloc(n * R, pl->stream));
     CU_TRY(pl->d_state.alloc(n * R, pl->stream));
+    if (pl->big) CU_TRY(pl->d_state_t.alloc(n * R, pl->stream));
     CU_TRY(pl->d_kred.alloc(N, pl->stream));
     pl->mp = a->member_anisotropy || a->member_damping || a->member_field_amplitude;
     const bool member_radii = !pl->mp && (a->radius_stride != 0 || a->member_temperature != nullptr);   // N = 1: sigma per member
@@ -750,7 +807,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         CU_TRY(cudaStreamSynchronize(pl->stream));
         pl->h2d += tab.size() * 8;
     }
-    if (pl->mma) {
+    if (pl->mma || pl->imid_mma) {
         // symmetric dipolar matrix D[(i,a),(j,b)] = c_dip / cube_ij (3 r_a r_b - delta_ab) in the row order
         // 24 (p / 8) + 8 a + p % 8, upper 24 x 24 blocks only, swizzled inside a block (cluster_mma.cu)
         const uint32_t G = pl->G;
@@ -823,6 +880,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.philox_m0 = 0xD2511F53u;
     P.philox_m1 = 0xCD9E8D57u;
     P.state = pl->d_state.p;
+    P.state_t = pl->d_state_t.p;
     P.target = pl->d_target.p;
     P.field_tab = pl->d_tab.p;
     P.dW = pl->d_dW.p;
@@ -887,7 +945,9 @@ int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
     st->kernel_family = pl->N == 1 ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SINGLE : MAGPY_B200_KERNEL_HEUN_SINGLE)
                         : pl->split ? MAGPY_B200_KERNEL_IMID_SPLIT
                         : pl->small ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SMALL : MAGPY_B200_KERNEL_HEUN_SMALL)
+                        : pl->big   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_BIG
                         : pl->mma   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA
+                        : pl->imid_mma ? MAGPY_B200_KERNEL_IMID_CLUSTER_MMA
                                     : (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER : MAGPY_B200_KERNEL_HEUN_CLUSTER);
     st->kernel_variant = (pl->N == 1 && !pl->implicit) ? (uint64_t)pl->k1_min_blocks : 0;
     if (pl->ran) {
@@ -1331,6 +1391,24 @@ int magpy_b200_gaussians(int device, int64_t seed, uint64_t member, uint32_t par
                       : gauss_mode == MAGPY_B200_GAUSS_F32 ? mb::NOISE_PHILOX_F32 : mb::NOISE_PHILOX_PACKED;
     CU_TRY(mb::launch_gaussians(noise, (uint64_t)seed, (uint32_t)member, particle, first_step, n_steps, d.p));
     CU_TRY(cudaMemcpy(out, d.p, 3 * n_steps * 8, cudaMemcpyDeviceToHost));
+    return MAGPY_B200_OK;
+}
+
+int magpy_b200_solve3(int device, size_t n, const double* A, const double* b, double* x, int* ok) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (!A || !b || !x || !ok || n == 0) return fail(MAGPY_B200_ERR_BAD_ARG, "bad arguments");
+    DevBuf<double> dA, db, dx;
+    DevBuf<int> dok;
+    CU_TRY(dA.alloc(9 * n));
+    CU_TRY(db.alloc(3 * n));
+    CU_TRY(dx.alloc(3 * n));
+    CU_TRY(dok.alloc(n));
+    CU_TRY(cudaMemcpy(dA.p, A, 9 * n * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(db.p, b, 3 * n * 8, cudaMemcpyHostToDevice));
+    CU_TRY(mb::launch_solve3(dA.p, db.p, dx.p, dok.p, n));
+    CU_TRY(cudaMemcpy(x, dx.p, 3 * n * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(ok, dok.p, n * sizeof(int), cudaMemcpyDeviceToHost));
     return MAGPY_B200_OK;
 }
 

@@ -24,7 +24,7 @@ constexpr int MMA_BLK = 576;   // doubles per 24 x 24 block of D
 // correction, for a block read transposed.
 // DG: the blocks of D are read from global memory (`dg`, read-only path) instead of the CTA's shared memory — clusters
 // of 65..128 particles, whose packed matrix (up to 612 KB) does not fit next to the moments.
-template <bool DG>
+template <bool DG, int NT = 2>
 __device__ __forceinline__ void load_frags(double (&af)[3], double (&bf)[2], const double* __restrict__ sm,
                                            const double* __restrict__ dg, const int a_idx, const bool direct, const int dsw,
                                            const int b_idx, const int ks, const int LD4) {
@@ -34,7 +34,8 @@ __device__ __forceinline__ void load_frags(double (&af)[3], double (&bf)[2], con
     for (int a = 0; a < 3; ++a) af[a] = DG ? __ldg(ap + a * sa) : ap[a * sa];
     const double* bq = sm + b_idx + ks * LD4;
     bf[0] = bq[0];
-    bf[1] = bq[8];
+    if (NT > 1) bf[1] = bq[8];
+    else bf[1] = 0.0;
 }
 
 // acc[a][j][e] = H_a(particle 8 pg + g, member 16 mh + 8 j + 2 t + e).  The operand fragments of the next k-step
@@ -58,15 +59,15 @@ __device__ __forceinline__ void dipolar_mma(double (&acc)[3][2][2], const double
     };
     int a_cur = a_index(0), b_cur = b0;
     double af[3], bf[2];
-    load_frags<DG>(af, bf, sm, dg, a_cur, 0 >= pg, dsw, b_cur, 0, LD4);
+    load_frags<DG, NT>(af, bf, sm, dg, a_cur, 0 >= pg, dsw, b_cur, 0, LD4);
     for (int kg = 0; kg < G; ++kg) {
         const int kn = kg + 1 < G ? kg + 1 : kg;   // the last prefetch re-reads a valid block
         const int a_nxt = a_index(kn), b_nxt = b0 + kn * LD24;
 #pragma unroll
         for (int ks = 0; ks < 6; ++ks) {
             double an[3], bn[2];
-            if (ks < 5) load_frags<DG>(an, bn, sm, dg, a_cur, kg >= pg, dsw, b_cur, ks + 1, LD4);
-            else load_frags<DG>(an, bn, sm, dg, a_nxt, kn >= pg, dsw, b_nxt, 0, LD4);
+            if (ks < 5) load_frags<DG, NT>(an, bn, sm, dg, a_cur, kg >= pg, dsw, b_cur, ks + 1, LD4);
+            else load_frags<DG, NT>(an, bn, sm, dg, a_nxt, kn >= pg, dsw, b_nxt, 0, LD4);
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll

@@ -250,6 +250,25 @@ cudaError_t launch_gauss_stats(int noise, uint64_t seed, uint64_t first_member, 
     return cudaGetLastError();
 }
 
+// device self-test of the 3x3 solve of the quasi-Newton update (llg_math.cuh: solve3_adjugate) on caller matrices
+__global__ void solve3_kernel(const double* A, const double* b, double* x, int* ok, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a[9], rhs[3], d[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 9; ++q) a[q] = A[9 * i + q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) rhs[q] = b[3 * i + q];
+    ok[i] = solve3_adjugate(a, rhs, d) ? 1 : 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) x[3 * i + q] = d[q];
+}
+
+cudaError_t launch_solve3(const double* A, const double* b, double* x, int* ok, uint64_t n) {
+    solve3_kernel<<<(unsigned)((n + 127) / 128), 128>>>(A, b, x, ok, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_field_table(double* tab, uint64_t j0, uint64_t n_steps, double dt, double second_offset, int shape,
                                double h0, double f_red, cudaStream_t s) {
     field_table_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, s>>>(tab, j0, n_steps, dt, second_offset, shape, h0, f_red);

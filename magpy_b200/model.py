@@ -266,7 +266,15 @@ class EnsembleModel:
             else:
                 # several parameter groups: one plan (own CUDA stream) per group, all enqueued before the first is waited
                 # for, so that the groups' kernels — each usually far too small to fill the GPU — run concurrently
-                pending.append((core.EnsemblePlan(*args, **kwargs), idx))
+                try:
+                    plan = core.EnsemblePlan(*args, **kwargs)
+                except MemoryError:
+                    # every pending plan holds its own device buffers: run and release them, then try this group again
+                    if not pending:
+                        raise
+                    flush()
+                    plan = core.EnsemblePlan(*args, **kwargs)
+                pending.append((plan, idx))
                 if len(pending) >= _MAX_CONCURRENT_PLANS:
                     flush()
         flush()

@@ -179,6 +179,22 @@ def test_heun_cluster_mma_injected(orc, core, N, renorm, members, monkeypatch):
     assert_traj(ref, out, c)
 
 
+# Beyond 128 particles: the capacity-free kernel (cluster_big.cu: moments in global memory, increments regenerated for the
+# corrector).  The reference takes any cluster size (lib/simulation.cpp:182-200).
+@pytest.mark.parametrize('N,renorm,members', [(130, True, 35), (192, False, 5)])
+def test_heun_cluster_beyond_128_particles(orc, core, N, renorm, members):
+    rng = np.random.default_rng(N)
+    c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
+                     dt=1e-13, t_end=1.5e-11, S=13, interactions=True, renorm=renorm, field_shape='sine',
+                     H0=1e4, f=1e10, T=330.0, rng=rng)
+    seeds = np.arange(1, members + 1) * 101
+    t, fl, ref, out, _ = injected_pair(orc, core, c, seeds, per_member=(N == 130))
+    assert out['stats']['kernel'] == 'heun_cluster_big'
+    assert_traj(ref, out, c)
+    with pytest.raises(ValueError):   # implicit midpoint stops at 128 particles
+        gpu_run(core, ol.Case(dict(c, implicit=True)), seeds)
+
+
 @pytest.mark.parametrize('N,renorm,gauss', [(24, False, 'f32p'), (33, True, 'f64'), (64, False, 'f64')])
 def test_mma_and_scalar_cluster_kernels_agree_member_by_member(core, N, renorm, gauss, monkeypatch):
     """Production noise (in-kernel Philox), 300 members, 400 steps, polydisperse: the matrix-product kernel and the
@@ -222,19 +238,31 @@ def test_mma_member_distribution_is_invisible(core, N):
     assert np.allclose(big['sums'][-1], want, rtol=1e-11)
 
 
-# 40: eight own particles per thread (33..64 particles; the oracle's dense (3N)^3 path limits members and steps)
-@pytest.mark.parametrize('N,interactions', [(2, True), (3, False), (4, True), (5, True), (12, True), (32, True), (40, True)])
+# 8 and more particles: the matrix-product kernel (cluster_mma_imid.cu), 64 = the full shared-memory matrix; the scalar
+# kernel (cluster.cu) is kept and tested through MAGPY_B200_CLUSTER_KERNEL=simt (the oracle's dense (3N)^3 path limits
+# members and steps at N >= 32)
+@pytest.mark.parametrize('N,interactions', [(2, True), (3, False), (4, True), (5, True), (8, True), (12, True), (16, False),
+                                            (32, True), (40, True), (64, True)])
 def test_implicit_cluster_injected(orc, core, N, interactions, monkeypatch):
     rng = np.random.default_rng(100 + N)
     c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
                      dt=1e-12, t_end=4e-11, S=21, implicit=True, interactions=interactions, T=330.0, rng=rng)
     seeds = np.arange(1, 34 if N < 32 else 7 if N == 32 else 4) * 13   # the oracle's dense (3N)^3 implicit path is slow at N >= 32
     if N > 32:
-        c['t_end'], c['S'] = 1.2e-11, 7
-    t, fl, ref, out, newton = injected_pair(orc, core, c, seeds, per_member=(N in (2, 4)))
+        c['t_end'], c['S'] = 1.2e-11 if N < 64 else 6e-12, 7 if N < 64 else 4
+    t, fl, ref, out, newton = injected_pair(orc, core, c, seeds, per_member=(N in (2, 4, 12)))
     assert_traj(ref, out, c)
-    assert out['stats']['newton_iterations'] == sum(n[0] - n[2] for n in newton)
-    assert out['stats']['kernel'] == ('imid_split' if N == 4 else 'imid_small' if N <= 3 else 'imid_cluster')
+    assert out['stats']['newton_iterations'] == sum(n[0] - n[2] for n in newton)     # identical iteration counts
+    assert out['stats']['kernel'] == ('imid_split' if N == 4 else 'imid_small' if N <= 3 else 'imid_cluster' if N <= 16
+                                      else 'imid_cluster_mma')
+    if N in (8, 12, 16, 40):   # the other cluster kernel on the same case (default: scalar up to 16 particles, matrix product above)
+        other = 'mma' if N <= 16 else 'simt'
+        monkeypatch.setenv('MAGPY_B200_CLUSTER_KERNEL', other)
+        t, fl, ref, out2, newton = injected_pair(orc, core, c, seeds, per_member=(N == 12))
+        assert out2['stats']['kernel'] == ('imid_cluster_mma' if other == 'mma' else 'imid_cluster')
+        assert_traj(ref, out2, c)
+        assert out2['stats']['newton_iterations'] == out['stats']['newton_iterations']
+        monkeypatch.delenv('MAGPY_B200_CLUSTER_KERNEL')
     if N in (2, 4):   # both mappings of small clusters: one thread per cluster and one lane per particle
         monkeypatch.setenv('MAGPY_B200_SMALL_KERNEL', 'thread' if N == 4 else 'split')
         t, fl, ref, out2, newton = injected_pair(orc, core, c, seeds, per_member=True)
@@ -274,6 +302,36 @@ def test_exact_newton_mode_is_the_converged_reference_iteration(orc, core, N, ax
         fast2 = gpu_run(core, ol.Case(dict(c, eps=1e-9)), seeds, dW=dW, implicit_newton='exact')
         assert fast2['stats']['kernel'] == 'imid_small'
         assert np.abs(fast2['trajectories'] - ref).max() / c.Ms < 1e-11
+
+
+def test_adjugate_solve_against_pivoted_elimination(core):
+    """The implicit kernels solve each particle's 3x3 quasi-Newton system by the adjugate (llg_math.cuh) where the
+    reference calls dgesv (pivoted elimination, lib/optimisation.cpp:134).  On the matrices of the iteration (I + O(dt))
+    no pivoting happens and the two agree to a few ulp; this checks the regime where the pivot order WOULD matter:
+    random matrices with condition numbers up to 1e8, matrices with a zero or tiny leading entry (elimination needs a
+    row swap, the adjugate needs nothing), and exactly singular ones (dgesv info > 0 <-> ok = False).  Forward error
+    within cond * eps of LAPACK's solution — the bound pivoted elimination itself obeys."""
+    rng = np.random.default_rng(42)
+    n = 4096
+    U, _ = np.linalg.qr(rng.normal(size=(n, 3, 3)))
+    V, _ = np.linalg.qr(rng.normal(size=(n, 3, 3)))
+    sv = np.stack([np.ones(n), 10.0 ** rng.uniform(-4, 0, n), 10.0 ** rng.uniform(-8, 0, n)], axis=1)
+    A = U @ (sv[:, :, None] * np.swapaxes(V, 1, 2))
+    A[:512, 0, 0] = 0.0                          # zero pivot in the natural order
+    A[512:1024, 0, 0] *= 1e-14                   # tiny pivot
+    near_id = np.eye(3) + 0.05 * rng.normal(size=(n, 3, 3))
+    A[1024:2048] = near_id[1024:2048]            # what the iteration actually produces
+    b = rng.normal(size=(n, 3))
+    x, ok = core.solve3(A, b)
+    want = np.linalg.solve(A, b[:, :, None])[:, :, 0]          # LAPACK gesv: partial pivoting
+    cond = np.linalg.cond(A)
+    rel = np.linalg.norm(x - want, axis=1) / np.linalg.norm(want, axis=1)
+    assert ok.all()
+    assert (rel <= 32 * cond * np.finfo(float).eps).all(), (rel / (cond * np.finfo(float).eps)).max()
+    assert rel[1024:2048].max() < 1e-14           # the iteration's own matrices: a few ulp
+    S = np.zeros((3, 3, 3)); S[0] = [[1, 2, 3], [2, 4, 6], [0, 1, 5]]; S[1] = 0; S[2] = [[1, 0, 0], [0, 1, 0], [1, 1, 0]]
+    _, ok_s = core.solve3(S, np.ones((3, 3)))
+    assert not ok_s.any()
 
 
 @pytest.mark.parametrize('implicit', [False, True])
@@ -441,7 +499,8 @@ def test_coarsened_noise_is_the_sum_of_the_fine_stream(core, implicit):
         gpu_run(core, ol.make_case(N=2), seeds, noise_coarsen_log2=1)
 
 
-@pytest.mark.parametrize('N,implicit', [(1, False), (3, False), (6, False), (12, False), (40, False), (1, True), (2, True), (6, True)])
+@pytest.mark.parametrize('N,implicit', [(1, False), (3, False), (6, False), (12, False), (40, False), (1, True), (2, True), (6, True),
+                                        (12, True), (24, True), (130, False)])
 def test_every_kernel_family_consumes_the_same_philox_stream(core, N, implicit, monkeypatch):
     """The increment of (seed, member, particle, step) is one function — the one `core.gaussians` exposes and
     tests/test_parity_gpu.py checks against the oracle — whichever kernel consumes it: pipelined pairs (single
