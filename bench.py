@@ -62,6 +62,17 @@ WORKLOADS = {
              '2000 steps per pass',
         N=64, R=100_000, radius=12e-9, anisotropy=4e4, Ms=4e5, alpha=0.1, T=300.0,
         dt=1e-14, t_end=2e-11, S=21, field_shape='constant', H0=0.0, f=0.0, random_state=1001),
+    # the two small BASELINE configurations (latency bound: a thousand members cannot fill a B200) — same contract line
+    'c1': dict(
+        name='C1: 1000 x 1-particle (12 nm magnetite), no field, Heun dt=1e-14 s to 1e-9 s (1e5 steps), 1000 samples, '
+             'per-member trajectories returned',
+        N=1, R=1000, radius=12e-9, anisotropy=4e4, Ms=4e5, alpha=0.1, T=300.0, m0=[1.0, 0.0, 0.0],
+        dt=1e-14, t_end=1e-9, S=1000, field_shape='constant', H0=0.0, f=0.0, random_state=1001, traj=True),
+    'c2': dict(
+        name='C2: 10k x 2 dipolar-coupled 7 nm particles 9 nm apart, implicit midpoint (reference quasi-Newton, eps 1e-9), '
+             'dt=1e-12 s, 1000 steps, 500 samples',
+        N=2, R=10_000, radius=7e-9, anisotropy=1e5, Ms=4e5, alpha=0.1, T=330.0, implicit=True,
+        dt=1e-12, t_end=1e-9, S=500, field_shape='constant', H0=0.0, f=0.0, random_state=1001),
 }
 WORKLOAD = WORKLOADS['c3']
 
@@ -71,7 +82,11 @@ def workload_arrays(R):
     N = w['N']
     if N == 1:
         return dict(radius=np.array([w['radius']]), anisotropy=np.array([w['anisotropy']]),
-                    axis=np.array([[0.0, 0.0, 1.0]]), m0=np.array([[0.0, 0.0, 1.0]]), location=np.zeros((1, 3)))
+                    axis=np.array([[0.0, 0.0, 1.0]]), m0=np.array([w.get('m0', [0.0, 0.0, 1.0])]), location=np.zeros((1, 3)))
+    if N == 2:   # the dimer of docs/source/notebooks/two-particle-equilibrium.ipynb
+        z = np.array([[0.0, 0.0, 1.0]] * 2)
+        return dict(radius=np.full(2, w['radius']), anisotropy=np.full(2, w['anisotropy']), axis=z, m0=z.copy(),
+                    location=np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 9e-9]]))
     from magpy_b200 import geometry   # host-side input generation only (numpy)
     axes = geometry.uniform_random_axes(N, rng=4)
     return dict(radius=np.full(N, w['radius']), anisotropy=np.full(N, w['anisotropy']), axis=axes, m0=axes.copy(),
@@ -154,8 +169,8 @@ def load_cpu_reference():
             el = lib.ref_ensemble(
                 C.c_size_t(len(seeds)), P(seeds), C.c_size_t(w['N']), P(arr['radius']), P(arr['anisotropy']),
                 P(arr['axis']), C.c_size_t(0), P(arr['m0']), C.c_size_t(0), P(arr['location']),
-                C.c_double(w['Ms']), C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0),
-                C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']),
+                C.c_double(w['Ms']), C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1),
+                C.c_int(int(w.get('implicit', False))), C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']),
                 C.c_int(field_code), C.c_double(w['H0']), C.c_double(w['f']), C.c_int(cores), P(sums), None)
             if el < 0:
                 raise RuntimeError('reference ensemble failed')
@@ -175,8 +190,8 @@ def load_cpu_reference():
         lib.orc_ensemble(
             C.c_size_t(len(seeds)), P(seeds), C.c_int(w['N']), P(arr['radius']), P(arr['anisotropy']), P(arr['axis']),
             C.c_size_t(0), P(arr['m0']), C.c_size_t(0), P(arr['location']), C.c_double(w['Ms']),
-            C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0), C.c_double(1e-9),
-            C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']), C.c_int(field_code),
+            C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(int(w.get('implicit', False))),
+            C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(w['S']), C.c_int(field_code),
             C.c_double(w['H0']), C.c_double(w['f']), P(sums), None)
         return time.perf_counter() - t0
     return 'port', cores, run
@@ -191,8 +206,8 @@ def _joblib_member(seed, w, arr):
     N, S = w['N'], w['S']
     t, fl, m = np.zeros(S), np.zeros(S), np.zeros((N, 3, S))
     rc = lib.ref_simulate(C.c_size_t(N), P(arr['radius']), P(arr['anisotropy']), P(arr['axis']), P(arr['m0']), P(arr['location']),
-                          C.c_double(w['Ms']), C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1), C.c_int(0),
-                          C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(S), C.c_long(int(seed)),
+                          C.c_double(w['Ms']), C.c_double(w['alpha']), C.c_double(w['T']), C.c_int(0), C.c_int(1),
+                          C.c_int(int(w.get('implicit', False))), C.c_double(1e-9), C.c_double(w['dt']), C.c_double(w['t_end']), C.c_size_t(S), C.c_long(int(seed)),
                           C.c_int({'sine': 0, 'square': 1, 'constant': 2}[w['field_shape']]), C.c_double(w['H0']),
                           C.c_double(w['f']), P(t), P(fl), P(m))
     if rc != 0:
@@ -276,8 +291,8 @@ def reference_arm(args):
     for _ in range(args.steps):
         t += run(seeds[:n])
     value = WORKLOAD['N'] * args.steps * n * n_steps / t
-    sample = '%d realisations x %d Heun steps per step (of the %d-realisation workload), %d host threads' % (
-        n, n_steps, WORKLOAD['R'], cores)
+    sample = '%d realisations x %d %s steps per step (of the %d-realisation workload), %d host threads' % (
+        n, n_steps, 'implicit-midpoint' if WORKLOAD.get('implicit') else 'Heun', WORKLOAD['R'], cores)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True,
@@ -296,9 +311,9 @@ def reference_arm(args):
 def _make_plan(core, arr, seeds, R_local, offset, device, comm, gauss='f32p', t_end=None):
     w = WORKLOAD
     return core.EnsemblePlan(arr['radius'], arr['anisotropy'], arr['axis'], arr['m0'], arr['location'], w['Ms'],
-                             w['alpha'], w['T'], False, True, False, w['dt'], t_end or w['t_end'], w['S'], seeds,
+                             w['alpha'], w['T'], False, True, bool(w.get('implicit', False)), w['dt'], t_end or w['t_end'], w['S'], seeds,
                              field_shape=w['field_shape'], field_amplitude=w['H0'], field_frequency=w['f'],
-                             device=device, stream_offset=offset, return_trajectories=False,
+                             device=device, stream_offset=offset, return_trajectories=bool(w.get('traj', False)),
                              return_sums=True, return_final=True, gauss=gauss, comm=comm)
 
 
@@ -387,7 +402,7 @@ def ours(args):
 
     # the other Gaussian transforms of the Philox stream on the same workload (N = 1 run of the default workload only)
     rng_rates = None
-    if world == 1 and w['N'] == 1:
+    if world == 1 and w is WORKLOADS['c3']:
         rng_rates = {}
         for g, frac in (('f32', 0.2), ('f64', 0.05)):
             p3 = _make_plan(core, arr, seeds_all[lo:hi], R, lo, local_rank, None, gauss=g, t_end=w['t_end'] * frac)
@@ -402,14 +417,15 @@ def ours(args):
     ens = mp.EnsembleModel(R_total, base)
     shard = (rank, world) if world > 1 else None
     e2e_passes = max(1, min(args.steps, 2))
-    ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'], implicit_solve=False, device=local_rank,
-                 return_trajectories=False, shard=shard, comm=comm)   # warm-up
+    implicit, traj = bool(w.get('implicit', False)), bool(w.get('traj', False))
+    ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'], implicit_solve=implicit, device=local_rank,
+                 return_trajectories=traj, shard=shard, comm=comm)   # warm-up
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for i in range(e2e_passes):
-        res = ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'], implicit_solve=False,
-                           device=local_rank, return_trajectories=False, shard=shard, comm=comm)
+        res = ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'], implicit_solve=implicit,
+                           device=local_rank, return_trajectories=traj, shard=shard, comm=comm)
         h2d += sum(s['h2d_bytes'] for s in res.stats)
         d2h += sum(s['d2h_bytes'] for s in res.stats)
         final_mz = float(res.ensemble_magnetisation()[-1])        # the step's result, read on the host
@@ -425,9 +441,11 @@ def ours(args):
     if rank != 0:
         return
 
-    W_ALG = w_alg(w['N'])
+    # implicit midpoint has no fixed algorithmic work (the iteration count is data dependent): the
+    # line then carries the quasi-Newton iterations per step instead of a roofline fraction
+    W_ALG = None if w.get('implicit') else w_alg(w['N'])
     # the dominant kernel of a rank processes that rank's share of the pass
-    achieved = W_ALG * (ps_per_pass / world) / (int_ms * 1e-3) / 1e12
+    achieved = W_ALG * (ps_per_pass / world) / (int_ms * 1e-3) / 1e12 if W_ALG else None
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'heun_single_traffic.json')
     if w['N'] == 1 and world == 1 and os.path.exists(prof):
@@ -470,12 +488,18 @@ def ours(args):
                    'l2': 'state is register resident; no input is re-read between passes (0 B/step steady-state HBM '
                          'traffic), so no L2 flush applies',
                    'timing': 'CUDA events on the launching stream (integration + reduction + all-reduce), max over ranks',
-                   'kernel_variant': 'heun_single min-blocks %s' % variant if w['N'] == 1 else None,
+                   'kernel_variant': ({1: 'heun_single, free register allocation (6 CTAs/SM)', 7: 'heun_single, 7 CTAs/SM',
+                                       100: 'heun_single, latency variant (field table prefetched)',
+                                       200: 'heun_single_balanced: persistent kernel over (time segment, 128-member block) tasks'
+                                       }.get(variant, str(variant)) if w['N'] == 1 and not w.get('implicit') else None),
                    'other_scaling_mode': other,
                    'mean_mz_over_Ms_at_end': mean_mz, 'wall_s_timed_region': wall},
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': traffic,
-                     'kernel': st['kernel'] + '_kernel', 'kernel_ms_per_launch': int_ms,
+                     'frac': achieved / peak_tflops if (peak_tflops and achieved) else None, 'traffic': traffic,
+                     'newton_iterations_per_step': (st['newton_iterations'] / max(1, st['particle_steps'] / w['N'])
+                                                    if w.get('implicit') else None),
+                     'kernel': ('heun_single_balanced' if variant == 200 else st['kernel']) + '_kernel',
+                     'kernel_ms_per_launch': int_ms,
                      'algorithmic_flop_per_particle_step': W_ALG,
                      'peak_dfma_chain': dfma_tflops, 'peak_dmma_chain': dmma_tflops, 'sm_clock_mhz_max': max_mhz,
                      'peak_source': 'measured in this run: the larger of the library\'s register-resident DFMA-chain and '
@@ -501,7 +525,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS),
-                    help='c3 (default): the configuration the BASELINE metric is quoted on; c4: 64-particle clusters')
+                    help='c3 (default): the configuration the BASELINE metric is quoted on; c4: 64-particle clusters; '
+                         'c1, c2: the two small (latency-bound) BASELINE configurations')
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'],
                     help='strong (default): the workload\'s realisations are shared out over the GPUs (BASELINE: 1M in '
                          'total); weak: every GPU takes the full count.  The other mode is measured too and reported in '

@@ -60,9 +60,12 @@ typedef struct magpy_b200_stats {
     uint64_t h2d_bytes;            /* host->device bytes copied by this call                */
     uint64_t d2h_bytes;            /* device->host bytes copied by this call                */
     uint64_t kernel_family;        /* MAGPY_B200_KERNEL_*: which integration kernel ran (ABI v3) */
-    uint64_t kernel_variant;       /* heun_single: resident CTAs per SM asked of the register allocator — 1 (free: 6
-                                      CTAs of 128 threads) or 7 (when the shard fits one wave of 7 per SM but not
-                                      one of 6); 0 for the other kernels (ABI v4)                             */
+    uint64_t kernel_variant;       /* heun_single: 1 = free register allocation (6 CTAs of 128 threads per SM), 7 = 7
+                                      CTAs per SM (when the shard fits one such wave but not one of 6), 100 = latency
+                                      variant for ensembles below one warp per SM sub-partition (field table
+                                      prefetched a step pair ahead), 200 = persistent kernel over (time segment,
+                                      member block) tasks for shards of more than one wave (no rounding up to whole
+                                      warps per SM sub-partition); 0 for the other kernels (ABI v4)            */
     /* host wall-clock of the blocking entry points (magpy_b200_simulate_ensemble[_multi]), ms (ABI v4): */
     double host_setup_ms;          /* plan creation: validation, schedule, allocations, uploads             */
     double host_run_ms;            /* launch + wait for the device                                          */

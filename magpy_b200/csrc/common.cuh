@@ -78,6 +78,11 @@ struct RunParams {
     double* traj;               // nullptr or [S][n][R]
     double* partial;            // nullptr or [(k1-k0)][gridDim.x][4]
     unsigned long long* newton; // [3] total / max / failures
+    // K1b (heun_single_balanced.cu): persistent kernel over (time segment, block of 128 members) tasks
+    uint32_t bal_vctas, bal_segments;   // member blocks ("virtual CTAs") and time segments of this launch
+    unsigned int* bal_counter;          // task counter (zeroed before the launch)
+    unsigned int* bal_flags;            // [bal_vctas] segments completed by each member block
+    const uint32_t* bal_seg_k;          // [bal_segments] first sample of the launch with state index >= the segment's first step
 };
 
 // ---------------------------------------------------------------------------------

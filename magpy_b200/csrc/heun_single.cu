@@ -8,42 +8,6 @@ namespace mb {
 // lib/llg.cpp:332-348 with the field of lib/simulation.cpp:271-290, N = 1)
 // ---------------------------------------------------------------------------------
 
-// One Heun step of a single macrospin in 40 fp64 instructions (47 with a general easy axis).
-// With u = g + alpha (m x g) the LLG increment is f(m,g) = -m x u, so the predictor
-// x~ = m + f(m,g) and the corrector m' = (m + x~)/2 + f(x~,g~)/2 are accumulated directly in the
-// FMAs of the second cross product (no separate adds, and f1 is never materialised).
-// `dt` only multiplies the applied field here (the anisotropy term carries it in edt = k dt e): the MP instantiations
-// pass h0_r dt_r with the unit waveform in hz0 / hz1.
-template <bool AXIS_Z>
-__device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V3& edt, const double alpha,
-                                               const double dt, const V3& cw, const double hz0, const double hz1) {
-    // stage 1: g = h(m,t) dt + sigma sqrt(dt) w
-    V3 g;
-    if (AXIS_Z) {  // easy axis = z: h = (k m_z + h_app) z, two fp64 ops instead of seven
-        g = V3{cw.x, cw.y, fma(m.z, edt.z, fma(hz0, dt, cw.z))};
-    } else {
-        const double s = dot(m, e);
-        g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz0, dt, cw.z))};
-    }
-    V3 p = cross(m, g);
-    V3 u{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
-    const V3 mt{fma(-m.y, u.z, fma(m.z, u.y, m.x)), fma(-m.z, u.x, fma(m.x, u.z, m.y)),
-                fma(-m.x, u.y, fma(m.y, u.x, m.z))};
-    // stage 2 at (x~, t+dt), same Wiener increment
-    if (AXIS_Z) {
-        g = V3{cw.x, cw.y, fma(mt.z, edt.z, fma(hz1, dt, cw.z))};
-    } else {
-        const double s = dot(mt, e);
-        g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz1, dt, cw.z))};
-    }
-    p = cross(mt, g);
-    u = V3{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
-    const V3 hm{0.5 * mt.x, 0.5 * mt.y, 0.5 * mt.z};
-    const V3 h{fma(0.5, m.x, hm.x), fma(0.5, m.y, hm.y), fma(0.5, m.z, hm.z)};
-    return V3{fma(-hm.y, u.z, fma(hm.z, u.y, h.x)), fma(-hm.z, u.x, fma(hm.x, u.z, h.y)),
-              fma(-hm.x, u.y, fma(hm.y, u.x, h.z))};
-}
-
 #ifndef MB_PHILOX_SPLIT
 #define MB_PHILOX_SPLIT 0   // leading Philox rounds whose wide multiplies are issued as IMAD.HI + IMAD (tuning knob, rng.cuh)
 #endif
@@ -52,8 +16,11 @@ __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V
 // SM but not in one of 6 (magpy_b200.cu: choose_k1_variant; measured in profiles/r02_probe_k1_variants.log).
 // MP = per-member material parameters (anisotropy, damping, field amplitude next to radius / temperature): alpha, dt,
 // the noise amplitude, the field scale and the sampling schedule are per-thread values (RunParams::mp_*).
+// MINB = K1_LATENCY: the variant for ensembles too small to hide latency with warps — the applied-field table entries of
+// the NEXT step pair are fetched while the current pair is integrated (8 more registers; free allocation).
 template <int NOISE, bool FIELD_TAB, bool AXIS_Z, bool RENORM, int MINB, bool MP = false>
-__global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const __grid_constant__ RunParams P) {
+__global__ void __launch_bounds__(SINGLE_THREADS, MINB == 7 ? 7 : 1) heun_single_kernel(const __grid_constant__ RunParams P) {
+    constexpr bool PREFETCH_TAB = MINB == K1_LATENCY && FIELD_TAB;
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     const uint64_t r_raw = (uint64_t)blockIdx.x * SINGLE_THREADS + threadIdx.x;
     const bool live = r_raw < P.R;
@@ -82,6 +49,10 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const
             hz0 = h.x; hz1 = h.y;
         }
         m = heun_single_step<AXIS_Z>(m, e, edt, alpha, hdt, cw, hz0, hz1);
+        if (RENORM) renormalise(m);
+    };
+    auto advance_h = [&](const V3& cw, const double2 h) {   // the same with the table entry already in registers
+        m = heun_single_step<AXIS_Z>(m, e, edt, alpha, hdt, cw, h.x, h.y);
         if (RENORM) renormalise(m);
     };
 
@@ -121,11 +92,21 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB) heun_single_kernel(const
             uint32_t blk = (uint32_t)(j >> 1);
             const double2* tp = tab + (j - tab0);
             if (pairs != 0) need(blk);
+            double2 ha = make_double2(0.0, 0.0), hb = ha;
+            if (PREFETCH_TAB && pairs != 0) { ha = __ldg(tp); hb = __ldg(tp + 1); }
             for (uint32_t i = pairs; i != 0; --i, tp += 2) {
                 float gn[6];
+                double2 na, nb;
+                if (PREFETCH_TAB) { na = __ldg(tp + 2); nb = __ldg(tp + 3); }   // the table is allocated with a margin of rows
                 philox_gauss6_f32<MB_PHILOX_SPLIT>(key0, key1, ++blk, 0u, member, bm_scale, gn, P.philox_m0, P.philox_m1);
-                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tp);
-                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tp + 1);
+                if (PREFETCH_TAB) {
+                    advance_h(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, ha);
+                    advance_h(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, hb);
+                    ha = na; hb = nb;
+                } else {
+                    advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tp);
+                    advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tp + 1);
+                }
 #pragma unroll
                 for (int q = 0; q < 6; ++q) g[q] = gn[q];
                 gblk = blk;
@@ -191,7 +172,7 @@ static void launch_hs_mp(bool tab, dim3 g, dim3 b, cudaStream_t s, const RunPara
     }
 }
 
-// min_blocks = 1 or 7 (production noise mode only; the other modes have the one free-allocation instantiation)
+// min_blocks = 1, 7 or K1_LATENCY (production noise mode only; the other modes have the one free-allocation instantiation)
 cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, int min_blocks, unsigned grid, cudaStream_t s,
                                const RunParams& P) {
     if (P.mp_dt != nullptr) {
@@ -206,6 +187,7 @@ cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, int min_blocks,
         case NOISE_PHILOX_COARSE: launch_hs<NOISE_PHILOX_COARSE, 1>(tab, axis_z, grid, s, P); break;
         default:
             if (min_blocks == 7) launch_hs<NOISE_PHILOX_PACKED, 7>(tab, axis_z, grid, s, P);
+            else if (min_blocks == K1_LATENCY && tab) launch_hs<NOISE_PHILOX_PACKED, K1_LATENCY>(true, axis_z, grid, s, P);
             else launch_hs<NOISE_PHILOX_PACKED, 1>(tab, axis_z, grid, s, P);
             break;
     }

@@ -1,0 +1,156 @@
+// heun_single_balanced.cu — K1b: heun_single_kernel as a persistent kernel over (time segment, member block) tasks.
+//
+// K1 is bound by the FP64-side issue time of a warp-step, so the time of a launch is (warps per SM sub-partition,
+// rounded UP) x steps x 151 cycles: a shard of 125,000 members (1M members over 8 GPUs) is 6.6 warps per sub-partition
+// and pays for 7 (0.92 measured, profiles/r02_probe_k1_variants.log); 250,000 members pay 14 for 13.2.  Members are
+// independent but a member's steps are sequential, so the only way to hand a sub-partition a FRACTION of a warp's work
+// is to cut the time axis: the launch's step range is cut into segments, the ensemble into blocks of 128 members
+// ("virtual CTAs"), and a grid of exactly the resident CTAs (6 per SM) pulls (segment, block) tasks from a counter in
+// segment-major order.  A block's state is parked in HBM between its segments (24 B per member per segment — the same
+// hand-over the host-side chunking uses) and a per-block flag orders a segment after its predecessor (release / acquire;
+// the predecessor was handed out earlier to a CTA that is running, so the wait cannot deadlock).  Every SM then stays
+// busy until the last round of tasks: with 64 segments the rounding loss is < 1 %.
+// Same Philox counters and arithmetic as K1: bit-identical results (tests/test_parity_gpu.py).
+#include "common.cuh"
+#include "launch.h"
+
+namespace mb {
+
+template <bool FIELD_TAB, bool AXIS_Z, bool RENORM>
+__global__ void __launch_bounds__(SINGLE_THREADS, 6) heun_single_balanced_kernel(const __grid_constant__ RunParams P) {
+    __shared__ double red[(SINGLE_THREADS / 32) * 4];
+    __shared__ unsigned int s_task;
+    const uint32_t n_vcta = P.bal_vctas, n_seg = P.bal_segments;
+    const uint64_t n_tasks = (uint64_t)n_vcta * n_seg;
+    const double alpha = P.alpha, dt = P.dt, kdt = P.k_red[0] * dt;
+    const double2* tab = reinterpret_cast<const double2*>(P.field_tab);
+
+    for (;;) {
+        if (threadIdx.x == 0) s_task = atomicAdd(P.bal_counter, 1u);
+        __syncthreads();
+        const uint64_t task = s_task;
+        if (task >= n_tasks) break;
+        const uint32_t seg = (uint32_t)(task / n_vcta), vcta = (uint32_t)(task % n_vcta);
+        // steps [ja, jb) of this launch's [j0, j1); the samples this segment records are those whose state index lies in
+        // [ja, jb), plus — last segment — those at j1 itself
+        const uint64_t span = P.j1 - P.j0;
+        const uint64_t ja = P.j0 + span * seg / n_seg, jb = P.j0 + span * (seg + 1) / n_seg;
+        const bool last = seg + 1 == n_seg;
+        if (threadIdx.x == 0 && seg > 0) {     // the block's previous segment has parked its state
+            unsigned int done;
+            do {
+                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(done) : "l"(P.bal_flags + vcta));
+                if (done < seg) __nanosleep(200);
+            } while (done < seg);
+        }
+        __syncthreads();
+
+        const uint64_t r_raw = (uint64_t)vcta * SINGLE_THREADS + threadIdx.x;
+        const bool live = r_raw < P.R;
+        const uint64_t r = live ? r_raw : P.R - 1;
+        V3 m{__ldcg(P.state + r), __ldcg(P.state + P.R + r), __ldcg(P.state + 2 * P.R + r)};   // written by another SM: bypass L1
+        V3 e{0.0, 0.0, 1.0};
+        if (!AXIS_Z)
+            e = V3{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
+        const V3 edt{e.x * kdt, e.y * kdt, e.z * kdt};
+        const double c = P.sig[r * P.sig_rs] * P.sqrt_dt;
+        const float bm_scale = scale_to_bm(c);
+        const uint64_t seed = (uint64_t)P.seeds[r];
+        const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+        const uint32_t member = member_id(P, r);
+        auto advance = [&](const V3& cw, const double2* tp) {
+            double hz0 = P.h_const, hz1 = P.h_const;
+            if (FIELD_TAB) {
+                const double2 h = __ldg(tp);
+                hz0 = h.x; hz1 = h.y;
+            }
+            m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
+            if (RENORM) renormalise(m);
+        };
+        float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint32_t gblk = 0;
+        bool have = false;
+        auto need = [&](const uint32_t blk) {
+            if (!have || gblk != blk) {
+                philox_gauss6_f32<0>(key0, key1, blk, 0u, member, bm_scale, g, P.philox_m0, P.philox_m1);
+                gblk = blk;
+                have = true;
+            }
+        };
+        uint64_t j = ja;
+        // first sample of the launch whose state index is >= ja (P.bal_seg_k[seg], found on the host)
+        for (uint32_t k = P.bal_seg_k[seg];; ++k) {
+            const bool sample = k < P.k1 && (P.target[k] < jb || (last && P.target[k] == jb));
+            const uint64_t tgt = sample ? P.target[k] : jb;
+            if ((j & 1) && j < tgt) {
+                need((uint32_t)(j >> 1));
+                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tab + (j - P.j0));
+                ++j;
+            }
+            const uint32_t pairs = (uint32_t)((tgt - j) >> 1);
+            uint32_t blk = (uint32_t)(j >> 1);
+            const double2* tp = tab + (j - P.j0);
+            if (pairs != 0) need(blk);
+            for (uint32_t i = pairs; i != 0; --i, tp += 2) {
+                float gn[6];
+                philox_gauss6_f32<0>(key0, key1, ++blk, 0u, member, bm_scale, gn, P.philox_m0, P.philox_m1);
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tp);
+                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tp + 1);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) g[q] = gn[q];
+                gblk = blk;
+            }
+            j += 2ull * pairs;
+            if (j < tgt) {
+                need((uint32_t)(j >> 1));
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tab + (j - P.j0));
+                ++j;
+            }
+            if (!sample) break;
+            if (P.traj != nullptr && live) {
+                double* t = P.traj + (uint64_t)k * 3 * P.R + r;
+                t[0] = m.x; t[P.R] = m.y; t[2 * P.R] = m.z;
+            }
+            if (P.partial != nullptr) {
+                const double z = live ? m.z : 0.0;
+                cta_partial_sums<SINGLE_THREADS / 32>(live ? m.x : 0.0, live ? m.y : 0.0, z, z * z, red,
+                                                      P.partial + ((uint64_t)(k - P.k0) * n_vcta + vcta) * 4);
+            }
+        }
+        if (live) {
+            __stcg(P.state + r, m.x); __stcg(P.state + P.R + r, m.y); __stcg(P.state + 2 * P.R + r, m.z);
+        }
+        __syncthreads();                       // every thread's state is stored before the flag is raised
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(P.bal_flags + vcta), "r"(seg + 1) : "memory");
+        }
+    }
+}
+
+cudaError_t launch_heun_single_balanced(bool tab, bool axis_z, unsigned phys_grid, cudaStream_t s, const RunParams& P) {
+    const dim3 g(phys_grid), b(SINGLE_THREADS);
+    const bool renorm = P.renorm != 0;
+#define MB_HSB(T, A)                                                              \
+    if (renorm) heun_single_balanced_kernel<T, A, true><<<g, b, 0, s>>>(P);       \
+    else heun_single_balanced_kernel<T, A, false><<<g, b, 0, s>>>(P)
+    if (tab) { if (axis_z) { MB_HSB(true, true); } else { MB_HSB(true, false); } }
+    else { if (axis_z) { MB_HSB(false, true); } else { MB_HSB(false, false); } }
+#undef MB_HSB
+    return cudaGetLastError();
+}
+
+int heun_single_balanced_resident_ctas(bool tab, bool axis_z, bool renorm) {
+    int n = 0;
+    auto q = [&](auto kernel) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, SINGLE_THREADS, 0); };
+    if (tab) {
+        if (axis_z) { if (renorm) q(heun_single_balanced_kernel<true, true, true>); else q(heun_single_balanced_kernel<true, true, false>); }
+        else { if (renorm) q(heun_single_balanced_kernel<true, false, true>); else q(heun_single_balanced_kernel<true, false, false>); }
+    } else {
+        if (axis_z) { if (renorm) q(heun_single_balanced_kernel<false, true, true>); else q(heun_single_balanced_kernel<false, true, false>); }
+        else { if (renorm) q(heun_single_balanced_kernel<false, false, true>); else q(heun_single_balanced_kernel<false, false, false>); }
+    }
+    return n;
+}
+
+}  // namespace mb

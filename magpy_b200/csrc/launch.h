@@ -8,10 +8,16 @@ namespace mb {
 
 struct RunParams;
 
+constexpr int K1_LATENCY = 100;
+
 // noise: NOISE_PHILOX_F32 | NOISE_PHILOX_F64 | NOISE_INJECTED | NOISE_PHILOX_PACKED; tab: applied field from field_tab
-// min_blocks: register-allocation variant of the production (packed-noise) instantiation: 1 (free) or 7 CTAs per SM
+// min_blocks: variant of the production (packed-noise) instantiation: 1 (free registers), 7 (7 CTAs per SM) or
+// K1_LATENCY (small ensembles: applied-field table entries fetched one step pair ahead)
 cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, int min_blocks, unsigned grid, cudaStream_t s,
                                const RunParams& P);
+// K1b (heun_single_balanced.cu): the same integration as a persistent kernel over (time segment, member block) tasks
+cudaError_t launch_heun_single_balanced(bool tab, bool axis_z, unsigned phys_grid, cudaStream_t s, const RunParams& P);
+int heun_single_balanced_resident_ctas(bool tab, bool axis_z, bool renorm);
 int heun_single_resident_ctas(bool tab, bool axis_z, bool renorm, int min_blocks);
 cudaError_t launch_imid_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P);
 cudaError_t launch_heun_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);

@@ -187,6 +187,10 @@ struct Chunk {
 // the field table of a launch covers this many extra steps on either side
 constexpr uint64_t kMpMargin = 4;
 
+// K1b: at most this many time segments per launch, each at least kBalMinSteps long
+constexpr uint32_t kBalMaxSegments = 64;
+constexpr uint64_t kBalMinSteps = 1024;
+
 }  // namespace
 
 struct magpy_b200_plan {
@@ -210,6 +214,9 @@ struct magpy_b200_plan {
     int layout = 0;        // Heun cluster kernel: see cluster.cu
     bool use_table = false;
     bool axis_z = false;   // N = 1 and one shared easy axis exactly along +z: specialised Heun kernel
+    bool k1_balanced = false;   // K1b: multi-wave shards run as a persistent kernel over (time segment, member block) tasks
+    unsigned bal_phys = 0;      //   ... its physical grid (resident CTAs)
+    std::vector<uint32_t> bal_segments;   //   ... segments per chunk (1 = plain launch)
     int k1_min_blocks = 1; // K1: register-allocation variant (resident CTAs per SM asked of ptxas), see choose_k1_variant
     bool small = false;    // few particles: one thread per cluster, all moments in registers
     bool split = false;    //   ... implicit, one lane per particle (imid_split_kernel)
@@ -226,7 +233,8 @@ struct magpy_b200_plan {
     DevBuf<double> d_state_t;
     DevBuf<double> d_state0, d_state, d_axis, d_kred, d_sig, d_dip, d_dmat, d_vred, d_traj, d_sums, d_partial, d_tab, d_dW, d_stage;
     DevBuf<int64_t> d_seeds;
-    DevBuf<uint32_t> d_member_idx, d_member_j;
+    DevBuf<uint32_t> d_member_idx, d_member_j, d_bal_seg_k;
+    DevBuf<unsigned int> d_bal_sync;   // [1 + grid]: task counter, then one flag per member block
     DevBuf<double> d_mp;            // per-member material parameters: alpha | dt | h0 | Ts, [4][R]
     bool mp = false;                // per-member anisotropy / damping / field amplitude (N = 1): MP kernel instantiations
     magpy_b200_comm* comm = nullptr;   // all-reduce the sums over this communicator at the end of every run
@@ -243,7 +251,7 @@ struct magpy_b200_plan {
         d_state_t.release(); d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
         d_dmat.release(); d_vred.release();
         d_traj.release(); d_sums.release(); d_partial.release(); d_tab.release(); d_dW.release(); d_stage.release();
-        d_seeds.release(); d_member_idx.release(); d_member_j.release(); d_mp.release(); d_target.release(); d_newton.release();
+        d_seeds.release(); d_member_idx.release(); d_member_j.release(); d_bal_seg_k.release(); d_bal_sync.release(); d_mp.release(); d_target.release(); d_newton.release();
         if (stream) cudaStreamSynchronize(stream);
         for (auto e : ev_k) cudaEventDestroy(e);
         if (ev_begin) cudaEventDestroy(ev_begin);
@@ -386,10 +394,16 @@ void choose_k1_variant(magpy_b200_plan* pl, bool renorm) {
     if (pl->N != 1 || pl->implicit || plan_noise(pl) != mb::NOISE_PHILOX_PACKED) return;
     if (const char* env = std::getenv("MAGPY_B200_K1_MIN_BLOCKS")) {
         const int v = std::atoi(env);
-        if (v == 1 || v == 7) { pl->k1_min_blocks = v; return; }
+        if (v == 1 || v == 7 || v == mb::K1_LATENCY) { pl->k1_min_blocks = v; return; }
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    // below ~4 warps per SM sub-partition a step is (mostly) one warp's dependent chain (10 DFMAs deep, ~19 cycles each: 193 cycles
+    // per step however small the ensemble, profiles/r02_probe_c1_split_kernel.log); an applied-field table entry fetched at
+    // its point of use then adds its L2 latency to every step (334 cycles): the latency variant fetches it a pair ahead
+    // (profiles/r02_probe_c1.log: 1000 members 17.0 -> 11.3 ms per 1e5 steps, 37,888 members 24.5 -> 17.6 ms, break-even near
+    // 76k members = 4 CTAs per SM)
+    if (pl->use_table && pl->grid <= (unsigned)(4 * sms)) { pl->k1_min_blocks = mb::K1_LATENCY; return; }
     const int free_ctas = mb::heun_single_resident_ctas(pl->use_table, pl->axis_z, renorm, 1);
     const int tight_ctas = mb::heun_single_resident_ctas(pl->use_table, pl->axis_z, renorm, 7);
     if (free_ctas > 0 && tight_ctas > free_ctas && pl->grid > (unsigned)(sms * free_ctas) &&
@@ -595,7 +609,6 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     pl->axis_z = N == 1 && a->axis_stride == 0 && a->anisotropy_axis[0] == 0.0 && a->anisotropy_axis[1] == 0.0 &&
                  a->anisotropy_axis[2] == 1.0;
     choose_k1_variant(pl, a->renorm != 0);
-
     // chunking: bound the field table / injected-noise window and the partial-sum buffer
     uint64_t max_steps = 4ull << 20;
     if (const char* env = std::getenv("MAGPY_B200_MAX_CHUNK_STEPS")) {   // test hook: force many small launches
@@ -627,6 +640,27 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     for (const Chunk& c : pl->chunks) {
         pl->max_chunk_steps = std::max(pl->max_chunk_steps, c.j1 - c.j0);
         pl->max_chunk_samples = std::max(pl->max_chunk_samples, c.k1 - c.k0);
+    }
+
+    // K1b (heun_single_balanced.cu): a single-particle Heun shard of more than one wave of resident CTAs pays for a
+    // whole number of warps per SM sub-partition (section 7 of DESIGN.md); cut into (time segment, member block) tasks
+    // pulled by a grid of resident CTAs, every SM stays busy to the end.  MAGPY_B200_K1_BALANCE=0|1 overrides.
+    pl->bal_segments.assign(pl->chunks.size(), 1);
+    if (N == 1 && !pl->implicit && plan_noise(pl) == mb::NOISE_PHILOX_PACKED && pl->k1_min_blocks == 1 &&
+        !(a->member_anisotropy || a->member_damping || a->member_field_amplitude)) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+        const int per_sm = mb::heun_single_balanced_resident_ctas(pl->use_table, pl->axis_z, a->renorm != 0);
+        pl->bal_phys = (unsigned)(sms * std::max(1, per_sm));
+        bool on = pl->grid > pl->bal_phys;
+        if (const char* env = std::getenv("MAGPY_B200_K1_BALANCE")) on = std::atoi(env) != 0;
+        if (on) {
+            for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
+                const uint64_t span = pl->chunks[ci].j1 - pl->chunks[ci].j0;
+                pl->bal_segments[ci] = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kBalMaxSegments, span / kBalMinSteps));
+                if (pl->bal_segments[ci] > 1) pl->k1_balanced = true;
+            }
+        }
     }
 
     // memory budget
@@ -720,6 +754,26 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     }
     CU_TRY(cudaMemcpyAsync(pl->d_target.p, pl->target.data(), pl->S * 8, cudaMemcpyHostToDevice, pl->stream));
     pl->h2d += N * 16 + pl->S * 8;
+    std::vector<uint32_t> seg_k;
+    if (pl->k1_balanced) {
+        // first sample of the chunk whose state index is >= the first step of each time segment
+        seg_k.assign(pl->chunks.size() * kBalMaxSegments, 0);
+        for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
+            const Chunk& c = pl->chunks[ci];
+            const uint64_t span = c.j1 - c.j0, ns = pl->bal_segments[ci];
+            uint32_t k = c.k0;
+            for (uint64_t sgm = 0; sgm < ns; ++sgm) {
+                const uint64_t ja = c.j0 + span * sgm / ns;
+                while (k < c.k1 && pl->target[k] < ja) ++k;
+                seg_k[ci * kBalMaxSegments + sgm] = k;
+            }
+        }
+        CU_TRY(pl->d_bal_seg_k.alloc(seg_k.size(), pl->stream));
+        CU_TRY(pl->d_bal_sync.alloc(1 + (size_t)pl->grid, pl->stream));
+        CU_TRY(cudaMemcpyAsync(pl->d_bal_seg_k.p, seg_k.data(), seg_k.size() * 4, cudaMemcpyHostToDevice, pl->stream));
+        CU_TRY(cudaStreamSynchronize(pl->stream));
+        pl->h2d += seg_k.size() * 4;
+    }
     std::vector<int64_t> zero_seeds;
     const int64_t* seeds = a->seeds;
     if (!seeds) {
@@ -914,9 +968,24 @@ int plan_run(magpy_b200_plan* pl) {
             LAUNCH_TRY(mb::launch_field_table(pl->d_tab.p, c.j0, ns, pl->red.dt, second, pl->field_shape, pl->red.h0,
                                               pl->red.f, pl->stream));
         }
+        const bool balanced = pl->k1_balanced && pl->bal_segments[ci] > 1;
+        if (balanced) {   // task counter and per-block flags back to zero, this chunk's first-sample table
+            CU_TRY(cudaMemsetAsync(pl->d_bal_sync.p, 0, (size_t)(1 + pl->grid) * sizeof(unsigned int), pl->stream));
+            P.bal_vctas = pl->grid;
+            P.bal_segments = pl->bal_segments[ci];
+            P.bal_counter = pl->d_bal_sync.p;
+            P.bal_flags = pl->d_bal_sync.p + 1;
+            P.bal_seg_k = pl->d_bal_seg_k.p + ci * kBalMaxSegments;
+        }
         CU_TRY(cudaEventRecord(pl->ev_k[2 * ci], pl->stream));
-        int rc = launch_integrate(pl, P);
-        if (rc) return rc;
+        if (balanced) {
+            const uint64_t tasks = (uint64_t)pl->grid * P.bal_segments;
+            LAUNCH_TRY(mb::launch_heun_single_balanced(pl->use_table, pl->axis_z, (unsigned)std::min<uint64_t>(tasks, pl->bal_phys),
+                                                       pl->stream, P));
+        } else {
+            int rc = launch_integrate(pl, P);
+            if (rc) return rc;
+        }
         CU_TRY(cudaEventRecord(pl->ev_k[2 * ci + 1], pl->stream));
         if (c.k1 > c.k0) {
             LAUNCH_TRY(mb::launch_reduce_partials(pl->d_partial.p, pl->d_sums.p, c.k0, c.k1 - c.k0, pl->grid, pl->stream));
@@ -942,14 +1011,15 @@ int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
     st->kernel_launches = pl->launches;
     st->h2d_bytes = pl->h2d;
     st->d2h_bytes = pl->d2h;
-    st->kernel_family = pl->N == 1 ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SINGLE : MAGPY_B200_KERNEL_HEUN_SINGLE)
+    st->kernel_family = pl->N == 1 ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SINGLE
+                                      : MAGPY_B200_KERNEL_HEUN_SINGLE)
                         : pl->split ? MAGPY_B200_KERNEL_IMID_SPLIT
                         : pl->small ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SMALL : MAGPY_B200_KERNEL_HEUN_SMALL)
                         : pl->big   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_BIG
                         : pl->mma   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA
                         : pl->imid_mma ? MAGPY_B200_KERNEL_IMID_CLUSTER_MMA
                                     : (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER : MAGPY_B200_KERNEL_HEUN_CLUSTER);
-    st->kernel_variant = (pl->N == 1 && !pl->implicit) ? (uint64_t)pl->k1_min_blocks : 0;
+    st->kernel_variant = (pl->N == 1 && !pl->implicit) ? (pl->k1_balanced ? 200u : (uint64_t)pl->k1_min_blocks) : 0;
     if (pl->ran) {
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, pl->ev_begin, pl->ev_end));

@@ -221,28 +221,33 @@ class EnsembleModel:
                 consume(out, idx)
             del pending[:]
         stats = []
+        converted = {}
         reduced_on_device = False
         for idx in groups:
             first = int(idx[0])
             params = dict(base, **{k: self._overrides[k][first] for k in other_keys})
 
+            def member_values(key):
+                # one vectorised conversion of the whole override list (1M members: a Python loop would take seconds)
+                if key not in converted:
+                    converted[key] = np.asarray(self._overrides[key], dtype=np.float64)
+                return converted[key][idx]
+
             def member_array(key):
                 if key in self._overrides:
-                    return np.ascontiguousarray(
-                        np.asarray([self._overrides[key][i] for i in idx], dtype=np.float64).reshape(len(idx), N, 3))
+                    return np.ascontiguousarray(member_values(key).reshape(len(idx), N, 3))
                 return np.ascontiguousarray(np.asarray(base[key], dtype=np.float64).reshape(N, 3))
 
             radius = params['radius']
             if N == 1 and 'radius' in self._overrides:
-                radius = np.ascontiguousarray(
-                    np.asarray([self._overrides['radius'][i] for i in idx], dtype=np.float64).reshape(len(idx), 1))
+                radius = np.ascontiguousarray(member_values('radius').reshape(len(idx), 1))
             temperature = params['temperature']
             if N == 1 and 'temperature' in self._overrides:
-                temperature = np.asarray([self._overrides['temperature'][i] for i in idx], dtype=np.float64)
+                temperature = np.ascontiguousarray(member_values('temperature').reshape(len(idx)))
 
             def member_scalar(key, column=False):
                 if key in self._overrides and key in fast:
-                    v = np.asarray([np.asarray(self._overrides[key][i], dtype=np.float64).reshape(-1)[0] for i in idx])
+                    v = member_values(key).reshape(len(idx))
                     return np.ascontiguousarray(v.reshape(len(idx), 1) if column else v)
                 return params[key]
             args = (radius, member_scalar('anisotropy', True), member_array('anisotropy_axis'),
