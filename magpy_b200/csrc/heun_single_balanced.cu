@@ -37,10 +37,15 @@ __global__ void __launch_bounds__(SINGLE_THREADS, 6) heun_single_balanced_kernel
         const uint64_t ja = P.j0 + span * seg / n_seg, jb = P.j0 + span * (seg + 1) / n_seg;
         const bool last = seg + 1 == n_seg;
         if (threadIdx.x == 0 && seg > 0) {     // the block's previous segment has parked its state
-            unsigned int done;
+            unsigned int done, spins = 0;
             do {
                 asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(done) : "l"(P.bal_flags + vcta));
-                if (done < seg) __nanosleep(200);
+                if (done < seg) {
+                    __nanosleep(200);
+                    // the predecessor was handed out earlier to a running CTA, so this wait is bounded by one segment's run
+                    // time (milliseconds); a minute of waiting is a bug: fail the launch instead of hanging the device
+                    if (++spins > (1u << 28)) __trap();
+                }
             } while (done < seg);
         }
         __syncthreads();
