@@ -188,8 +188,8 @@ struct Chunk {
 constexpr uint64_t kMpMargin = 4;
 
 // K1b: at most this many time segments per launch, each at least kBalMinSteps long
-constexpr uint32_t kBalMaxSegments = 64;
-constexpr uint64_t kBalMinSteps = 1024;
+constexpr uint32_t kBalMaxSegments = 128;   // 125,000 members x 1e5 steps: 64 segments 54.9 ms, 128 54.0, 256 54.5
+constexpr uint64_t kBalMinSteps = 512;
 
 }  // namespace
 
@@ -646,7 +646,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     // whole number of warps per SM sub-partition (section 7 of DESIGN.md); cut into (time segment, member block) tasks
     // pulled by a grid of resident CTAs, every SM stays busy to the end.  MAGPY_B200_K1_BALANCE=0|1 overrides.
     pl->bal_segments.assign(pl->chunks.size(), 1);
-    if (N == 1 && !pl->implicit && plan_noise(pl) == mb::NOISE_PHILOX_PACKED && pl->k1_min_blocks == 1 &&
+    if (N == 1 && !pl->implicit && plan_noise(pl) == mb::NOISE_PHILOX_PACKED && pl->k1_min_blocks != mb::K1_LATENCY &&
         !(a->member_anisotropy || a->member_damping || a->member_field_amplitude)) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
@@ -660,6 +660,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
                 pl->bal_segments[ci] = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kBalMaxSegments, span / kBalMinSteps));
                 if (pl->bal_segments[ci] > 1) pl->k1_balanced = true;
             }
+            if (pl->k1_balanced) pl->k1_min_blocks = 1;   // short launches of the same plan use the free-allocation kernel
         }
     }
 
