@@ -103,15 +103,16 @@ class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu')
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.t_mark = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '40'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -121,7 +122,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(',')]))
+
+    def mark(self):
+        """Start of the timed region: samples from here on are 'timed', earlier ones (the warm-up passes of the same
+        workload) are only used when the timed region is too short to catch any."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -131,18 +137,27 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
+
+        def digest(rows):
+            sm, mx, reasons = [], [], set()
+            for r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                except (ValueError, IndexError):
+                    continue
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            return sm, mx, reasons
+        timed = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
+        sm, mx, reasons = digest(timed)
+        window = 'timed passes'
+        if len(sm) < 3:   # a timed region of a few tens of ms: add the samples of the warm-up passes of the same workload
+            sm, mx, reasons = digest([r for _, r in self.rows])
+            window = 'warm-up + timed passes (the timed region alone caught %d samples)' % len(timed)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'reasons': sorted(reasons), 'window': window, 'period_ms': 40}
 
 
 # --------------------------------------------------------------------------------------
@@ -364,11 +379,12 @@ def ours(args):
     peak_tflops = max(dfma_tflops, dmma_tflops)
 
     plan = _make_plan(core, arr, seeds_all[lo:hi], R, lo, local_rank, comm)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     _timed_passes(plan, comm, max(args.warmup, 0))
     launches0 = plan.sync()['kernel_launches']
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     wall0 = time.perf_counter()
     t_dev, t_int, st = _timed_passes(plan, comm, args.steps)
     barrier()
