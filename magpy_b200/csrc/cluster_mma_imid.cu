@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(512, 1) imid_cluster_mma_kernel(const __grid_c
     };
     double* red_a = sm_red;
     double* red_b = sm_red + (size_t)G * MB;
+    double* red_c = sm_red + (size_t)2 * G * MB;   // the tolerance norm has its own slab: its readers are not fenced off
+                                                   // from the first iteration's writers of red_a by a barrier
     // field of the own particle of member e at moments x: anisotropy + applied + dipolar (acc)
     auto field = [&](const int e, const V3& ax, const V3& x, const double (&acc)[3][2][2], const double hz) {
         const double s = dot(x, ax) * kred;
@@ -146,10 +148,10 @@ __global__ void __launch_bounds__(512, 1) imid_cluster_mma_kernel(const __grid_c
             }
             group_barrier(bar_id, bar_n);          // every warp of the group has multiplied x0
             put(X);
-            group_sum2(part, red_a);
+            group_sum2(part, red_c);
             group_barrier(bar_id, bar_n);          // X and the norm partials are visible
             double tol[2], err[2];
-            group_read2(tol, red_a);
+            group_read2(tol, red_c);
             // err > tol is tested on the squares (no square root in the dependent chain of an iteration)
             int iter[2] = {1000, 1000};
             unsigned long long done[2] = {0ull, 0ull};

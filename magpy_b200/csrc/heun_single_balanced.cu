@@ -9,13 +9,14 @@
 // segment-major order.  A block's state is parked in HBM between its segments (24 B per member per segment — the same
 // hand-over the host-side chunking uses) and a per-block flag orders a segment after its predecessor (release / acquire;
 // the predecessor was handed out earlier to a CTA that is running, so the wait cannot deadlock).
-// Measured (profiles/r02_probe_k1_balance.log, 100,000 steps in the bench's sine field): 250,000 members 0.925 -> 0.99 of
-// the 1M rate, 500,000 0.97 -> 1.01, 1M +1.8 %; 125,000 members 0.78-0.88 -> 0.92.  What keeps the last from 0.99 was
-// traced (profiles/r02_probe_k1_trace_fixed_segments.log): the sm_100a warp scheduler serves the oldest warps first and a
+// Measured (profiles/r02_probe_k1_balance*.log, 100,000 steps in the bench's sine field) with 6 CTAs per SM: 250,000 members
+// 0.925 -> 0.99 of the 1M rate, 500,000 0.97 -> 1.01, 1M +1.8 %; 125,000 members 0.78-0.88 -> 0.92.  What kept the last
+// from 0.99 was traced (profiles/r02_probe_k1_trace_fixed_segments.log): the sm_100a warp scheduler serves the oldest warps first and a
 // single warp already takes 45 % of the FP64 pipe, so of the 6 CTAs resident on an SM the youngest two crawl — task
 // durations per physical CTA differ by 9.5-19x on the SAME SM — a block that lands on one is held for milliseconds, and
 // with only 1.1 blocks per CTA the launch ends in a ~10 ms tail of sequential stragglers (slot utilisation 0.85; 0.994
-// at 1M members).  Two remedies were tried and did not pay: a FIFO of ready blocks instead of the in-order hand-out
+// at 1M members).  The remedy that works is to leave the starved CTAs out — FOUR CTAs per SM, see below: 125,000 members
+// 0.98.  Two others were tried and did not pay: a FIFO of ready blocks instead of the in-order hand-out
 // (same times), and slices sized per CTA for equal duration (profiles/r02_probe_k1_trace_adaptive_slices.log: utilisation
 // 0.89, but 60 % more tasks and their overhead: 57.3 ms against 54.9, and 3 % slower at 1M).
 // Same Philox counters and arithmetic as K1: bit-identical results (tests/test_parity_gpu.py).
@@ -24,8 +25,13 @@
 
 namespace mb {
 
-// resident CTAs per SM as the plain kernel gets them from a free register allocation: 6 with the easy axis along z (76
-// registers), 5 with a general axis (86) — forcing the latter into 80 registers costs 4 % (profiles/r02_probe_k1_balance_first.log)
+// The register allocation is the plain kernel's (6 CTAs per SM with the easy axis along z: 76 registers; 5 with a general
+// axis: 86 — forcing the latter into 80 costs 4 %), but only FOUR CTAs per SM are launched
+// (profiles/r02_probe_k1_bal_ctas.log): the FP64 pipe is saturated by the four oldest warps of a sub-partition, the fifth
+// and sixth CTA of an SM only hold blocks back — 125,000 members x 1e5 steps: 54.1 ms with 6 CTAs per SM, 52.3 with 5,
+// 51.1 with 4, 52.4 with 3 (1M members: 403.3 / 401.1 / 402.6 / 417.7).  Spending the freed registers on a prefetch of
+// the next step pair's field-table entries was measured and is slower at full load (1M: 417 ms,
+// profiles/r02_probe_k1_bal_ctas_prefetch.log).
 template <bool FIELD_TAB, bool AXIS_Z, bool RENORM>
 __global__ void __launch_bounds__(SINGLE_THREADS, AXIS_Z ? 6 : 5) heun_single_balanced_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
@@ -82,6 +88,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, AXIS_Z ? 6 : 5) heun_single_ba
             m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
             if (RENORM) renormalise(m);
         };
+
         float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         uint32_t gblk = 0;
         bool have = false;

@@ -651,8 +651,12 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
         const int per_sm = mb::heun_single_balanced_resident_ctas(pl->use_table, pl->axis_z, a->renorm != 0);
-        pl->bal_phys = (unsigned)(sms * std::max(1, per_sm));
-        bool on = pl->grid > pl->bal_phys;
+        // four CTAs per SM saturate the FP64 pipe (oldest-first warp scheduling); more only hold blocks back
+        int use_per_sm = std::max(1, std::min(per_sm, 4));
+        if (const char* env = std::getenv("MAGPY_B200_K1_BAL_CTAS")) use_per_sm = std::max(1, std::min(per_sm, std::atoi(env)));
+        const bool on_default = pl->grid > (unsigned)(sms * use_per_sm);
+        pl->bal_phys = (unsigned)(sms * use_per_sm);
+        bool on = on_default;
         if (const char* env = std::getenv("MAGPY_B200_K1_BALANCE")) on = std::atoi(env) != 0;
         if (on) {
             for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {

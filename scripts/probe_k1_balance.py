@@ -16,7 +16,7 @@ def run(R, steps, balance, renorm=False, axis=(0, 0, 1.0)):
     return st['particle_steps'] / (st['integrate_ms'] * 1e-3), st['integrate_ms'], st['kernel_variant']
 
 base = None
-for R in (1000000, 500000, 250000, 125000, 132608, 151552, 200000, 113664):
+for R in (1000000, 500000, 250000, 125000, 132608, 151552, 200000, 113664, 100000, 80000):
     row = []
     for b in ('0', '1'):
         rate, ms, var = run(R, 100000, b)

@@ -510,6 +510,39 @@ def test_per_member_material_parameters_single_particle(orc, core, implicit, sha
                                field_amplitude=1e4, field_frequency=base.f)
 
 
+@pytest.mark.parametrize('implicit', [False, True])
+def test_per_member_parameters_do_not_depend_on_chunking(core, implicit, monkeypatch):
+    """The per-member-parameter kernels carry every member's own step index between launches (the members' schedules differ
+    by a step at exact ties): many short launches — sampling launches and pure-advance launches — give bit-identical
+    results to one launch, with the Philox stream and with more samples than steps."""
+    rng = np.random.default_rng(5)
+    R = 200
+    K = rng.uniform(2e4, 9e4, R).reshape(R, 1)
+    al = rng.uniform(0.05, 0.5, R)
+    H0 = rng.uniform(0.0, 3e4, R)
+    seeds = np.arange(R) * 3 + 11
+    for S, t_end in ((17, 2.4e-11 if not implicit else 1.12e-10), (3, 2.4e-11 if not implicit else 1.12e-10), (500, 3e-11 if not implicit else 1.2e-10)):
+        c = ol.make_case(N=1, dt=1e-13 if not implicit else 1e-12, t_end=t_end, S=S, implicit=implicit, field_shape='sine',
+                         H0=1.5e4, f=5e9, axis=[[0.6, 0, 0.8]], m0=[[0, 0, 1.0]])
+
+        def run():
+            return core.simulate_ensemble(c.radius, K, c.axis, c.m0, c.location, c.Ms, al, c.T, False, True, implicit, c.dt,
+                                          c.t_end, c.S, seeds, field_shape='sine', field_amplitude=H0, field_frequency=c.f,
+                                          stream_offset=9)
+        monkeypatch.delenv('MAGPY_B200_MAX_CHUNK_STEPS', raising=False)
+        whole = run()
+        for chunk in ('7', '40'):
+            monkeypatch.setenv('MAGPY_B200_MAX_CHUNK_STEPS', chunk)
+            parts = run()
+            assert parts['stats']['kernel_launches'] > whole['stats']['kernel_launches'] + 2
+            assert np.array_equal(whole['trajectories'], parts['trajectories']), (S, chunk)
+            assert np.array_equal(whole['final'], parts['final'])
+            assert np.allclose(whole['sums'], parts['sums'], rtol=1e-13, atol=0)
+            if implicit:
+                assert whole['stats']['newton_iterations'] == parts['stats']['newton_iterations']
+        assert np.array_equal(whole['final'], whole['trajectories'][..., -1])
+
+
 def test_single_simulate_api_and_schedule_edges(orc, core):
     """core.simulate keeps the reference's dict; sampling finer than the time step repeats states."""
     c = ol.make_case(N=2, dt=1e-12, t_end=1e-11, S=40, implicit=False)    # Ts < dt: zero-order hold repeats
