@@ -32,8 +32,11 @@ namespace mb {
 // 51.1 with 4, 52.4 with 3 (1M members: 403.3 / 401.1 / 402.6 / 417.7).  Spending the freed registers on a prefetch of
 // the next step pair's field-table entries was measured and is slower at full load (1M: 417 ms,
 // profiles/r02_probe_k1_bal_ctas_prefetch.log).
+#ifndef MB_K1B_MIN_BLOCKS
+#define MB_K1B_MIN_BLOCKS (AXIS_Z ? 6 : 5)   // tuning knob (scripts/build_variant.sh): a free allocation (82 registers) is 1.9 % slower
+#endif
 template <bool FIELD_TAB, bool AXIS_Z, bool RENORM>
-__global__ void __launch_bounds__(SINGLE_THREADS, AXIS_Z ? 6 : 5) heun_single_balanced_kernel(const __grid_constant__ RunParams P) {
+__global__ void __launch_bounds__(SINGLE_THREADS, MB_K1B_MIN_BLOCKS) heun_single_balanced_kernel(const __grid_constant__ RunParams P) {
     __shared__ double red[(SINGLE_THREADS / 32) * 4];
     __shared__ unsigned int s_task;
     const uint32_t n_vcta = P.bal_vctas, n_seg = P.bal_segments;
