@@ -31,28 +31,31 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB == 7 ? 7 : 1) heun_single
     if (!AXIS_Z)
         e = V3{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
     const double alpha = MP ? P.mp_alpha[r] : P.alpha, dt = MP ? P.mp_dt[r] : P.dt;
-    const double kdt = P.k_red[0] * dt;
-    const V3 edt{e.x * kdt, e.y * kdt, e.z * kdt};
-    const double c = P.sig[r * P.sig_rs] * (MP ? sqrt(dt) : P.sqrt_dt);   // per-member sigma when the radii differ between members
+    // heun_single_step works in HALF units (llg_math.cuh): k dt e / 2, dt / 2, sigma sqrt(dt) w / 2.  The halves of the
+    // ensemble-wide constants come from the host as kernel parameters (uniform-register operands)
+    const double hkdt = MP ? 0.5 * (P.k_red[0] * dt) : P.half_kdt0;
+    const V3 eh{e.x * hkdt, e.y * hkdt, e.z * hkdt};
+    // per-member sigma when the radii differ between members; ch = sigma sqrt(dt) / 2
+    const double ch = 0.5 * (P.sig[r * P.sig_rs] * (MP ? sqrt(dt) : P.sqrt_dt));
     const double mp_h0 = MP ? P.mp_h0[r] : 0.0, mp_Ts = MP ? P.mp_Ts[r] : 0.0;
-    const double hdt = MP ? mp_h0 * dt : dt;            // multiplies the applied field (MP: unit waveform in the table)
-    const float bm_scale = scale_to_bm(c);
+    const double hdth = MP ? 0.5 * (mp_h0 * dt) : P.half_dt;   // multiplies the applied field (MP: unit waveform in the table)
+    const float bm_scale = scale_to_bm(ch);
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t member = member_id(P, r);
 
-    // one Heun step from the scaled increment cw; `tp` = this step's entry of the field table
+    // one Heun step from the HALVED scaled increment cw; `tp` = this step's entry of the field table
     auto advance = [&](const V3& cw, const double2* tp) {
         double hz0 = MP ? 1.0 : P.h_const, hz1 = hz0;
         if (FIELD_TAB) {
             const double2 h = __ldg(tp);
             hz0 = h.x; hz1 = h.y;
         }
-        m = heun_single_step<AXIS_Z>(m, e, edt, alpha, hdt, cw, hz0, hz1);
+        m = heun_single_step<AXIS_Z>(m, e, eh, alpha, hdth, cw, hz0, hz1);
         if (RENORM) renormalise(m);
     };
     auto advance_h = [&](const V3& cw, const double2 h) {   // the same with the table entry already in registers
-        m = heun_single_step<AXIS_Z>(m, e, edt, alpha, hdt, cw, h.x, h.y);
+        m = heun_single_step<AXIS_Z>(m, e, eh, alpha, hdth, cw, h.x, h.y);
         if (RENORM) renormalise(m);
     };
 
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB == 7 ? 7 : 1) heun_single
     bool have = false;
     auto need = [&](const uint32_t blk) {
         if (!have || gblk != blk) {
-            philox_gauss6_f32<MB_PHILOX_SPLIT>(key0, key1, blk, 0u, member, bm_scale, g, P.philox_m0, P.philox_m1);
+            philox_gauss6_f32<MB_PHILOX_SPLIT>(key0, key1, blk, 0u, member, bm_scale, g, P.philox_m0, P.philox_m1, P.bm_mask_r, P.bm_mask_a);
             gblk = blk;
             have = true;
         }
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB == 7 ? 7 : 1) heun_single
                 float gn[6];
                 double2 na, nb;
                 if (PREFETCH_TAB) { na = __ldg(tp + 2); nb = __ldg(tp + 3); }   // the table is allocated with a margin of rows
-                philox_gauss6_f32<MB_PHILOX_SPLIT>(key0, key1, ++blk, 0u, member, bm_scale, gn, P.philox_m0, P.philox_m1);
+                philox_gauss6_f32<MB_PHILOX_SPLIT>(key0, key1, ++blk, 0u, member, bm_scale, gn, P.philox_m0, P.philox_m1, P.bm_mask_r, P.bm_mask_a);
                 if (PREFETCH_TAB) {
                     advance_h(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, ha);
                     advance_h(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, hb);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MINB == 7 ? 7 : 1) heun_single
         } else {
             const double2* tp = tab + (j - tab0);
 #pragma unroll 2
-            for (; j < tgt; ++j, ++tp) advance(draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, c, bm_scale), tp);
+            for (; j < tgt; ++j, ++tp) advance(draw_scaled<NOISE>(P, key0, key1, j, 0u, member, r, ch, bm_scale), tp);
         }
         if (k < P.k1) {
             if (P.traj != nullptr && live) {

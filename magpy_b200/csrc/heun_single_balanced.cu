@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1B_MIN_BLOCKS) heun_single
     __shared__ unsigned int s_task;
     const uint32_t n_vcta = P.bal_vctas, n_seg = P.bal_segments;
     const uint64_t n_tasks = (uint64_t)n_vcta * n_seg;
-    const double alpha = P.alpha, dt = P.dt, kdt = P.k_red[0] * dt;
+    const double alpha = P.alpha, hkdt = P.half_kdt0, hdt = P.half_dt;   // half units: llg_math.cuh, heun_single_step
     const double2* tab = reinterpret_cast<const double2*>(P.field_tab);
 
     for (;;) {
@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1B_MIN_BLOCKS) heun_single
         V3 e{0.0, 0.0, 1.0};
         if (!AXIS_Z)
             e = V3{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
-        const V3 edt{e.x * kdt, e.y * kdt, e.z * kdt};
-        const double c = P.sig[r * P.sig_rs] * P.sqrt_dt;
-        const float bm_scale = scale_to_bm(c);
+        const V3 eh{e.x * hkdt, e.y * hkdt, e.z * hkdt};
+        const double ch = 0.5 * (P.sig[r * P.sig_rs] * P.sqrt_dt);
+        const float bm_scale = scale_to_bm(ch);
         const uint64_t seed = (uint64_t)P.seeds[r];
         const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
         const uint32_t member = member_id(P, r);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1B_MIN_BLOCKS) heun_single
                 const double2 h = __ldg(tp);
                 hz0 = h.x; hz1 = h.y;
             }
-            m = heun_single_step<AXIS_Z>(m, e, edt, alpha, dt, cw, hz0, hz1);
+            m = heun_single_step<AXIS_Z>(m, e, eh, alpha, hdt, cw, hz0, hz1);
             if (RENORM) renormalise(m);
         };
 
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1B_MIN_BLOCKS) heun_single
         bool have = false;
         auto need = [&](const uint32_t blk) {
             if (!have || gblk != blk) {
-                philox_gauss6_f32<0>(key0, key1, blk, 0u, member, bm_scale, g, P.philox_m0, P.philox_m1);
+                philox_gauss6_f32<0>(key0, key1, blk, 0u, member, bm_scale, g, P.philox_m0, P.philox_m1, P.bm_mask_r, P.bm_mask_a);
                 gblk = blk;
                 have = true;
             }
@@ -116,9 +116,21 @@ __global__ void __launch_bounds__(SINGLE_THREADS, MB_K1B_MIN_BLOCKS) heun_single
             uint32_t blk = (uint32_t)(j >> 1);
             const double2* tp = tab + (j - P.j0);
             if (pairs != 0) need(blk);
-            for (uint32_t i = pairs; i != 0; --i, tp += 2) {
+            uint32_t i = pairs;
+            // two step pairs per trip: the generator alternates between the two blocks of increments, no copies
+            for (; i >= 2; i -= 2, tp += 4) {
                 float gn[6];
-                philox_gauss6_f32<0>(key0, key1, ++blk, 0u, member, bm_scale, gn, P.philox_m0, P.philox_m1);
+                philox_gauss6_f32<0>(key0, key1, ++blk, 0u, member, bm_scale, gn, P.philox_m0, P.philox_m1, P.bm_mask_r, P.bm_mask_a);
+                advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tp);
+                advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tp + 1);
+                philox_gauss6_f32<0>(key0, key1, ++blk, 0u, member, bm_scale, g, P.philox_m0, P.philox_m1, P.bm_mask_r, P.bm_mask_a);
+                advance(V3{widen_f32(gn[0]), widen_f32(gn[1]), widen_f32(gn[2])}, tp + 2);
+                advance(V3{widen_f32(gn[3]), widen_f32(gn[4]), widen_f32(gn[5])}, tp + 3);
+                gblk = blk;
+            }
+            for (; i != 0; --i, tp += 2) {
+                float gn[6];
+                philox_gauss6_f32<0>(key0, key1, ++blk, 0u, member, bm_scale, gn, P.philox_m0, P.philox_m1, P.bm_mask_r, P.bm_mask_a);
                 advance(V3{widen_f32(g[0]), widen_f32(g[1]), widen_f32(g[2])}, tp);
                 advance(V3{widen_f32(g[3]), widen_f32(g[4]), widen_f32(g[5])}, tp + 1);
 #pragma unroll

@@ -29,40 +29,43 @@ __device__ __forceinline__ V3 llg_f(const V3& m, const V3& g, const double alpha
     return V3{-fma(alpha, q.x, p.x), -fma(alpha, q.y, p.y), -fma(alpha, q.z, p.z)};
 }
 
-// One Heun step of a single macrospin in 40 fp64 instructions (47 with a general easy axis).
-// With u = g + alpha (m x g) the LLG increment is f(m,g) = -m x u, so the predictor
-// x~ = m + f(m,g) and the corrector m' = (m + x~)/2 + f(x~,g~)/2 are accumulated directly in the
-// FMAs of the second cross product (no separate adds, and f1 is never materialised).
-// `dt` only multiplies the applied field here (the anisotropy term carries it in edt = k dt e): the MP instantiations
-// pass h0_r dt_r with the unit waveform in hz0 / hz1.
+// One Heun step of a single macrospin in 37 fp64 instructions (44 with a general easy axis), everything in HALF units.
+// With u = g + alpha (m x g) the LLG increment is f(m,g) = -m x u.  Fed with HALF the stage-1 argument, g1/2, the second
+// cross product yields the midpoint h = (m + x~)/2 = m - m x u1/2 directly in its FMAs; the predictor is x~ = 2 h - m
+// (one FMA per component) and the corrector m' = h - x~ x u2/2 is accumulated in the FMAs of the last cross product.
+// The round-1 form (predictor from the full-size u1, then 0.5 x~ and 0.5 m + 0.5 x~) spent three more multiplies.
+// Arguments: eh = k dt e / 2, dth = dt / 2 (times the field amplitude in the MP instantiations, whose table holds the
+// unit waveform), cwh = sigma sqrt(dt) w / 2 (the Box-Muller scale carries the 1/2), hz0 / hz1 = applied field at t, t + dt.
+// On sm_100a an FP64 instruction holds its sub-partition's issue port for 2 cycles, 3 when all three operands are
+// distinct registers (scripts/micro/dfma_operands.cu), and the kernel is bound by exactly that:
+// what counts is the number of FP64 instructions and of three-register DFMAs, not the flop count.
 template <bool AXIS_Z>
-__device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V3& edt, const double alpha,
-                                               const double dt, const V3& cw, const double hz0, const double hz1) {
-    // stage 1: g = h(m,t) dt + sigma sqrt(dt) w
+__device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V3& eh, const double alpha,
+                                               const double dth, const V3& cwh, const double hz0, const double hz1) {
+    // stage 1: g/2 = (h(m,t) dt + sigma sqrt(dt) w) / 2
     V3 g;
     if (AXIS_Z) {  // easy axis = z: h = (k m_z + h_app) z, two fp64 ops instead of seven
-        g = V3{cw.x, cw.y, fma(m.z, edt.z, fma(hz0, dt, cw.z))};
+        g = V3{cwh.x, cwh.y, fma(m.z, eh.z, fma(hz0, dth, cwh.z))};
     } else {
         const double s = dot(m, e);
-        g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz0, dt, cw.z))};
+        g = V3{fma(s, eh.x, cwh.x), fma(s, eh.y, cwh.y), fma(s, eh.z, fma(hz0, dth, cwh.z))};
     }
     V3 p = cross(m, g);
     V3 u{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
-    const V3 mt{fma(-m.y, u.z, fma(m.z, u.y, m.x)), fma(-m.z, u.x, fma(m.x, u.z, m.y)),
-                fma(-m.x, u.y, fma(m.y, u.x, m.z))};
+    const V3 h{fma(-m.y, u.z, fma(m.z, u.y, m.x)), fma(-m.z, u.x, fma(m.x, u.z, m.y)),
+               fma(-m.x, u.y, fma(m.y, u.x, m.z))};
+    const V3 mt{fma(2.0, h.x, -m.x), fma(2.0, h.y, -m.y), fma(2.0, h.z, -m.z)};
     // stage 2 at (x~, t+dt), same Wiener increment
     if (AXIS_Z) {
-        g = V3{cw.x, cw.y, fma(mt.z, edt.z, fma(hz1, dt, cw.z))};
+        g = V3{cwh.x, cwh.y, fma(mt.z, eh.z, fma(hz1, dth, cwh.z))};
     } else {
         const double s = dot(mt, e);
-        g = V3{fma(s, edt.x, cw.x), fma(s, edt.y, cw.y), fma(s, edt.z, fma(hz1, dt, cw.z))};
+        g = V3{fma(s, eh.x, cwh.x), fma(s, eh.y, cwh.y), fma(s, eh.z, fma(hz1, dth, cwh.z))};
     }
     p = cross(mt, g);
     u = V3{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
-    const V3 hm{0.5 * mt.x, 0.5 * mt.y, 0.5 * mt.z};
-    const V3 h{fma(0.5, m.x, hm.x), fma(0.5, m.y, hm.y), fma(0.5, m.z, hm.z)};
-    return V3{fma(-hm.y, u.z, fma(hm.z, u.y, h.x)), fma(-hm.z, u.x, fma(hm.x, u.z, h.y)),
-              fma(-hm.x, u.y, fma(hm.y, u.x, h.z))};
+    return V3{fma(-mt.y, u.z, fma(mt.z, u.y, h.x)), fma(-mt.z, u.x, fma(mt.x, u.z, h.y)),
+              fma(-mt.x, u.y, fma(mt.y, u.x, h.z))};
 }
 
 // Solve the 3x3 system A d = b of one particle's quasi-Newton update in registers.  The reference hands its

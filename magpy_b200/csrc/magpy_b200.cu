@@ -912,6 +912,8 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.clampA = std::sqrt(2 * 1000.0 * std::abs(std::log(rd.dt)));  // lib/integrators.cpp:598-599
     P.h_const = rd.h0;
     P.k_red = pl->d_kred.p;
+    P.half_kdt0 = 0.5 * (rd.k_red[0] * rd.dt);
+    P.half_dt = 0.5 * rd.dt;
     P.sig = pl->d_sig.p;
     P.sig_rs = (pl->mp || a->radius_stride != 0 || a->member_temperature != nullptr) ? 1 : 0;
     if (pl->mp) {
@@ -938,6 +940,8 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.coarsen_log2 = a->noise_coarsen_log2;
     P.philox_m0 = 0xD2511F53u;
     P.philox_m1 = 0xCD9E8D57u;
+    P.bm_mask_r = 0x007fffffu;
+    P.bm_mask_a = 0x007fffe0u;
     P.state = pl->d_state.p;
     P.state_t = pl->d_state_t.p;
     P.target = pl->d_target.p;

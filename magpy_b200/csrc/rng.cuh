@@ -41,8 +41,11 @@ __host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint3
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
                                                        uint32_t k0, uint32_t k1) {
+#ifndef MB_ABL_ROUNDS
+#define MB_ABL_ROUNDS 10   // timing ablation only (scripts/experiments/probe_k1_ablation.py): anything but 10 is not Philox4x32-10
+#endif
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < MB_ABL_ROUNDS; ++r) {
         uint32_t h0, l0, h1, l1;
         mulhilo32(0xD2511F53u, c0, h0, l0);
         mulhilo32(0xCD9E8D57u, c2, h1, l1);
@@ -91,7 +94,9 @@ __device__ __forceinline__ void philox4x32_10_split(uint32_t& c0, uint32_t& c1, 
 // mantissa shifted by 3) makes the Heun kernel 9 % slower end to end (2.22e11 vs 2.44e11 particle-steps/s):
 // the kernel has no issue slots to spare for 24 more instructions per step pair.  F2F stays.
 __device__ __forceinline__ double widen_f32(float f) {
-#ifdef MB_WIDEN_INT
+#ifdef MB_ABL_NOF2F   // timing ablation: a reinterpretation instead of the conversion (wrong values, same dependencies)
+    return __hiloint2double((int)(__float_as_uint(f) >> 4), 0);
+#elif defined(MB_WIDEN_INT)
     const uint32_t b = __float_as_uint(f);
     const uint32_t hi = (((b & 0x7fffffffu) >> 3) + 0x38000000u) | (b & 0x80000000u);
     const uint32_t lo = b << 29;
@@ -141,11 +146,13 @@ __device__ __forceinline__ void philox_gauss3_f32(uint32_t seed_lo, uint32_t see
 }
 
 // Packed mode: SIX draws of N(0, amp^2) from one Philox block, i.e. the increments of the two
-// steps s = 2b and s = 2b + 1 (s = 0-based step index) of one (member, particle).  The 128 bits
-// w0:w1:w2:w3 are cut, most significant first, into three (24-bit radius field, 18-bit angle) pairs;
-// the top 22 bits of each radius field are used, as cell midpoints (see bm_pair_packed; radius up to 5.65 sigma);
-// 2^18 equidistant directions reproduce every circular moment below order 2^18.
-//   pair 0 -> g[0], g[1]    pair 1 -> g[2], g[3]    pair 2 -> g[4], g[5]
+// steps s = 2b and s = 2b + 1 (s = 0-based step index) of one (member, particle).  The 128 bits are cut into three
+// (23-bit radius field, 18-bit angle) pairs (layout in philox_gauss6_f32); the top 22 bits of each radius field are used,
+// as cell midpoints (see bm_pair_packed; radius up to 5.65 sigma); 2^18 equidistant directions reproduce every circular
+// moment below order 2^18.
+//   pair 0 = (w0[22:0], {w1:w0}[40:23])   -> g[0], g[1]
+//   pair 1 = (w1[31:9], {w3:w2}[40:23])   -> g[2], g[3]
+//   pair 2 = (w2[22:0], w3[31:14])        -> g[4], g[5]
 // g[0..2] belong to the even step, g[3..5] to the odd one.
 #define MB_PACKED_KEY_TAG (2u << 24)
 
@@ -160,27 +167,39 @@ __device__ __forceinline__ void bm_pair_packed(uint32_t r23_bits /* 23 bits, alr
                                                uint32_t a18_bits /* 18 bits, in the top of the mantissa */,
                                                float neg2ln2_amp2, float& c, float& s) {
     const float u = 2.0f - __uint_as_float(r23_bits | 0x3f800001u);          // (k + 1/2) 2^-22 in (0, 1)
+#ifdef MB_ABL_NOMUFU   // timing ablation: the four MUFU of a pair replaced by FMULs
+    const float r = (u * neg2ln2_amp2) * 0.7f;
+    const float a = __uint_as_float(a18_bits | 0x3f800000u) * 6.283185307179586f;
+    c = r * (a * 0.3f);
+    s = r * (a * 0.4f);
+#else
     const float r = sqrt_approx(lg2_approx(u) * neg2ln2_amp2);
     const float a = __uint_as_float(a18_bits | 0x3f800000u) * 6.283185307179586f;   // 2 pi (1 + k 2^-18)
     c = r * __cosf(a);
     s = r * __sinf(a);
+#endif
 }
 
 template <int SPLIT = 0>
 __device__ __forceinline__ void philox_gauss6_f32(uint32_t seed_lo, uint32_t seed_hi, uint64_t pair_index,
                                                   uint32_t particle, uint32_t member, float neg2ln2_amp2,
                                                   float (&g)[6], const uint32_t m0r = 0xD2511F53u,
-                                                  const uint32_t m1r = 0xCD9E8D57u) {
+                                                  const uint32_t m1r = 0xCD9E8D57u, const uint32_t mask_r = 0x007fffffu,
+                                                  const uint32_t mask_a = 0x007fffe0u) {
     uint32_t w0 = (uint32_t)pair_index, w1 = member, w2 = seed_lo, w3 = seed_hi;
     if (SPLIT > 0) philox4x32_10_split<SPLIT>(w0, w1, w2, w3, particle | MB_PACKED_KEY_TAG, MB_PHILOX_KEY1, m0r, m1r);
     else philox4x32_10(w0, w1, w2, w3, particle | MB_PACKED_KEY_TAG, MB_PHILOX_KEY1);
-    // 23-bit radius fields land in mantissa bits 22..0, 18-bit angle fields in mantissa bits 22..5
-    const uint32_t r0 = w0 >> 9;                                              // string bits   0..22  (bit 23 unused)
-    const uint32_t a0 = (__funnelshift_l(w1, w0, 15)) & 0x007fffe0u;          // string bits  24..41
-    const uint32_t r1 = __funnelshift_l(w2, w1, 10) >> 9;                     // string bits  42..64  (bit 65 unused)
-    const uint32_t a1 = (w2 >> 7) & 0x007fffe0u;                              // string bits  66..83
-    const uint32_t r2 = __funnelshift_l(w3, w2, 20) >> 9;                     // string bits  84..106 (bit 107 unused)
-    const uint32_t a2 = (w3 << 3) & 0x007fffe0u;                              // string bits 108..125
+    // Field layout: each 64-bit half {w1:w0}, {w3:w2} is [23-bit radius field in place | 18-bit angle | 23 bits].  A field
+    // that already sits in mantissa position costs ONE LOP3 ((w & mask) | exponent — the masks arrive in registers in the
+    // single-particle kernels so that ptxas keeps it one instruction), one that straddles the words a funnel shift more:
+    // 10 instructions per block against the 18 of the round-1 layout (most-significant-first string of 24 + 18 bit pairs).
+    // The kernel is bound by instruction issue, so these count.
+    const uint32_t r0 = w0 & mask_r;                                   // {w1:w0} bits  0..22
+    const uint32_t a0 = __funnelshift_r(w0, w1, 18) & mask_a;          // {w1:w0} bits 23..40 -> mantissa bits 5..22
+    const uint32_t r1 = w1 >> 9;                                       // {w1:w0} bits 41..63
+    const uint32_t r2 = w2 & mask_r;                                   // {w3:w2} bits  0..22
+    const uint32_t a1 = __funnelshift_r(w2, w3, 18) & mask_a;          // {w3:w2} bits 23..40
+    const uint32_t a2 = (w3 >> 9) & mask_a;                            // {w3:w2} bits 46..63 (41..45 unused)
     bm_pair_packed(r0, a0, neg2ln2_amp2, g[0], g[1]);
     bm_pair_packed(r1, a1, neg2ln2_amp2, g[2], g[3]);
     bm_pair_packed(r2, a2, neg2ln2_amp2, g[4], g[5]);

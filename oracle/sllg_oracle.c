@@ -132,8 +132,8 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * mode 0: fp32 Box-Muller of one Philox block (device uses SFU approximations, so compare
  *         with a ~1e-5 tolerance); mode 1: fp64 Box-Muller from 53-bit uniforms, two blocks;
  * mode 2: packed fp32 Box-Muller — ONE block, counter word 0 = (step-1)>>1, key word 0 =
- *         particle | 2<<24, feeds the two steps 2b+1, 2b+2: the 128 bits w0:w1:w2:w3 are cut
- *         into three (24-bit radius field of which the top 22 bits are used as cell midpoints, 18-bit angle)
+ *         particle | 2<<24, feeds the two steps 2b+1, 2b+2: the 128 bits are cut into three
+ *         (23-bit radius field of which the top 22 bits are used as cell midpoints, 18-bit angle)
  *         pairs -> six draws, the first three for the odd `step` (1-based), the last three
  *         for the even one. */
 static float u32_to_float_rz(uint32_t x) { /* cvt.rz.f32.u32 */
@@ -159,17 +159,12 @@ void orc_philox_gauss3(uint64_t seed, uint32_t member, uint32_t particle, uint64
         uint32_t v[4];
         float g[6];
         orc_philox4x32_10(pctr, pkey, v);
-        const uint64_t hi = ((uint64_t)v[0] << 32) | v[1], lo = ((uint64_t)v[2] << 32) | v[3];
-        /* bit i of the 128-bit string (0 = most significant) */
-#define ORC_BITS(pos, len)                                                                         \
-    (uint32_t)((((pos) + (len) <= 64) ? (hi >> (64 - (pos) - (len)))                                 \
-                : ((pos) >= 64)      ? (lo >> (128 - (pos) - (len)))                                \
-                                     : ((hi << ((pos) + (len) - 64)) | (lo >> (128 - (pos) - (len))))) & \
-               ((1ull << (len)) - 1))
-        bm_pair_packed(ORC_BITS(0, 23), ORC_BITS(24, 18), &g[0], &g[1]);
-        bm_pair_packed(ORC_BITS(42, 23), ORC_BITS(66, 18), &g[2], &g[3]);
-        bm_pair_packed(ORC_BITS(84, 23), ORC_BITS(108, 18), &g[4], &g[5]);
-#undef ORC_BITS
+        /* field layout of magpy_b200/csrc/rng.cuh (philox_gauss6_f32): each 64-bit half {v1:v0}, {v3:v2} is
+         * [23-bit radius field | 18-bit angle | 23 bits] from the least significant bit up */
+        const uint64_t h0 = ((uint64_t)v[1] << 32) | v[0], h1 = ((uint64_t)v[3] << 32) | v[2];
+        bm_pair_packed(v[0] & 0x7fffffu, (uint32_t)(h0 >> 23) & 0x3ffffu, &g[0], &g[1]);
+        bm_pair_packed(v[1] >> 9, (uint32_t)(h1 >> 23) & 0x3ffffu, &g[2], &g[3]);
+        bm_pair_packed(v[2] & 0x7fffffu, v[3] >> 14, &g[4], &g[5]);
         const int odd = (int)((step - 1) & 1);
         for (int i = 0; i < 3; ++i) out[i] = (double)g[3 * odd + i];
         return;
