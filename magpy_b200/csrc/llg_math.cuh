@@ -39,16 +39,18 @@ __device__ __forceinline__ V3 llg_f(const V3& m, const V3& g, const double alpha
 // On sm_100a an FP64 instruction holds its sub-partition's issue port for 2 cycles, 3 when all three operands are
 // distinct registers (scripts/micro/dfma_operands.cu), and the kernel is bound by exactly that:
 // what counts is the number of FP64 instructions and of three-register DFMAs, not the flop count.
+// heun_single_core: the step proper, from the two z-field constants of its stages t0 = h_app(t) dt/2 + cwh.z and
+// t1 = h_app(t+dt) dt/2 + cwh.z (the producer warps of heun_single_split.cu hand exactly these over).
 template <bool AXIS_Z>
-__device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V3& eh, const double alpha,
-                                               const double dth, const V3& cwh, const double hz0, const double hz1) {
+__device__ __forceinline__ V3 heun_single_core(const V3& m, const V3& e, const V3& eh, const double alpha, const double cx,
+                                               const double cy, const double t0, const double t1) {
     // stage 1: g/2 = (h(m,t) dt + sigma sqrt(dt) w) / 2
     V3 g;
     if (AXIS_Z) {  // easy axis = z: h = (k m_z + h_app) z, two fp64 ops instead of seven
-        g = V3{cwh.x, cwh.y, fma(m.z, eh.z, fma(hz0, dth, cwh.z))};
+        g = V3{cx, cy, fma(m.z, eh.z, t0)};
     } else {
         const double s = dot(m, e);
-        g = V3{fma(s, eh.x, cwh.x), fma(s, eh.y, cwh.y), fma(s, eh.z, fma(hz0, dth, cwh.z))};
+        g = V3{fma(s, eh.x, cx), fma(s, eh.y, cy), fma(s, eh.z, t0)};
     }
     V3 p = cross(m, g);
     V3 u{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
@@ -57,15 +59,21 @@ __device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V
     const V3 mt{fma(2.0, h.x, -m.x), fma(2.0, h.y, -m.y), fma(2.0, h.z, -m.z)};
     // stage 2 at (x~, t+dt), same Wiener increment
     if (AXIS_Z) {
-        g = V3{cwh.x, cwh.y, fma(mt.z, eh.z, fma(hz1, dth, cwh.z))};
+        g = V3{cx, cy, fma(mt.z, eh.z, t1)};
     } else {
         const double s = dot(mt, e);
-        g = V3{fma(s, eh.x, cwh.x), fma(s, eh.y, cwh.y), fma(s, eh.z, fma(hz1, dth, cwh.z))};
+        g = V3{fma(s, eh.x, cx), fma(s, eh.y, cy), fma(s, eh.z, t1)};
     }
     p = cross(mt, g);
     u = V3{fma(alpha, p.x, g.x), fma(alpha, p.y, g.y), fma(alpha, p.z, g.z)};
     return V3{fma(-mt.y, u.z, fma(mt.z, u.y, h.x)), fma(-mt.z, u.x, fma(mt.x, u.z, h.y)),
               fma(-mt.x, u.y, fma(mt.y, u.x, h.z))};
+}
+
+template <bool AXIS_Z>
+__device__ __forceinline__ V3 heun_single_step(const V3& m, const V3& e, const V3& eh, const double alpha,
+                                               const double dth, const V3& cwh, const double hz0, const double hz1) {
+    return heun_single_core<AXIS_Z>(m, e, eh, alpha, cwh.x, cwh.y, fma(hz0, dth, cwh.z), fma(hz1, dth, cwh.z));
 }
 
 // Solve the 3x3 system A d = b of one particle's quasi-Newton update in registers.  The reference hands its

@@ -217,6 +217,7 @@ struct magpy_b200_plan {
     bool k1_balanced = false;   // K1b: multi-wave shards run as a persistent kernel over (time segment, member block) tasks
     unsigned bal_phys = 0;      //   ... its physical grid (resident CTAs)
     std::vector<uint32_t> bal_segments;   //   ... segments per chunk (1 = plain launch)
+    bool k1_split = false;      // K1s: ensembles of at most 32 members per SM: integrator warp + generator warp per 32 members
     int k1_min_blocks = 1; // K1: register-allocation variant (resident CTAs per SM asked of ptxas), see choose_k1_variant
     bool small = false;    // few particles: one thread per cluster, all moments in registers
     bool split = false;    //   ... implicit, one lane per particle (imid_split_kernel)
@@ -284,6 +285,7 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
     const bool tab = pl->use_table;
     if (pl->N == 1) {
         if (pl->implicit) LAUNCH_TRY(mb::launch_imid_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
+        else if (pl->k1_split) LAUNCH_TRY(mb::launch_heun_single_split(tab, pl->axis_z, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_single(noise, tab, pl->axis_z, pl->k1_min_blocks, pl->grid, pl->stream, P));
     } else if (pl->small) {
         if (pl->split) LAUNCH_TRY(mb::launch_imid_split(noise, tab, pl->N, pl->grid, pl->stream, P));
@@ -389,7 +391,7 @@ int validate(const magpy_b200_ensemble* a) {
 // towards one CTA on every SM the block scheduler doubles some SMs up (1036 CTAs: 86 %).  The 7-CTA instantiation
 // (66 registers, no spills) holds up to 1036 CTAs in ONE wave at 97 %; an 8-CTA one (62 registers) was measured too and
 // never beats two waves of 6, so it is not built.  MAGPY_B200_K1_MIN_BLOCKS=1|7 overrides.
-void choose_k1_variant(magpy_b200_plan* pl, bool renorm) {
+void choose_k1_variant(magpy_b200_plan* pl, bool renorm, bool mp) {
     pl->k1_min_blocks = 1;
     if (pl->N != 1 || pl->implicit || plan_noise(pl) != mb::NOISE_PHILOX_PACKED) return;
     if (const char* env = std::getenv("MAGPY_B200_K1_MIN_BLOCKS")) {
@@ -398,11 +400,27 @@ void choose_k1_variant(magpy_b200_plan* pl, bool renorm) {
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-    // below ~4 warps per SM sub-partition a step is (mostly) one warp's dependent chain (10 DFMAs deep, ~19 cycles each: 193 cycles
-    // per step however small the ensemble, profiles/r02_probe_c1_split_kernel.log); an applied-field table entry fetched at
-    // its point of use then adds its L2 latency to every step (334 cycles): the latency variant fetches it a pair ahead
-    // (profiles/r02_probe_c1.log: 1000 members 17.0 -> 11.3 ms per 1e5 steps, 37,888 members 24.5 -> 17.6 ms, break-even near
-    // 76k members = 4 CTAs per SM)
+    // K1s (heun_single_split.cu): at most 32 members per SM leave three of an SM's four sub-partitions idle; the step is
+    // split over an integrator warp and three generator warps on them (BASELINE config 1, 1000 members x 1e5 steps:
+    // 9.52 -> 8.74 ms, in a sine field 10.63 -> 8.74 ms, profiles/r02_probe_c1_split_v2.log).  With renorm or a general
+    // easy axis the integrator's longer chain leaves no gain (17.2 vs 16.5 ms).  Not for per-member material parameters.
+    // MAGPY_B200_K1_SPLIT=0|1 overrides.
+    {
+        const uint64_t split_grid = (pl->R + 31) / 32;
+        bool split = !mp && split_grid <= (uint64_t)sms && pl->axis_z && !renorm;
+        if (const char* env = std::getenv("MAGPY_B200_K1_SPLIT")) split = !mp && std::atoi(env) != 0 && split_grid < 0x7fffffffull;
+        if (split) {
+            pl->k1_split = true;
+            pl->grid = (unsigned)split_grid;
+            pl->block = dim3(128);
+            return;
+        }
+    }
+    // below ~4 warps per SM sub-partition a step is (mostly) one warp's own in-order stream — 11 dependent levels of FP64
+    // instructions at 8.1 cycles of latency plus the serial issue of each level's members: 187 cycles per step however small
+    // the ensemble — and an applied-field table entry fetched at its point of use adds its L2 latency to every step (334
+    // cycles): the latency variant fetches it a pair ahead (profiles/r02_probe_c1.log: 1000 members 17.0 -> 11.3 ms per 1e5
+    // steps, 37,888 members 24.5 -> 17.6 ms, break-even near 76k members = 4 CTAs per SM)
     if (pl->use_table && pl->grid <= (unsigned)(4 * sms)) { pl->k1_min_blocks = mb::K1_LATENCY; return; }
     const int free_ctas = mb::heun_single_resident_ctas(pl->use_table, pl->axis_z, renorm, 1);
     const int tight_ctas = mb::heun_single_resident_ctas(pl->use_table, pl->axis_z, renorm, 7);
@@ -608,7 +626,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     pl->use_table = a->field_shape != MAGPY_B200_FIELD_CONSTANT;
     pl->axis_z = N == 1 && a->axis_stride == 0 && a->anisotropy_axis[0] == 0.0 && a->anisotropy_axis[1] == 0.0 &&
                  a->anisotropy_axis[2] == 1.0;
-    choose_k1_variant(pl, a->renorm != 0);
+    choose_k1_variant(pl, a->renorm != 0, a->member_anisotropy || a->member_damping || a->member_field_amplitude);
     // chunking: bound the field table / injected-noise window and the partial-sum buffer
     uint64_t max_steps = 4ull << 20;
     if (const char* env = std::getenv("MAGPY_B200_MAX_CHUNK_STEPS")) {   // test hook: force many small launches
@@ -646,7 +664,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     // whole number of warps per SM sub-partition (section 7 of DESIGN.md); cut into (time segment, member block) tasks
     // pulled by a grid of resident CTAs, every SM stays busy to the end.  MAGPY_B200_K1_BALANCE=0|1 overrides.
     pl->bal_segments.assign(pl->chunks.size(), 1);
-    if (N == 1 && !pl->implicit && plan_noise(pl) == mb::NOISE_PHILOX_PACKED && pl->k1_min_blocks != mb::K1_LATENCY &&
+    if (N == 1 && !pl->implicit && plan_noise(pl) == mb::NOISE_PHILOX_PACKED && pl->k1_min_blocks != mb::K1_LATENCY && !pl->k1_split &&
         !(a->member_anisotropy || a->member_damping || a->member_field_amplitude)) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
@@ -1028,7 +1046,7 @@ int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
                         : pl->mma   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA
                         : pl->imid_mma ? MAGPY_B200_KERNEL_IMID_CLUSTER_MMA
                                     : (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER : MAGPY_B200_KERNEL_HEUN_CLUSTER);
-    st->kernel_variant = (pl->N == 1 && !pl->implicit) ? (pl->k1_balanced ? 200u : (uint64_t)pl->k1_min_blocks) : 0;
+    st->kernel_variant = (pl->N == 1 && !pl->implicit) ? (pl->k1_balanced ? 200u : pl->k1_split ? (uint64_t)mb::K1_SPLIT : (uint64_t)pl->k1_min_blocks) : 0;
     if (pl->ran) {
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, pl->ev_begin, pl->ev_end));

@@ -11,7 +11,7 @@ dst=$root/variants/$name/magpy_b200
 mkdir -p $dst/obj
 cp $root/magpy_b200/*.py $root/magpy_b200/core*.so $dst/
 objs=""
-for u in magpy_b200 comm heun_single heun_single_balanced imid_single small_heun small_imid cluster cluster_mma cluster_mma_imid cluster_big service dom; do
+for u in magpy_b200 comm heun_single heun_single_balanced heun_single_split imid_single small_heun small_imid cluster cluster_mma cluster_mma_imid cluster_big service dom; do
     if [[ ",$unit," == *",$u.cu,"* ]]; then
         nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -c -o $dst/obj/$u.o $src/$u.cu
         objs="$objs $dst/obj/$u.o"

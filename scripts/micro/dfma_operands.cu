@@ -9,6 +9,7 @@
 // and each of them with MIX independent LOP3 per DFMA.  Reported: SM cycles per DFMA per sub-partition.
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o dfma_operands dfma_operands.cu && ./dfma_operands
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 template <int V, int MIX>
@@ -45,6 +46,42 @@ __global__ void k(double* out, const double* in, int iters, double a, double b, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s + w;
 }
 
+// dependent-issue latency: ONE chain per thread, one warp per sub-partition; CH > 1 = that many independent chains
+template <int CH, bool THREE_REG>
+__global__ void chain(double* out, const double* in, int iters, double a, double b) {
+    double x[CH], p = in[threadIdx.x + 32 * 16], q = in[threadIdx.x + 32 * 24];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) x[i] = in[threadIdx.x + 32 * i];
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 64 / CH; ++u) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) x[i] = THREE_REG ? fma(x[i], p, q) : fma(x[i], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int CH, bool THREE_REG>
+void run_chain(const double* in, double* out) {
+    int dev = 0; cudaDeviceProp pr; cudaGetDeviceProperties(&pr, dev);
+    const int iters = 4096;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 4; ++r) {
+        cudaEventRecord(e0);
+        chain<CH, THREE_REG><<<pr.multiProcessorCount, 128>>>(out, in, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (r && ms < best) best = ms;
+    }
+    int khz; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    printf("%d dependent chain(s) per warp, one warp per SMSP, %s: %6.2f cycles per DFMA of a chain\n", CH,
+           THREE_REG ? "three register operands" : "uniform multiplier / addend", best * 1e-3 * khz * 1e3 / (iters * 64.0 / CH));
+}
+
 template <int V, int MIX>
 void run(const char* name, int warps_per_smsp, const double* in, double* out) {
     int dev = 0; cudaDeviceProp pr; cudaGetDeviceProperties(&pr, dev);
@@ -65,7 +102,20 @@ void run(const char* name, int warps_per_smsp, const double* in, double* out) {
 
 int main() {
     double *in, *out;
-    cudaMalloc(&in, 8 * 32 * 32); cudaMemset(in, 0, 8 * 32 * 32); cudaMalloc(&out, 8 * 148 * 8 * 128);
+    cudaMalloc(&in, 8 * 32 * 32);
+    {   // NON-ZERO operands: multipliers near 1, addends near 1e-3 (an all-zero buffer runs up to 4x faster: the FP64 pipe of
+        // sm_100a is data dependent — found the hard way, profiles/r02_dfma_operands_zero_operands.txt)
+        double h[32 * 32];
+        unsigned long long st = 88172645463325252ull;
+        for (int i = 0; i < 32 * 32; ++i) {
+            st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+            const double u = (double)(st >> 11) * (1.0 / 9007199254740992.0);
+            const int row = i / 32;
+            h[i] = getenv("DFMA_ZERO") ? 0.0 : (row < 16 ? 0.5 + u : row < 24 ? 0.999 + 1e-4 * u : 1e-3 * (0.5 + u));
+        }
+        cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice);
+    } cudaMalloc(&out, 8 * 148 * 8 * 128);
+    run_chain<1, false>(in, out); run_chain<1, true>(in, out); run_chain<2, true>(in, out); run_chain<4, true>(in, out); run_chain<8, true>(in, out);
     for (int w : {1, 2, 4, 8}) {
         run<1, 0>("V1 fma(x, a, b)  uniform a b", w, in, out);
         run<2, 0>("V2 fma(x, p[i], b)", w, in, out);

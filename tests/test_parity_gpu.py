@@ -305,7 +305,8 @@ def test_exact_newton_mode_is_the_converged_reference_iteration(orc, core, N, ax
 
 
 @pytest.mark.parametrize('field_shape,axis,renorm,chunk', [('sine', (0, 0, 1.0), True, 7), ('sine', (0.6, 0, 0.8), False, 13),
-                                                           ('square', (0.6, 0, 0.8), True, None)])
+                                                           ('square', (0.6, 0, 0.8), True, None), ('sine', (0, 0, 1.0), False, 5),
+                                                           ('constant', (0, 0, 1.0), False, None)])
 def test_heun_single_register_and_latency_variants_are_bit_identical(core, field_shape, axis, renorm, chunk, monkeypatch):
     """heun_single_kernel has three instantiations of its production (packed-noise) form: free register allocation, 7
     resident CTAs per SM (shards that fit one such wave), and the latency variant for small ensembles (applied-field table
@@ -327,8 +328,21 @@ def test_heun_single_register_and_latency_variants_are_bit_identical(core, field
             assert np.array_equal(outs['1']['trajectories'], outs[v]['trajectories'])
             assert np.array_equal(outs['1']['final'], outs[v]['final'])
             assert np.array_equal(outs['1']['sums'], outs[v]['sums'])
-    monkeypatch.delenv('MAGPY_B200_K1_MIN_BLOCKS')
-    assert gpu_run(core, c, np.arange(100))['stats']['kernel_variant'] == 100        # the default for small ensembles in a field
+        # K1s (heun_single_split.cu): an integrator warp fed by a generator warp through a shared-memory ring — the same
+        # arithmetic per member (bit-identical trajectories and final states); the ensemble sums are formed per 32 members
+        # instead of per 128, i.e. in another fixed order
+        monkeypatch.delenv('MAGPY_B200_K1_MIN_BLOCKS')
+        monkeypatch.setenv('MAGPY_B200_K1_SPLIT', '1')
+        sp = gpu_run(core, cc, seeds, stream_offset=5)
+        monkeypatch.delenv('MAGPY_B200_K1_SPLIT')
+        assert sp['stats']['kernel'] == 'heun_single' and sp['stats']['kernel_variant'] == 300
+        assert np.array_equal(outs['1']['trajectories'], sp['trajectories'])
+        assert np.array_equal(outs['1']['final'], sp['final'])
+        assert np.allclose(outs['1']['sums'], sp['sums'], rtol=1e-13, atol=1e-13 * np.abs(outs['1']['sums']).max())
+    plain = tuple(axis) == (0, 0, 1.0) and not renorm        # K1s is the default up to 32 members per SM for this shape only
+    small = 100 if field_shape != 'constant' else 1          # otherwise: the latency variant when there is a field table
+    assert gpu_run(core, c, np.arange(100))['stats']['kernel_variant'] == (300 if plain else small)
+    assert gpu_run(core, c, np.arange(6000))['stats']['kernel_variant'] == small
     assert gpu_run(core, c, np.arange(200000), return_trajectories=False)['stats']['kernel_variant'] == 1    # 437 steps: too short to cut into segments
 
 
