@@ -74,6 +74,7 @@ struct RunParams {
     uint32_t coarsen_log2;      // NOISE_PHILOX_COARSE: step s sums the packed stream's fine steps s 2^L .. (s+1) 2^L - 1
     double* state;              // [n][R]
     double* state_t;            // [n][R] predictor moments of the capacity-free Heun kernel (cluster_big.cu) or nullptr
+    double* state_u;            // [n][R] second midpoint-iterate buffer of the capacity-free implicit kernel or nullptr
     const uint64_t* target;     // [S] state index stored by sample k
     uint64_t j0, j1;            // advance the state from index j0 to j1
     uint32_t k0, k1;            // samples recorded by this launch

@@ -35,6 +35,8 @@ cudaError_t launch_heun_cluster_mma(int noise, bool tab, bool one_buf, unsigned 
                                     size_t smem, cudaStream_t s, const RunParams& P);
 // cluster_big.cu: Heun for any cluster size (moments in global memory); CTA = 32 members x 16 particle slots
 cudaError_t launch_heun_cluster_big(int noise, bool tab, unsigned grid, cudaStream_t s, const RunParams& P);
+// the same layout for the implicit midpoint scheme (two iterate buffers in global memory)
+cudaError_t launch_imid_cluster_big(int noise, bool tab, unsigned grid, cudaStream_t s, const RunParams& P);
 // K4m (cluster_mma_imid.cu): threads = 32 * G * column tiles of 8 members
 cudaError_t launch_imid_cluster_mma(int noise, bool tab, unsigned grid, unsigned threads, size_t smem, cudaStream_t s,
                                     const RunParams& P);

@@ -223,7 +223,7 @@ struct magpy_b200_plan {
     bool split = false;    //   ... implicit, one lane per particle (imid_split_kernel)
     bool mma = false;      // Heun cluster kernel on the FP64 MMA path (cluster_mma.cu)
     bool imid_mma = false; // implicit cluster kernel on the FP64 MMA path (cluster_mma_imid.cu)
-    bool big = false;      // Heun beyond 128 particles: moments in global memory (cluster_big.cu)
+    bool big = false;      // beyond 128 particles: moments in global memory (cluster_big.cu), Heun and implicit midpoint
     bool one_buf = false;  //   ... with one shared-memory moment buffer
     uint32_t G = 0;        //   ... particle groups of 8
     uint32_t mma_full = 0, mma_tail = 0;   //   ... member distribution over CTAs (see choose_mma)
@@ -231,7 +231,7 @@ struct magpy_b200_plan {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_k;   // pairs around each integration launch
-    DevBuf<double> d_state_t;
+    DevBuf<double> d_state_t, d_state_u;
     DevBuf<double> d_state0, d_state, d_axis, d_kred, d_sig, d_dip, d_dmat, d_vred, d_traj, d_sums, d_partial, d_tab, d_dW, d_stage;
     DevBuf<int64_t> d_seeds;
     DevBuf<uint32_t> d_member_idx, d_member_j, d_bal_seg_k;
@@ -249,7 +249,7 @@ struct magpy_b200_plan {
 
     ~magpy_b200_plan() {
         cudaSetDevice(device);
-        d_state_t.release(); d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
+        d_state_t.release(); d_state_u.release(); d_state0.release(); d_state.release(); d_axis.release(); d_kred.release(); d_sig.release(); d_dip.release();
         d_dmat.release(); d_vred.release();
         d_traj.release(); d_sums.release(); d_partial.release(); d_tab.release(); d_dW.release(); d_stage.release();
         d_seeds.release(); d_member_idx.release(); d_member_j.release(); d_bal_seg_k.release(); d_bal_sync.release(); d_mp.release(); d_target.release(); d_newton.release();
@@ -296,7 +296,8 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
                                                pl->stream, P));
         if (pl->mma_full > 0 && pl->grid > pl->mma_full) pl->launches++;   // whole waves + partial last wave
     } else if (pl->big) {
-        LAUNCH_TRY(mb::launch_heun_cluster_big(noise, tab, pl->grid, pl->stream, P));
+        if (pl->implicit) LAUNCH_TRY(mb::launch_imid_cluster_big(noise, tab, pl->grid, pl->stream, P));
+        else LAUNCH_TRY(mb::launch_heun_cluster_big(noise, tab, pl->grid, pl->stream, P));
     } else if (pl->imid_mma) {
         LAUNCH_TRY(mb::launch_imid_cluster_mma(noise, tab, pl->grid, pl->block.x, pl->smem, pl->stream, P));
     } else if (pl->implicit) {
@@ -375,11 +376,8 @@ int validate(const magpy_b200_ensemble* a) {
     if (a->comm && mbh::comm_device(a->comm) != a->device)
         return fail(MAGPY_B200_ERR_BAD_ARG, "the communicator was created for device %d, the ensemble runs on device %d",
                     mbh::comm_device(a->comm), a->device);
-    if (a->use_implicit) {
-        if (a->n_particles > 128) return fail(MAGPY_B200_ERR_BAD_ARG, "implicit midpoint supports at most 128 particles per cluster");
-    } else if (a->n_particles > 2048) {
-        return fail(MAGPY_B200_ERR_BAD_ARG, "Heun supports at most 2048 particles per cluster");
-    }
+    if (a->n_particles > 2048)   // the reference has no limit in its code; its dense (3N)^3 work arrays set one long before this
+        return fail(MAGPY_B200_ERR_BAD_ARG, "at most 2048 particles per cluster");
     return MAGPY_B200_OK;
 }
 
@@ -583,8 +581,9 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
                 pl->grid = (unsigned)((R * N + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
             }
         }
-    } else if (!pl->implicit && N > 128) {
-        // cluster_big.cu: any cluster size, moments in global memory
+    } else if (N > 128 || (std::getenv("MAGPY_B200_CLUSTER_KERNEL") && std::strcmp(std::getenv("MAGPY_B200_CLUSTER_KERNEL"), "big") == 0)) {
+        // cluster_big.cu: any cluster size, moments (and the implicit scheme's midpoint iterates) in global memory;
+        // MAGPY_B200_CLUSTER_KERNEL=big forces it for smaller clusters (tests: the oracle's dense path is slow beyond 64)
         pl->big = true;
         pl->np = 1;
         pl->block = dim3(mb::CL_LANES, 16);
@@ -694,6 +693,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
     double need = 8.0 * (3.0 * n * R + (double)n * R /*axis*/ + 4.0 * pl->S + 4.0 * pl->max_chunk_samples * pl->grid +
                          2.0 * pl->max_chunk_steps + (double)N * N * 4);
+    if (pl->big) need += 8.0 * (pl->implicit ? 2.0 : 1.0) * (double)n * R;
     if (pl->want_traj) need += 8.0 * 2.0 * (double)pl->S * n * R;
     if (pl->injected) need += 8.0 * 2.0 * (double)pl->total_steps * n * R;
     if (need > 0.9 * (double)free_b) {   // blocks cached by the pool count as used: give them back and look again
@@ -719,6 +719,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     CU_TRY(pl->d_state0.alloc(n * R, pl->stream));
     CU_TRY(pl->d_state.alloc(n * R, pl->stream));
     if (pl->big) CU_TRY(pl->d_state_t.alloc(n * R, pl->stream));
+    if (pl->big && pl->implicit) CU_TRY(pl->d_state_u.alloc(n * R, pl->stream));
     CU_TRY(pl->d_kred.alloc(N, pl->stream));
     pl->mp = a->member_anisotropy || a->member_damping || a->member_field_amplitude;
     const bool member_radii = !pl->mp && (a->radius_stride != 0 || a->member_temperature != nullptr);   // N = 1: sigma per member
@@ -965,6 +966,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.bm_mask_a = 0x007fffe0u;
     P.state = pl->d_state.p;
     P.state_t = pl->d_state_t.p;
+    P.state_u = pl->d_state_u.p;
     P.target = pl->d_target.p;
     P.field_tab = pl->d_tab.p;
     P.dW = pl->d_dW.p;
@@ -1045,7 +1047,7 @@ int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
                                       : MAGPY_B200_KERNEL_HEUN_SINGLE)
                         : pl->split ? MAGPY_B200_KERNEL_IMID_SPLIT
                         : pl->small ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SMALL : MAGPY_B200_KERNEL_HEUN_SMALL)
-                        : pl->big   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_BIG
+                        : pl->big   ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER_BIG : MAGPY_B200_KERNEL_HEUN_CLUSTER_BIG)
                         : pl->mma   ? MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA
                         : pl->imid_mma ? MAGPY_B200_KERNEL_IMID_CLUSTER_MMA
                                     : (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER : MAGPY_B200_KERNEL_HEUN_CLUSTER);

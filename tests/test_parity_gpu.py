@@ -191,8 +191,36 @@ def test_heun_cluster_beyond_128_particles(orc, core, N, renorm, members):
     t, fl, ref, out, _ = injected_pair(orc, core, c, seeds, per_member=(N == 130))
     assert out['stats']['kernel'] == 'heun_cluster_big'
     assert_traj(ref, out, c)
-    with pytest.raises(ValueError):   # implicit midpoint stops at 128 particles
-        gpu_run(core, ol.Case(dict(c, implicit=True)), seeds)
+
+
+# The implicit scheme beyond 128 particles (cluster_big.cu, imid_cluster_big_kernel: midpoint iterates in two global
+# buffers, a per-member bit says which is current).  The oracle's dense (3N)^3 path limits what can be compared at N > 128
+# (474 MB of work arrays and a 390 x 390 dgesv per iteration at N = 130), so the kernel is also forced onto smaller
+# clusters (MAGPY_B200_CLUSTER_KERNEL=big), where members that converge after different numbers of iterations share a
+# CTA; Heun through the same knob for symmetry.
+@pytest.mark.parametrize('N,implicit,interactions,members,steps', [(20, True, True, 40, 12), (33, True, False, 7, 6),
+                                                                   (20, False, True, 40, 30), (130, True, True, 2, 3)])
+def test_capacity_free_cluster_kernels(orc, core, N, implicit, interactions, members, steps, monkeypatch):
+    rng = np.random.default_rng(300 + N)
+    c = ol.make_case(N=N, radius=7e-9 * (1 + 0.1 * rng.random(N)), anisotropy=1e5 * (1 + 0.2 * rng.random(N)),
+                     dt=1e-12 if implicit else 1e-13, t_end=(1e-12 if implicit else 1e-13) * steps, S=steps // 3 + 1,
+                     implicit=implicit, interactions=interactions, renorm=(N == 33), field_shape='sine', H0=1e4, f=1e10,
+                     T=330.0, rng=rng)
+    seeds = np.arange(1, members + 1) * 29
+    if N <= 128:
+        monkeypatch.setenv('MAGPY_B200_CLUSTER_KERNEL', 'big')
+    t, fl, ref, out, newton = injected_pair(orc, core, c, seeds, per_member=(N == 20))
+    assert out['stats']['kernel'] == ('imid_cluster_big' if implicit else 'heun_cluster_big')
+    assert_traj(ref, out, c)
+    if implicit:
+        assert out['stats']['newton_iterations'] == sum(n[0] - n[2] for n in newton)     # identical iteration counts
+        assert out['stats']['newton_failures'] == 0
+        if N == 20:   # the default kernel for this size on the same case: same iterates
+            monkeypatch.delenv('MAGPY_B200_CLUSTER_KERNEL')
+            t, fl, ref, out2, newton = injected_pair(orc, core, c, seeds, per_member=True)
+            assert out2['stats']['kernel'] == 'imid_cluster_mma'
+            assert out2['stats']['newton_iterations'] == out['stats']['newton_iterations']
+            assert np.abs(out2['trajectories'] - out['trajectories']).max() / c.Ms < 1e-11
 
 
 @pytest.mark.parametrize('N,renorm,gauss', [(24, False, 'f32p'), (33, True, 'f64'), (64, False, 'f64')])
