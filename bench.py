@@ -508,7 +508,9 @@ def ours(args):
                    'timing': 'CUDA events on the launching stream (integration + reduction + all-reduce), max over ranks',
                    'kernel_variant': ({1: 'heun_single, free register allocation (6 CTAs/SM)', 7: 'heun_single, 7 CTAs/SM',
                                        100: 'heun_single, latency variant (field table prefetched)',
-                                       200: 'heun_single_balanced: persistent kernel over (time segment, 128-member block) tasks'
+                                       200: 'heun_single_balanced: persistent kernel over (time segment, 128-member block) tasks',
+                                       300: 'heun_single_split: integrator warp + three generator warps per 32 members '
+                                            '(at most 32 members per SM)'
                                        }.get(variant, str(variant)) if w['N'] == 1 and not w.get('implicit') else None),
                    'other_scaling_mode': other,
                    'mean_mz_over_Ms_at_end': mean_mz, 'wall_s_timed_region': wall},
@@ -516,7 +518,14 @@ def ours(args):
                      'frac': achieved / peak_tflops if (peak_tflops and achieved) else None, 'traffic': traffic,
                      'newton_iterations_per_step': (st['newton_iterations'] / max(1, st['particle_steps'] / w['N'])
                                                     if w.get('implicit') else None),
-                     'kernel': ('heun_single_balanced' if variant == 200 else st['kernel']) + '_kernel',
+                     'kernel': ('heun_single_balanced' if variant == 200 else 'heun_single_split' if variant == 300
+                                else st['kernel']) + '_kernel',
+                     'what_binds': ('instruction issue, not the FP64 lanes: on sm_100a an FP64 instruction holds its sub-partition\'s '
+                                    'issue port 2 cycles, 3 with three distinct register operands (scripts/micro/dfma_operands.cu, '
+                                    'profiles/r02_dfma_operands.txt); a Heun step pair is 74 FP64 (30 three-register) + 91 other '
+                                    'instructions = 269 issue cycles per warp, 290 measured (DESIGN.md section 4); `frac` credits '
+                                    'W_alg = 98 flop per step, the kernel executes 37 FP64 instructions per step'
+                                    if w['N'] == 1 and not w.get('implicit') and variant == 200 else None),
                      'kernel_ms_per_launch': int_ms,
                      'algorithmic_flop_per_particle_step': W_ALG,
                      'peak_dfma_chain': dfma_tflops, 'peak_dmma_chain': dmma_tflops, 'sm_clock_mhz_max': max_mhz,
