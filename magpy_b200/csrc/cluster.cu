@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t member = member_id(P, r);
-    const bool renorm = P.renorm != 0, exact = P.newton_exact != 0;
+    const bool renorm = P.renorm != 0, exact = P.newton_exact != 0, zero_u = P.quirk_zero != 0;
     NewtonCount nc{0ull, 0ull, 0ull};
 
     Own own[NP];
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(256) imid_cluster_kernel(const __grid_constant
                         const V3 u{fma(alpha, pg.x, g.x), fma(alpha, pg.y, g.y), fma(alpha, pg.z, g.z)};
                         newton_matrix_exact(A, X[q], alpha, g, u, dt * own[q].kred, own[q].e);
                     } else {
-                        newton_matrix(A, X[q], alpha, h, sw[q], qu[q], e0);
+                        newton_matrix(A, X[q], alpha, h, sw[q], qu[q], e0, zero_u);
                     }
                     if (!solve3_adjugate(A, b, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                     dl[q] = V3{d[0], d[1], d[2]};

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(CL_LANES * BIG_SLOTS) imid_cluster_big_kernel(
     const uint64_t seed = (uint64_t)P.seeds[r];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t member = member_id(P, r);
-    const bool renorm = P.renorm != 0, inter = P.interactions != 0, exact = P.newton_exact != 0;
+    const bool renorm = P.renorm != 0, inter = P.interactions != 0, exact = P.newton_exact != 0, zero_u = P.quirk_zero != 0;
     const V3 e0{P.axis[r * P.axis_rs], P.axis[P.axis_cs + r * P.axis_rs], P.axis[2 * P.axis_cs + r * P.axis_rs]};
     const double k0 = P.k_red[0];
     NewtonCount nc{0ull, 0ull, 0ull};
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(CL_LANES * BIG_SLOTS) imid_cluster_big_kernel(
                             const V3 u{fma(alpha, pg.x, g.x), fma(alpha, pg.y, g.y), fma(alpha, pg.z, g.z)};
                             newton_matrix_exact(A, X, alpha, g, u, dt * __ldg(P.k_red + p), e);
                         } else {
-                            newton_matrix(A, X, alpha, h, sw, quirk_u(N, p, e0, k0), e0);
+                            newton_matrix(A, X, alpha, h, sw, quirk_u(N, p, e0, k0), e0, zero_u);
                         }
                         if (!solve3_adjugate(A, b, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                         store(dst, p, V3{X.x + d[0], X.y + d[1], X.z + d[2]});

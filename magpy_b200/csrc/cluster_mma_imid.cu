@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(512, 1) imid_cluster_mma_kernel(const __grid_c
     const bool valid = p_raw < N;
     const uint32_t pid = valid ? (uint32_t)p_raw : 0u;
     const double alpha = P.alpha, dt = P.dt, clampA = P.clampA, sqrt_dt = P.sqrt_dt, eps2 = P.eps * P.eps;
-    const bool renorm = P.renorm != 0, inter = P.interactions != 0, exact = P.newton_exact != 0;
+    const bool renorm = P.renorm != 0, inter = P.interactions != 0, exact = P.newton_exact != 0, zero_u = P.quirk_zero != 0;
     const double kred = __ldg(P.k_red + pid), vred = __ldg(P.v_red + pid), sr = __ldg(P.sig + pid), k0 = __ldg(P.k_red);
     const bool mono = P.mma_mono != 0;
     const int bar_id = 1 + ct, bar_n = 32 * G;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(512, 1) imid_cluster_mma_kernel(const __grid_c
                         newton_matrix_exact(A, X[e], alpha, gg, u, dt * kred, e_own);
                     } else {
                         const V3 e_zero = axis_of(0u, e);
-                        newton_matrix(A, X[e], alpha, h, sw[e], quirk_u((unsigned)N, pid, e_zero, k0), e_zero);
+                        newton_matrix(A, X[e], alpha, h, sw[e], quirk_u((unsigned)N, pid, e_zero, k0), e_zero, zero_u);
                     }
                     bool ok = true;
                     if (!solve3_adjugate(A, b, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }

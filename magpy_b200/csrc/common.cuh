@@ -39,6 +39,8 @@ struct RunParams {
     int interactions; // all-pairs dipolar field
     double alpha, dt, sqrt_dt;
     double eps, clampA;  // implicit: tolerance, Ah = sqrt(2*1000*|ln dt|)
+    int quirk_zero;      // implicit, N >= 2: the first easy axis (shared by all members) has no x and no y component, so the
+                         // "field Jacobian" block the reference reads is all zeros (llg_math.cuh: quirk_u, newton_matrix)
     int newton_exact;    // implicit: 0 = the reference's quasi-Newton iteration (parity), 1 = Newton with the exact Jacobian
     double h_const;      // applied field when no table is used (reduced units)
     const double* k_red; // [N]

@@ -930,6 +930,7 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
     P.dt = rd.dt;
     P.sqrt_dt = std::sqrt(rd.dt);
     P.eps = a->implicit_tol;
+    P.quirk_zero = (N >= 2 && a->axis_stride == 0 && a->anisotropy_axis[0] == 0.0 && a->anisotropy_axis[1] == 0.0) ? 1 : 0;
     P.newton_exact = (a->use_implicit && a->implicit_newton == MAGPY_B200_NEWTON_EXACT) ? 1 : 0;
     P.clampA = std::sqrt(2 * 1000.0 * std::abs(std::log(rd.dt)));  // lib/integrators.cpp:598-599
     P.h_const = rd.h0;

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
     const bool live = r_raw < P.R;
     const uint64_t r = live ? r_raw : P.R - 1;
     const double alpha = P.alpha, dt = P.dt, clampA = P.clampA, sqrt_dt = P.sqrt_dt;
-    const bool inter = P.interactions != 0, renorm = P.renorm != 0;
+    const bool inter = P.interactions != 0, renorm = P.renorm != 0, zero_u = P.quirk_zero != 0;
 
     V3 m[N], e[N], zero[N];
     double kred[N], sr[N];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_small_kernel(const __grid_
                         const V3 u{fma(alpha, pg.x, g.x), fma(alpha, pg.y, g.y), fma(alpha, pg.z, g.z)};
                         newton_matrix_exact(A, X[i], alpha, g, u, dt * kred[i], e[i]);
                     } else {
-                        newton_matrix(A, X[i], alpha, h[i], sw[i], quirk_u(N, i, e[0], kred[0]), e[0]);
+                        newton_matrix(A, X[i], alpha, h[i], sw[i], quirk_u(N, i, e[0], kred[0]), e[0], zero_u);
                     }
                     if (!solve3_adjugate(A, bb, d)) { ok = false; d[0] = d[1] = d[2] = 0.0; }
                     dl[i] = V3{d[0], d[1], d[2]};
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_split_kernel(const __grid_
     const bool live = r_raw < P.R;
     const uint64_t r = live ? r_raw : P.R - 1;
     const double alpha = P.alpha, dt = P.dt, clampA = P.clampA, sqrt_dt = P.sqrt_dt;
-    const bool inter = P.interactions != 0, renorm = P.renorm != 0, exact = P.newton_exact != 0;
+    const bool inter = P.interactions != 0, renorm = P.renorm != 0, exact = P.newton_exact != 0, zero_u = P.quirk_zero != 0;
 
     const uint64_t c0 = 3ull * p;
     V3 m{P.state[c0 * P.R + r], P.state[(c0 + 1) * P.R + r], P.state[(c0 + 2) * P.R + r]};
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) imid_split_kernel(const __grid_
                     const V3 u{fma(alpha, pg.x, g.x), fma(alpha, pg.y, g.y), fma(alpha, pg.z, g.z)};
                     newton_matrix_exact(A, X, alpha, g, u, dt * kred, e);
                 } else {
-                    newton_matrix(A, X, alpha, h, sw, qu, e0);
+                    newton_matrix(A, X, alpha, h, sw, qu, e0, zero_u);
                 }
                 const bool ok = solve3_adjugate(A, bb, d);
                 if (!ok) d[0] = d[1] = d[2] = 0.0;
