@@ -669,10 +669,11 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
         const int per_sm = mb::heun_single_balanced_resident_ctas(pl->use_table, pl->axis_z, a->renorm != 0);
         // four CTAs per SM saturate the issue port (oldest-first warp scheduling); more only hold blocks back — unless every
-        // CTA works through many blocks (>= 8: the 1M-member shard), where the tail no longer matters and the extra warps
-        // fill the fixed-latency stalls of the 37-instruction step (1M x 5e4 steps: 194.8 ms with 4, 192.8 with 5, 192.5 with 6,
-        // profiles/r02_probe_k1_variants2.log)
-        int use_per_sm = std::max(1, std::min(per_sm, pl->grid >= (unsigned)(8 * sms * per_sm) ? per_sm : 4));
+        // CTA works through many blocks (>= 5: shards of 500,000 members and more), where the tail no longer matters and a
+        // fifth warp per sub-partition fills the fixed-latency stalls of the 37-instruction step
+        // (profiles/r02_probe_k1_bal_ctas_37op.log, 1e5 steps: 1M members 388.4 ms with 4, 384.9 with 5 or 6; 500k 194.3 /
+        // 192.9 / 193.9; 250k 97.2 / 97.7 / 98.6; 125k 49.5 / 50.5 / 51.6)
+        int use_per_sm = std::max(1, std::min(per_sm, pl->grid >= (unsigned)(25 * sms) ? 5 : 4));
         if (const char* env = std::getenv("MAGPY_B200_K1_BAL_CTAS")) use_per_sm = std::max(1, std::min(per_sm, std::atoi(env)));
         const bool on_default = pl->grid > (unsigned)(sms * use_per_sm);
         pl->bal_phys = (unsigned)(sms * use_per_sm);
