@@ -1,24 +1,23 @@
 // heun_single_split.cu — K1s: explicit Heun, single particle, for ensembles too small to give every SM sub-partition
-// more than one warp (at most 32 members per SM: BASELINE config 1 has 1000 members).
+// more than one warp (up to 64 members per SM: BASELINE config 1 has 1000 members).
 //
 // A warp that has its sub-partition to itself is bound by its own in-order instruction stream: one Heun step is 11
 // dependent levels of FP64 instructions (8.1 cycles of latency each, scripts/micro/dfma_operands.cu) whose 2-3 members issue
 // one after the other at 2-3 cycles each, and next to them the ~48 generator and loop instructions of the step take an
 // issue slot each: 187 cycles per step measured for K1, whatever the ensemble size below one warp per sub-partition.  A
-// small ensemble leaves three of an SM's four sub-partitions idle, so everything that does not depend on the state is
+// small ensemble leaves most of an SM's four sub-partitions idle, so everything that does not depend on the state is
 // moved there: in a CTA of 128 threads warp 0 (the consumer) integrates 32 members and warps 1-3 (the producers, on the
 // other three sub-partitions, alternating batches) generate their Wiener increments — Philox, Box-Muller, float -> double
 // — read the applied-field table and form the two z-field constants of the Heun stages, t0 = h_app(t) dt/2 + cwh.z and
 // t1 = h_app(t + dt) dt/2 + cwh.z, a batch of SPLIT_B steps ahead, into a shared-memory ring.  The consumer's step is then
 // 35 FP64 instructions and two LDS.128; ring slots are handed over on named barriers (one "full" and one "empty" barrier
-// per slot, bar.arrive on one side, bar.sync on the other).
-// Measured (profiles/r02_probe_c1_split_v2.log): config 1 (1000 members x 1e5 steps) 9.52 -> 8.74 ms, the same ensemble in a
-// sine field 10.63 -> 8.74 ms (the table fetch leaves the integrator's stream too).  The consumer ALONE, fed from a ring
-// that is never refilled, takes 160 cycles per step: what is left is the dependent chain of the step itself — 11 levels x
-// (8.1 cycles + the serial issue of the level's members) — so this is within 7 % of what any mapping of one member's step
-// onto one in-order warp can reach; the 89-cycle bound of the bare chain is not reachable in order.  With `renorm` or a
-// general easy axis the longer chain makes the fused kernel's latency variant as fast, so the host uses K1s for the
-// easy-axis-z / no-renorm shape only (MAGPY_B200_K1_SPLIT=1 forces it).
+// per slot, bar.arrive on one side, bar.sync on the other).  A hand-over costs ~100 cycles, hence batches of 32 steps
+// (with 8 the kernel ran at 172 cycles per step, with 16 at 152, with 32 at 146).
+// Measured (profiles/r02_probe_c1_split_v2.log, r02_probe_k1s_shapes.log): config 1 (1000 members x 1e5 steps) 9.52 -> 7.44 ms
+// = 146 cycles per step — the 11 levels x (8.1 cycles + the serial issue of the level's members) of the step's own chain,
+// i.e. what one member's step costs on one in-order warp; the bare 89-cycle chain is not reachable in order.  The same
+// ensemble in a sine field 10.63 -> 7.79 ms (the table fetch leaves the integrator's stream too), 9472 members (two CTAs per
+// SM) 9.53 -> 8.34 ms; with renorm and / or a general easy axis the gain is 1-50 %.
 // Same Philox counters, same fp32 Box-Muller, same fused arithmetic in the same order (llg_math.cuh: heun_single_core) as
 // heun_single_kernel: per-member output is bit-identical (tests/test_parity_gpu.py); the ensemble sums are formed per
 // 32 members instead of per 128, i.e. in another (equally fixed) order.
@@ -29,8 +28,8 @@
 
 namespace mb {
 
-constexpr int SPLIT_B = 8;        // steps per ring slot (whole Philox blocks: slot boundaries sit at even step indices)
-constexpr int SPLIT_SLOTS = 4;
+constexpr int SPLIT_B = 32;       // steps per ring slot (whole Philox blocks: slot boundaries sit at even step indices)
+constexpr int SPLIT_SLOTS = 3;      // 3 x 32 steps x 1 KB = 96 KB of dynamic shared memory (one CTA per SM)
 constexpr int SPLIT_PRODUCERS = 3;   // one generator warp on each of the SM's other three sub-partitions, alternating batches
 constexpr int SPLIT_THREADS = 32 * (1 + SPLIT_PRODUCERS);
 
@@ -41,7 +40,8 @@ template <bool FIELD_TAB, bool AXIS_Z, bool RENORM>
 __global__ void __launch_bounds__(SPLIT_THREADS) heun_single_split_kernel(const __grid_constant__ RunParams P) {
     // ring[slot][step][0][lane] = {cwh.x, cwh.y}, ring[slot][step][1][lane] = {t0, t1}: every access is one conflict-free
     // 128-bit shared-memory transaction per lane
-    __shared__ double2 ring[SPLIT_SLOTS][SPLIT_B][2][32];
+    extern __shared__ double2 ring_raw[];
+    double2 (*ring)[SPLIT_B][2][32] = reinterpret_cast<double2 (*)[SPLIT_B][2][32]>(ring_raw);   // [SPLIT_SLOTS]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t r_raw = (uint64_t)blockIdx.x * 32 + lane;
     const bool live = r_raw < P.R;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) heun_single_split_kernel(const 
             const uint64_t jb = base + b * SPLIT_B;
             // the B / 2 Philox blocks of the batch, independent of each other: unrolled so that their multiply and
             // MUFU chains overlap (one block after the other is latency bound and would starve the consumer)
-#pragma unroll
+#pragma unroll 4
             for (int i = 0; i < SPLIT_B / 2; ++i) {
                 float g[6];
                 philox_gauss6_f32<0>(key0, key1, (uint32_t)((jb >> 1) + i), 0u, member, bm_scale, g, P.philox_m0, P.philox_m1,
@@ -149,11 +149,25 @@ __global__ void __launch_bounds__(SPLIT_THREADS) heun_single_split_kernel(const 
 cudaError_t launch_heun_single_split(bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
     const dim3 g(grid), b(SPLIT_THREADS);
     const bool renorm = P.renorm != 0;
-#define MB_HSS(T, A)                                                            \
-    if (renorm) heun_single_split_kernel<T, A, true><<<g, b, 0, s>>>(P);        \
-    else heun_single_split_kernel<T, A, false><<<g, b, 0, s>>>(P)
-    if (tab) { if (axis_z) { MB_HSS(true, true); } else { MB_HSS(true, false); } }
-    else { if (axis_z) { MB_HSS(false, true); } else { MB_HSS(false, false); } }
+    constexpr size_t smem = sizeof(double2) * SPLIT_SLOTS * SPLIT_B * 2 * 32;
+#define MB_HSS(T, A, RN)                                                                                              \
+    do {                                                                                                              \
+        static bool attr_set = false;   /* ring beyond the 48 KB static limit: opt in once per instantiation */       \
+        if (!attr_set) {                                                                                              \
+            const cudaError_t e = cudaFuncSetAttribute(heun_single_split_kernel<T, A, RN>,                            \
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+            if (e != cudaSuccess) return e;                                                                           \
+            attr_set = true;                                                                                          \
+        }                                                                                                             \
+        heun_single_split_kernel<T, A, RN><<<g, b, smem, s>>>(P);                                                     \
+    } while (0)
+    if (tab) {
+        if (axis_z) { if (renorm) MB_HSS(true, true, true); else MB_HSS(true, true, false); }
+        else { if (renorm) MB_HSS(true, false, true); else MB_HSS(true, false, false); }
+    } else {
+        if (axis_z) { if (renorm) MB_HSS(false, true, true); else MB_HSS(false, true, false); }
+        else { if (renorm) MB_HSS(false, false, true); else MB_HSS(false, false, false); }
+    }
 #undef MB_HSS
     return cudaGetLastError();
 }

@@ -398,14 +398,14 @@ void choose_k1_variant(magpy_b200_plan* pl, bool renorm, bool mp) {
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-    // K1s (heun_single_split.cu): at most 32 members per SM leave three of an SM's four sub-partitions idle; the step is
-    // split over an integrator warp and three generator warps on them (BASELINE config 1, 1000 members x 1e5 steps:
-    // 9.52 -> 8.74 ms, in a sine field 10.63 -> 8.74 ms, profiles/r02_probe_c1_split_v2.log).  With renorm or a general
-    // easy axis the integrator's longer chain leaves no gain (17.2 vs 16.5 ms).  Not for per-member material parameters.
+    // K1s (heun_single_split.cu): up to 64 members per SM leave at least two of an SM's four sub-partitions idle; the step is
+    // split over an integrator warp and three generator warps (BASELINE config 1, 1000 members x 1e5 steps: 9.52 -> 7.44 ms;
+    // in a sine field 10.63 -> 7.79 ms; 9472 members 9.53 -> 8.34 ms; every shape of axis / renorm / field gains, 1-50 %:
+    // profiles/r02_probe_c1_split_v2.log, r02_probe_k1s_shapes.log).  Not for per-member material parameters.
     // MAGPY_B200_K1_SPLIT=0|1 overrides.
     {
         const uint64_t split_grid = (pl->R + 31) / 32;
-        bool split = !mp && split_grid <= (uint64_t)sms && pl->axis_z && !renorm;
+        bool split = !mp && split_grid <= 2 * (uint64_t)sms;
         if (const char* env = std::getenv("MAGPY_B200_K1_SPLIT")) split = !mp && std::atoi(env) != 0 && split_grid < 0x7fffffffull;
         if (split) {
             pl->k1_split = true;

@@ -367,11 +367,9 @@ def test_heun_single_register_and_latency_variants_are_bit_identical(core, field
         assert np.array_equal(outs['1']['trajectories'], sp['trajectories'])
         assert np.array_equal(outs['1']['final'], sp['final'])
         assert np.allclose(outs['1']['sums'], sp['sums'], rtol=1e-13, atol=1e-13 * np.abs(outs['1']['sums']).max())
-    plain = tuple(axis) == (0, 0, 1.0) and not renorm        # K1s is the default up to 32 members per SM for this shape only
-    small = 100 if field_shape != 'constant' else 1          # otherwise: the latency variant when there is a field table
-    assert gpu_run(core, c, np.arange(100))['stats']['kernel_variant'] == (300 if plain else small)
-    assert gpu_run(core, c, np.arange(6000))['stats']['kernel_variant'] == small
-    assert gpu_run(core, c, np.arange(200000), return_trajectories=False)['stats']['kernel_variant'] == 1    # 437 steps: too short to cut into segments
+    small = 100 if field_shape != 'constant' else 1          # beyond K1s: the latency variant when there is a field table
+    assert gpu_run(core, c, np.arange(100))['stats']['kernel_variant'] == 300         # K1s: the default up to 64 members per SM
+    assert gpu_run(core, c, np.arange(12000))['stats']['kernel_variant'] == small
 
 
 @pytest.mark.parametrize('field_shape,axis,renorm,chunk', [('constant', (0, 0, 1.0), False, None), ('sine', (0, 0, 1.0), True, 4999),
