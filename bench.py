@@ -510,7 +510,7 @@ def ours(args):
                                        100: 'heun_single, latency variant (field table prefetched)',
                                        200: 'heun_single_balanced: persistent kernel over (time segment, 128-member block) tasks',
                                        300: 'heun_single_split: integrator warp + three generator warps per 32 members '
-                                            '(at most 32 members per SM)'
+                                            '(at most 64 members per SM)'
                                        }.get(variant, str(variant)) if w['N'] == 1 and not w.get('implicit') else None),
                    'other_scaling_mode': other,
                    'mean_mz_over_Ms_at_end': mean_mz, 'wall_s_timed_region': wall},

@@ -66,7 +66,7 @@ typedef struct magpy_b200_stats {
                                       prefetched a step pair ahead), 200 = persistent kernel over (time segment,
                                       member block) tasks for shards of more than one wave (no rounding up to whole
                                       warps per SM sub-partition), 300 = one integrator warp fed by three generator warps
-                                      per 32 members (ensembles of at most 32 members per SM); 0 for the other kernels
+                                      per 32 members (ensembles of at most 64 members per SM); 0 for the other kernels
                                       (ABI v4)                                                                  */
     /* host wall-clock of the blocking entry points (magpy_b200_simulate_ensemble[_multi]), ms (ABI v4): */
     double host_setup_ms;          /* plan creation: validation, schedule, allocations, uploads             */

@@ -150,15 +150,13 @@ cudaError_t launch_heun_single_split(bool tab, bool axis_z, unsigned grid, cudaS
     const dim3 g(grid), b(SPLIT_THREADS);
     const bool renorm = P.renorm != 0;
     constexpr size_t smem = sizeof(double2) * SPLIT_SLOTS * SPLIT_B * 2 * 32;
+    // the ring is beyond the 48 KB static limit: opt in before every launch (the attribute is per device, and a process may
+    // drive several devices)
 #define MB_HSS(T, A, RN)                                                                                              \
     do {                                                                                                              \
-        static bool attr_set = false;   /* ring beyond the 48 KB static limit: opt in once per instantiation */       \
-        if (!attr_set) {                                                                                              \
-            const cudaError_t e = cudaFuncSetAttribute(heun_single_split_kernel<T, A, RN>,                            \
-                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-            if (e != cudaSuccess) return e;                                                                           \
-            attr_set = true;                                                                                          \
-        }                                                                                                             \
+        const cudaError_t e = cudaFuncSetAttribute(heun_single_split_kernel<T, A, RN>,                                \
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        if (e != cudaSuccess) return e;                                                                               \
         heun_single_split_kernel<T, A, RN><<<g, b, smem, s>>>(P);                                                     \
     } while (0)
     if (tab) {
