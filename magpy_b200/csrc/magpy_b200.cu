@@ -217,7 +217,7 @@ struct magpy_b200_plan {
     bool k1_balanced = false;   // K1b: multi-wave shards run as a persistent kernel over (time segment, member block) tasks
     unsigned bal_phys = 0;      //   ... its physical grid (resident CTAs)
     std::vector<uint32_t> bal_segments;   //   ... segments per chunk (1 = plain launch)
-    bool k1_split = false;      // K1s: ensembles of at most 32 members per SM: integrator warp + generator warp per 32 members
+    bool k1_split = false;      // K1s: ensembles of at most 64 members per SM: integrator warp + three generator warps per 32 members
     int k1_min_blocks = 1; // K1: register-allocation variant (resident CTAs per SM asked of ptxas), see choose_k1_variant
     bool small = false;    // few particles: one thread per cluster, all moments in registers
     bool split = false;    //   ... implicit, one lane per particle (imid_split_kernel)
