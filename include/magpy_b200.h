@@ -85,6 +85,7 @@ typedef struct magpy_b200_stats {
 #define MAGPY_B200_KERNEL_HEUN_CLUSTER_MMA 7 /* cluster_mma.cu: dipolar field as a matrix product (DMMA)     */
 #define MAGPY_B200_KERNEL_IMID_SPLIT 8       /* small_imid.cu: one lane per particle (small ensembles, N = 2, 4) */
 #define MAGPY_B200_KERNEL_HEUN_CLUSTER_BIG 10 /* cluster_big.cu: Heun beyond 128 particles, moments in global memory      */
+#define MAGPY_B200_KERNEL_IMID_WARPS 12      /* small_imid.cu: one warp per particle (small ensembles, N = 2..4)  */
 #define MAGPY_B200_KERNEL_IMID_CLUSTER_BIG 11 /* cluster_big.cu: implicit midpoint beyond 128 particles, iterates in global memory */
 #define MAGPY_B200_KERNEL_IMID_CLUSTER_MMA 9 /* cluster_mma_imid.cu: implicit midpoint, dipolar field of every quasi-Newton
                                                 iteration as a matrix product (DMMA), 8..128 particles             */

@@ -221,7 +221,7 @@ cdef _raise(int rc):
 
 _KERNEL_NAMES = {1: 'heun_single', 2: 'imid_single', 3: 'heun_small', 4: 'imid_small', 5: 'heun_cluster',
                  6: 'imid_cluster', 7: 'heun_cluster_mma', 8: 'imid_split', 9: 'imid_cluster_mma', 10: 'heun_cluster_big',
-                 11: 'imid_cluster_big'}
+                 11: 'imid_cluster_big', 12: 'imid_warps'}
 
 
 cdef dict _stats_dict(magpy_b200_stats* st):

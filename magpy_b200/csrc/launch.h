@@ -26,6 +26,8 @@ cudaError_t launch_imid_single(int noise, bool tab, bool axis_z, unsigned grid, 
 cudaError_t launch_heun_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
 cudaError_t launch_imid_small(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
 cudaError_t launch_imid_split(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
+// one warp per particle (N = 2..4, small ensembles): grid = ceil(R / 32) CTAs of 32 N threads
+cudaError_t launch_imid_warps(int noise, bool tab, unsigned n_particles, unsigned grid, cudaStream_t s, const RunParams& P);
 // layout: 0 = pair table in global memory, 1 = table in shared memory, 2 = table in shared memory + one moment buffer
 cudaError_t launch_heun_cluster(int noise, bool tab, int np, int layout, dim3 grid, dim3 block, size_t smem,
                                 cudaStream_t s, const RunParams& P);

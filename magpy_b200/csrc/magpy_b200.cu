@@ -221,6 +221,7 @@ struct magpy_b200_plan {
     int k1_min_blocks = 1; // K1: register-allocation variant (resident CTAs per SM asked of ptxas), see choose_k1_variant
     bool small = false;    // few particles: one thread per cluster, all moments in registers
     bool split = false;    //   ... implicit, one lane per particle (imid_split_kernel)
+    bool warps = false;    //   ... implicit, one warp per particle (imid_warps_kernel)
     bool mma = false;      // Heun cluster kernel on the FP64 MMA path (cluster_mma.cu)
     bool imid_mma = false; // implicit cluster kernel on the FP64 MMA path (cluster_mma_imid.cu)
     bool big = false;      // beyond 128 particles: moments in global memory (cluster_big.cu), Heun and implicit midpoint
@@ -288,7 +289,8 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
         else if (pl->k1_split) LAUNCH_TRY(mb::launch_heun_single_split(tab, pl->axis_z, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_single(noise, tab, pl->axis_z, pl->k1_min_blocks, pl->grid, pl->stream, P));
     } else if (pl->small) {
-        if (pl->split) LAUNCH_TRY(mb::launch_imid_split(noise, tab, pl->N, pl->grid, pl->stream, P));
+        if (pl->warps) LAUNCH_TRY(mb::launch_imid_warps(noise, tab, pl->N, pl->grid, pl->stream, P));
+        else if (pl->split) LAUNCH_TRY(mb::launch_imid_split(noise, tab, pl->N, pl->grid, pl->stream, P));
         else if (pl->implicit) LAUNCH_TRY(mb::launch_imid_small(noise, tab, pl->N, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_small(noise, tab, pl->N, pl->grid, pl->stream, P));
     } else if (pl->mma) {
@@ -568,15 +570,27 @@ int plan_build(const magpy_b200_ensemble* a, magpy_b200_plan* pl) {
         // bound: one lane per particle instead (small_imid.cu, imid_split_kernel; a dimer's two particles already
         // interleave in one thread, so it gains nothing).
         // MAGPY_B200_SMALL_KERNEL=split|thread overrides the choice.
-        if (pl->implicit && (N == 2 || N == 4)) {   // measured (profiles/r01_probe_c2.log): a gain for N = 4 only
+        if (pl->implicit && N <= 4) {
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-            bool split = N == 4 && R < (uint64_t)sms * 4 * 2 * 32;
+            bool split = N == 4 && R < (uint64_t)sms * 4 * 2 * 32;   // measured (profiles/r01_probe_c2.log): a gain for N = 4 only
+            // one WARP per particle (imid_warps_kernel) for trimers / tetramers of at most one CTA per SM: 1000 tetramers 13.4 ms
+            // against 16.6 (one lane per particle) and 28.1 (one thread per cluster); dimers gain 4-7 % with general easy axes
+            // and LOSE with aligned ones (config 2: 14.5 against 11.2 ms), so they stay on one thread per cluster
+            // (profiles/r02_probe_c2.log)
+            bool warps = N >= 3 && R <= (uint64_t)sms * 32;
+            if (warps) split = false;
             if (const char* force = std::getenv("MAGPY_B200_SMALL_KERNEL")) {
-                if (std::strcmp(force, "split") == 0) split = R * N < 0xFFFFFFFFull;
-                else if (std::strcmp(force, "thread") == 0) split = false;
+                if (std::strcmp(force, "split") == 0) split = (N == 2 || N == 4) && R * N < 0xFFFFFFFFull;
+                else if (std::strcmp(force, "thread") == 0) { split = false; warps = false; }
+                else if (std::strcmp(force, "warps") == 0) { warps = true; split = false; }
+                if (std::strcmp(force, "split") == 0 && split) warps = false;
             }
-            if (split) {
+            if (warps) {
+                pl->warps = true;
+                pl->block = dim3(32 * N);
+                pl->grid = (unsigned)((R + 31) / 32);
+            } else if (split) {
                 pl->split = true;
                 pl->grid = (unsigned)((R * N + mb::SINGLE_THREADS - 1) / mb::SINGLE_THREADS);
             }
@@ -1047,6 +1061,7 @@ int plan_sync(magpy_b200_plan* pl, magpy_b200_stats* st) {
     st->d2h_bytes = pl->d2h;
     st->kernel_family = pl->N == 1 ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SINGLE
                                       : MAGPY_B200_KERNEL_HEUN_SINGLE)
+                        : pl->warps ? MAGPY_B200_KERNEL_IMID_WARPS
                         : pl->split ? MAGPY_B200_KERNEL_IMID_SPLIT
                         : pl->small ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_SMALL : MAGPY_B200_KERNEL_HEUN_SMALL)
                         : pl->big   ? (pl->implicit ? MAGPY_B200_KERNEL_IMID_CLUSTER_BIG : MAGPY_B200_KERNEL_HEUN_CLUSTER_BIG)

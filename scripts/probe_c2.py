@@ -7,7 +7,7 @@ from probe_cluster import run
 
 for R in (1000, 10000, 40000, 1 << 18):
     for N in (2, 4):
-        for kern in ('thread', 'split'):
+        for kern in ('thread', 'split', 'warps'):
             os.environ['MAGPY_B200_SMALL_KERNEL'] = kern
             print(kern, end=' ')
             run(N, R, 1000, implicit=True)

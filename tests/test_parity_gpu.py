@@ -281,7 +281,7 @@ def test_implicit_cluster_injected(orc, core, N, interactions, monkeypatch):
     t, fl, ref, out, newton = injected_pair(orc, core, c, seeds, per_member=(N in (2, 4, 12)))
     assert_traj(ref, out, c)
     assert out['stats']['newton_iterations'] == sum(n[0] - n[2] for n in newton)     # identical iteration counts
-    assert out['stats']['kernel'] == ('imid_split' if N == 4 else 'imid_small' if N <= 3 else 'imid_cluster' if N <= 16
+    assert out['stats']['kernel'] == ('imid_small' if N == 2 else 'imid_warps' if N <= 4 else 'imid_cluster' if N <= 16
                                       else 'imid_cluster_mma')
     if N in (8, 12, 16, 40):   # the other cluster kernel on the same case (default: scalar up to 16 particles, matrix product above)
         other = 'mma' if N <= 16 else 'simt'
@@ -291,12 +291,17 @@ def test_implicit_cluster_injected(orc, core, N, interactions, monkeypatch):
         assert_traj(ref, out2, c)
         assert out2['stats']['newton_iterations'] == out['stats']['newton_iterations']
         monkeypatch.delenv('MAGPY_B200_CLUSTER_KERNEL')
-    if N in (2, 4):   # both mappings of small clusters: one thread per cluster and one lane per particle
-        monkeypatch.setenv('MAGPY_B200_SMALL_KERNEL', 'thread' if N == 4 else 'split')
-        t, fl, ref, out2, newton = injected_pair(orc, core, c, seeds, per_member=True)
-        assert out2['stats']['kernel'] == ('imid_small' if N == 4 else 'imid_split')
-        assert_traj(ref, out2, c)
-        assert out2['stats']['newton_iterations'] == out['stats']['newton_iterations']
+    if N in (2, 3, 4):   # the mappings of small clusters: one thread per cluster, one lane per particle (N = 2, 4), one warp per
+        # particle (shared-memory exchange of the iterates; the default for small ensembles of trimers / tetramers)
+        for mapping, kernel in (('thread', 'imid_small'), ('split', 'imid_split'), ('warps', 'imid_warps')):
+            if mapping == 'split' and N == 3:
+                continue
+            monkeypatch.setenv('MAGPY_B200_SMALL_KERNEL', mapping)
+            t, fl, ref, out2, newton = injected_pair(orc, core, c, seeds, per_member=(N in (2, 4)))
+            assert out2['stats']['kernel'] == kernel
+            assert_traj(ref, out2, c)
+            assert out2['stats']['newton_iterations'] == out['stats']['newton_iterations']
+            assert out2['stats']['newton_failures'] == 0
 
 
 @pytest.mark.parametrize('N,axis_z', [(1, True), (1, False), (2, False), (4, False), (12, False)])
@@ -324,12 +329,13 @@ def test_exact_newton_mode_is_the_converged_reference_iteration(orc, core, N, ax
     assert 1e-11 < np.abs(slow['trajectories'] - ref).max() / c.Ms < 1e-7
     with pytest.raises(KeyError):
         gpu_run(core, c, seeds, dW=dW, implicit_newton='broyden')
-    if N == 4:   # small ensembles of tetramers default to one lane per particle; the thread-per-cluster kernel as well
-        assert fast['stats']['kernel'] == 'imid_split'
-        monkeypatch.setenv('MAGPY_B200_SMALL_KERNEL', 'thread')
-        fast2 = gpu_run(core, ol.Case(dict(c, eps=1e-9)), seeds, dW=dW, implicit_newton='exact')
-        assert fast2['stats']['kernel'] == 'imid_small'
-        assert np.abs(fast2['trajectories'] - ref).max() / c.Ms < 1e-11
+    if N == 4:   # small ensembles of tetramers default to one warp per particle; the other two mappings as well
+        assert fast['stats']['kernel'] == 'imid_warps'
+        for mapping, kernel in (('thread', 'imid_small'), ('split', 'imid_split')):
+            monkeypatch.setenv('MAGPY_B200_SMALL_KERNEL', mapping)
+            fast2 = gpu_run(core, ol.Case(dict(c, eps=1e-9)), seeds, dW=dW, implicit_newton='exact')
+            assert fast2['stats']['kernel'] == kernel
+            assert np.abs(fast2['trajectories'] - ref).max() / c.Ms < 1e-11
 
 
 @pytest.mark.parametrize('field_shape,axis,renorm,chunk', [('sine', (0, 0, 1.0), True, 7), ('sine', (0.6, 0, 0.8), False, 13),
