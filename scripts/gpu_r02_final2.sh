@@ -27,4 +27,8 @@ echo "== ncu full: heun_single (balanced persistent kernel, the bench kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:heun_single_balanced -c 1 \
     -f -o gpurun_out/r02_heun_single_balanced python scripts/probe_one.py 1 heun 1000000 4000 > gpurun_out/r02_ncu_k1b.log 2>&1
 tail -2 gpurun_out/r02_ncu_k1b.log
+echo "== ncu full: heun_single_split (K1s, config 1 shape: 1000 members x 4000 steps)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:heun_single_split -c 1 \
+    -f -o gpurun_out/r02_heun_single_split python scripts/probe_one.py 1 heun 1000 4000 > gpurun_out/r02_ncu_k1s.log 2>&1
+tail -2 gpurun_out/r02_ncu_k1s.log
 ls -la gpurun_out | tail -12
