@@ -16,8 +16,9 @@
 // Measured (profiles/r02_probe_c1_split_v2.log, r02_probe_k1s_shapes.log): config 1 (1000 members x 1e5 steps) 9.52 -> 7.44 ms
 // = 146 cycles per step — the 11 levels x (8.1 cycles + the serial issue of the level's members) of the step's own chain,
 // i.e. what one member's step costs on one in-order warp; the bare 89-cycle chain is not reachable in order.  The same
-// ensemble in a sine field 10.63 -> 7.79 ms (the table fetch leaves the integrator's stream too), 9472 members (two CTAs per
-// SM) 9.53 -> 8.34 ms; with renorm and / or a general easy axis the gain is 1-50 %.
+// ensemble in a sine field 10.63 -> 7.76 ms (the table fetch leaves the integrator's stream too: one coalesced load per batch
+// by the producer), 9472 members (two CTAs per SM, one producer each) 9.49 -> 7.80 ms, in a sine field 11.5 -> 8.0 ms; with
+// renorm and / or a general easy axis the gain is 1-50 %.
 // Same Philox counters, same fp32 Box-Muller, same fused arithmetic in the same order (llg_math.cuh: heun_single_core) as
 // heun_single_kernel: per-member output is bit-identical (tests/test_parity_gpu.py); the ensemble sums are formed per
 // 32 members instead of per 128, i.e. in another (equally fixed) order.
@@ -30,18 +31,20 @@ namespace mb {
 
 constexpr int SPLIT_B = 32;       // steps per ring slot (whole Philox blocks: slot boundaries sit at even step indices)
 constexpr int SPLIT_SLOTS = 3;      // 3 x 32 steps x 1 KB = 96 KB of dynamic shared memory (one CTA per SM)
-constexpr int SPLIT_PRODUCERS = 3;   // one generator warp on each of the SM's other three sub-partitions, alternating batches
-constexpr int SPLIT_THREADS = 32 * (1 + SPLIT_PRODUCERS);
+// NPROD generator warps per integrator warp: 3 (one on each of the SM's other three sub-partitions, alternating batches) when
+// there is at most one CTA per SM, 1 (CTAs of 64 threads) when two CTAs share an SM — one generator keeps up with its
+// integrator (~50 against 146 issue cycles per step), and two CTAs of two warps put every warp on its own sub-partition
 
 __device__ __forceinline__ void bar_sync(const int id, const int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <bool FIELD_TAB, bool AXIS_Z, bool RENORM>
-__global__ void __launch_bounds__(SPLIT_THREADS) heun_single_split_kernel(const __grid_constant__ RunParams P) {
+template <bool FIELD_TAB, bool AXIS_Z, bool RENORM, int NPROD>
+__global__ void __launch_bounds__(32 * (1 + NPROD)) heun_single_split_kernel(const __grid_constant__ RunParams P) {
     // ring[slot][step][0][lane] = {cwh.x, cwh.y}, ring[slot][step][1][lane] = {t0, t1}: every access is one conflict-free
     // 128-bit shared-memory transaction per lane
     extern __shared__ double2 ring_raw[];
     double2 (*ring)[SPLIT_B][2][32] = reinterpret_cast<double2 (*)[SPLIT_B][2][32]>(ring_raw);   // [SPLIT_SLOTS]
+    __shared__ double2 htab[NPROD][32];    // per producer warp: the applied field of the batch being generated
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t r_raw = (uint64_t)blockIdx.x * 32 + lane;
     const bool live = r_raw < P.R;
@@ -60,10 +63,19 @@ __global__ void __launch_bounds__(SPLIT_THREADS) heun_single_split_kernel(const 
         const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
         const uint32_t member = member_id(P, r);
         const double2* tab = reinterpret_cast<const double2*>(P.field_tab);
-        for (uint64_t b = warp - 1; b < n_batches; b += SPLIT_PRODUCERS) {
+        for (uint64_t b = warp - 1; b < n_batches; b += NPROD) {
             const int slot = (int)(b % SPLIT_SLOTS);
             if (b >= SPLIT_SLOTS) bar_sync(1 + SPLIT_SLOTS + slot, 64);      // the consumer has drained this slot
             const uint64_t jb = base + b * SPLIT_B;
+            // the applied field of the batch's SPLIT_B steps: ONE coalesced load (lane i fetches step jb + i), parked in shared
+            // memory and read back as broadcasts — a load per step at its point of use would put an L2 round trip into the
+            // chain of every Philox block and, with one producer per consumer, starve the consumer
+            if (FIELD_TAB) {
+                static_assert(SPLIT_B == 32, "one table entry per lane");
+                const uint64_t jl = jb + lane;
+                htab[warp - 1][lane] = (jl >= P.j0 && jl < P.j1) ? __ldg(tab + (jl - P.j0)) : make_double2(0.0, 0.0);   // steps outside the launch are never consumed
+                __syncwarp();
+            }
             // the B / 2 Philox blocks of the batch, independent of each other: unrolled so that their multiply and
             // MUFU chains overlap (one block after the other is latency bound and would starve the consumer)
 #pragma unroll 4
@@ -73,10 +85,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) heun_single_split_kernel(const 
                                      P.bm_mask_r, P.bm_mask_a);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint64_t j = jb + 2 * i + h;
                     double hz0 = P.h_const, hz1 = P.h_const;
-                    if (FIELD_TAB && j >= P.j0 && j < P.j1) {    // steps outside the launch are never consumed
-                        const double2 t = __ldg(tab + (j - P.j0));
+                    if (FIELD_TAB) {
+                        const double2 t = htab[warp - 1][2 * i + h];
                         hz0 = t.x; hz1 = t.y;
                     }
                     const double cz = widen_f32(g[3 * h + 2]);
@@ -84,6 +95,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) heun_single_split_kernel(const 
                     ring[slot][2 * i + h][1][lane] = make_double2(fma(hz0, dth, cz), fma(hz1, dth, cz));
                 }
             }
+            if (FIELD_TAB) __syncwarp();      // every lane has read the table slab before the next batch overwrites it
             __threadfence_block();
             bar_arrive(1 + slot, 64);                                          // the slot is full
         }
@@ -145,19 +157,25 @@ __global__ void __launch_bounds__(SPLIT_THREADS) heun_single_split_kernel(const 
     }
 }
 
-// grid = ceil(R / 32) CTAs of SPLIT_THREADS threads; packed-noise production mode only
-cudaError_t launch_heun_single_split(bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P) {
-    const dim3 g(grid), b(SPLIT_THREADS);
+// grid = ceil(R / 32) CTAs of 32 (1 + producers) threads; packed-noise production mode only
+cudaError_t launch_heun_single_split(bool tab, bool axis_z, int producers, unsigned grid, cudaStream_t s, const RunParams& P) {
+    const dim3 g(grid), b(32 * (1 + producers));
     const bool renorm = P.renorm != 0;
     constexpr size_t smem = sizeof(double2) * SPLIT_SLOTS * SPLIT_B * 2 * 32;
     // the ring is beyond the 48 KB static limit: opt in before every launch (the attribute is per device, and a process may
     // drive several devices)
-#define MB_HSS(T, A, RN)                                                                                              \
+#define MB_HSS2(T, A, RN, NP)                                                                                         \
     do {                                                                                                              \
-        const cudaError_t e = cudaFuncSetAttribute(heun_single_split_kernel<T, A, RN>,                                \
+        const cudaError_t e = cudaFuncSetAttribute(heun_single_split_kernel<T, A, RN, NP>,                            \
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
         if (e != cudaSuccess) return e;                                                                               \
-        heun_single_split_kernel<T, A, RN><<<g, b, smem, s>>>(P);                                                     \
+        heun_single_split_kernel<T, A, RN, NP><<<g, b, smem, s>>>(P);                                                 \
+    } while (0)
+#define MB_HSS(T, A, RN)                                             \
+    do {                                                             \
+        if (producers == 3) MB_HSS2(T, A, RN, 3);                    \
+        else if (producers == 1) MB_HSS2(T, A, RN, 1);               \
+        else return cudaErrorInvalidValue;                           \
     } while (0)
     if (tab) {
         if (axis_z) { if (renorm) MB_HSS(true, true, true); else MB_HSS(true, true, false); }
@@ -167,6 +185,7 @@ cudaError_t launch_heun_single_split(bool tab, bool axis_z, unsigned grid, cudaS
         else { if (renorm) MB_HSS(false, false, true); else MB_HSS(false, false, false); }
     }
 #undef MB_HSS
+#undef MB_HSS2
     return cudaGetLastError();
 }
 

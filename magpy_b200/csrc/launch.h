@@ -19,7 +19,7 @@ cudaError_t launch_heun_single(int noise, bool tab, bool axis_z, int min_blocks,
 cudaError_t launch_heun_single_balanced(bool tab, bool axis_z, unsigned phys_grid, cudaStream_t s, const RunParams& P);
 int heun_single_balanced_resident_ctas(bool tab, bool axis_z, bool renorm);
 // K1s (heun_single_split.cu): small ensembles, grid = ceil(R / 32) CTAs of one integrator warp and one generator warp
-cudaError_t launch_heun_single_split(bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P);
+cudaError_t launch_heun_single_split(bool tab, bool axis_z, int producers, unsigned grid, cudaStream_t s, const RunParams& P);
 constexpr int K1_SPLIT = 300;   // stats.kernel_variant of K1s
 int heun_single_resident_ctas(bool tab, bool axis_z, bool renorm, int min_blocks);
 cudaError_t launch_imid_single(int noise, bool tab, bool axis_z, unsigned grid, cudaStream_t s, const RunParams& P);

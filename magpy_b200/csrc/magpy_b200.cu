@@ -286,7 +286,7 @@ int launch_integrate(magpy_b200_plan* pl, const mb::RunParams& P) {
     const bool tab = pl->use_table;
     if (pl->N == 1) {
         if (pl->implicit) LAUNCH_TRY(mb::launch_imid_single(noise, tab, pl->axis_z, pl->grid, pl->stream, P));
-        else if (pl->k1_split) LAUNCH_TRY(mb::launch_heun_single_split(tab, pl->axis_z, pl->grid, pl->stream, P));
+        else if (pl->k1_split) LAUNCH_TRY(mb::launch_heun_single_split(tab, pl->axis_z, (int)pl->block.x / 32 - 1, pl->grid, pl->stream, P));
         else LAUNCH_TRY(mb::launch_heun_single(noise, tab, pl->axis_z, pl->k1_min_blocks, pl->grid, pl->stream, P));
     } else if (pl->small) {
         if (pl->warps) LAUNCH_TRY(mb::launch_imid_warps(noise, tab, pl->N, pl->grid, pl->stream, P));
@@ -402,8 +402,8 @@ void choose_k1_variant(magpy_b200_plan* pl, bool renorm, bool mp) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
     // K1s (heun_single_split.cu): up to 64 members per SM leave at least two of an SM's four sub-partitions idle; the step is
     // split over an integrator warp and three generator warps (BASELINE config 1, 1000 members x 1e5 steps: 9.52 -> 7.44 ms;
-    // in a sine field 10.63 -> 7.79 ms; 9472 members 9.53 -> 8.34 ms; every shape of axis / renorm / field gains, 1-50 %:
-    // profiles/r02_probe_c1_split_v2.log, r02_probe_k1s_shapes.log).  Not for per-member material parameters.
+    // in a sine field 10.63 -> 7.76 ms; 9472 members 9.49 -> 7.80 ms; every shape of axis / renorm / field gains, 1-50 %:
+    // profiles/r02_probe_c1_split_v2.log, r02_probe_k1s_shapes.log, r02_probe_k1s_producers.log).  Not for per-member material parameters.
     // MAGPY_B200_K1_SPLIT=0|1 overrides.
     {
         const uint64_t split_grid = (pl->R + 31) / 32;
@@ -412,7 +412,11 @@ void choose_k1_variant(magpy_b200_plan* pl, bool renorm, bool mp) {
         if (split) {
             pl->k1_split = true;
             pl->grid = (unsigned)split_grid;
-            pl->block = dim3(128);
+            // one CTA per SM: three generator warps on the SM's idle sub-partitions; two CTAs per SM: one generator each, so
+            // that every warp still has a sub-partition to itself (MAGPY_B200_K1_SPLIT_PRODUCERS=1|3 overrides)
+            int producers = split_grid <= (uint64_t)sms ? 3 : 1;
+            if (const char* env = std::getenv("MAGPY_B200_K1_SPLIT_PRODUCERS")) producers = std::atoi(env) == 1 ? 1 : 3;
+            pl->block = dim3(32 * (1 + producers));
             return;
         }
     }
