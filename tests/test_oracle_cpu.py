@@ -305,6 +305,33 @@ def test_philox_random123_known_answers(orc):
         assert tuple(ol.philox(orc, ctr, key)) == want
 
 
+def test_packed_gaussian_stream_layout_against_an_independent_restatement(orc):
+    """The production noise mode cuts one Philox4x32-10 block into three (radius, angle) pairs (magpy_b200/csrc/rng.cuh:
+    philox_gauss6_f32; restated in oracle/sllg_oracle.c, mode 2).  The kernel and the oracle are compared draw by draw on the
+    GPU; here the oracle's restatement is checked against a third, independent one written from the documented layout —
+    each 64-bit half {w1:w0}, {w3:w2} is [23-bit radius field | 18-bit angle | 23 bits], radius uniforms are the midpoints
+    of a 22-bit grid, 2^18 equidistant directions — so that oracle and kernel cannot drift together unnoticed."""
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        seed = int(rng.integers(0, 2**62)); member = int(rng.integers(0, 2**32)); particle = int(rng.integers(0, 200))
+        step = int(rng.integers(1, 2**33))
+        w = ol.philox(orc, [((step - 1) >> 1) & 0xffffffff, member, seed & 0xffffffff, seed >> 32],
+                      [particle | (2 << 24), 0xB2005EED])
+        h0 = (w[1] << 32) | w[0]; h1 = (w[3] << 32) | w[2]
+        fields = [(w[0] & 0x7fffff, (h0 >> 23) & 0x3ffff), (w[1] >> 9, (h1 >> 23) & 0x3ffff), (w[2] & 0x7fffff, w[3] >> 14)]
+        g = []
+        for r23, a18 in fields:
+            u = np.float32(1.0 - ((r23 >> 1) + 0.5) * 2.0 ** -22)                 # u = 2 - f: the midpoints of a 22-bit grid on (0, 1)
+            r = np.sqrt(np.float32(-2.0) * np.log(u, dtype=np.float32), dtype=np.float32)
+            a = np.float32(2 * np.pi * (1 + a18 * 2.0 ** -18))
+            g += [float(r * np.cos(a, dtype=np.float32)), float(r * np.sin(a, dtype=np.float32))]
+        want = g[3:] if (step - 1) & 1 else g[:3]
+        got = ol.philox_gauss3(orc, seed, member, particle, step, 2)
+        assert np.allclose(got, want, rtol=0, atol=3e-6), (got, want)
+    # the largest radius the stream can produce: the last cell, u = 2^-23 -> sqrt(2 ln 2^23) = 5.65
+    assert abs(np.sqrt(-2 * np.log(0.5 * 2.0 ** -22)) - 5.6468) < 1e-3
+
+
 def test_schedule_semantics(orc):
     # zero-order hold: sample k stores the state after cum[k]-1 steps; finer sampling than stepping repeats
     cum = ol.schedule(orc, 0.3, 1.0, 11)
