@@ -466,7 +466,7 @@ def ours(args):
     achieved = W_ALG * (ps_per_pass / world) / (int_ms * 1e-3) / 1e12 if W_ALG else None
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'heun_single_traffic.json')
-    if w['N'] == 1 and world == 1 and os.path.exists(prof):
+    if args.workload == 'c3' and world == 1 and os.path.exists(prof):   # the capture is of the C3 kernel at the C3 size
         try:
             traffic = json.load(open(prof)).get('dram_bytes_per_launch')
         except Exception:
