@@ -441,12 +441,15 @@ def ours(args):
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
+    pass_s = []                                                   # wall clock of every pass, for the record (this rank)
     for i in range(e2e_passes):
+        tp = time.perf_counter()
         res = ens.simulate(w['t_end'], w['dt'], w['S'], w['random_state'], implicit_solve=implicit,
                            device=local_rank, return_trajectories=traj, shard=shard, comm=comm)
         h2d += sum(s['h2d_bytes'] for s in res.stats)
         d2h += sum(s['d2h_bytes'] for s in res.stats)
         final_mz = float(res.ensemble_magnetisation()[-1])        # the step's result, read on the host
+        pass_s.append(time.perf_counter() - tp)
     barrier()
     tt = np.array([(time.perf_counter() - t0) / e2e_passes, float(h2d), float(d2h)])
     if comm is not None:
@@ -538,6 +541,7 @@ def ours(args):
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d // e2e_passes,
                 'd2h_bytes_per_step': d2h // e2e_passes, 'api': 'EnsembleModel.simulate', 'passes': e2e_passes,
+                'pass_s': [round(x, 6) for x in pass_s],
                 'mean_mz_over_Ms_at_end': final_mz / w['Ms'] / w['N']},
         'gpu_launches': int(gpu_launches),
         'clocks': clocks,
