@@ -468,3 +468,33 @@ def test_single_particle_radius_and_temperature_overrides_are_one_call(monkeypat
     dimer = mp.Model([7e-9, 7e-9], [1e5, 1e5], [[0, 0, 1.0]] * 2, [[0, 0, 1.0]] * 2, [[0, 0, 0], [0, 0, 9e-9]], 4e5, 0.1, 330.0)
     mp.EnsembleModel(R, dimer, temperature=temps).simulate(1e-9, 1e-12, 5, random_state=1, implicit_solve=False)
     assert sorted(int(c['n']) for c in calls) == [1, 1, 1, 3] and all(np.ndim(c['T']) == 0 for c in calls)
+
+
+def test_bench_kernel_instruction_budget():
+    """K1 is bound by instruction issue: an FP64 instruction holds its sub-partition's issue port 2
+    cycles, 3 with three distinct register operands, every other instruction 1.  The inner loop of the bench kernel is read
+    from the SASS of the built library (no GPU needed) and held to its budget, so that a source change that makes ptxas emit
+    a longer loop — or spill, or lose the sixth resident CTA — is caught here and not on the next bench run."""
+    import shutil
+    import subprocess
+    import sys as _sys
+    lib = os.path.join(ROOT, 'magpy_b200', 'libmagpy_b200.so')
+    if shutil.which('cuobjdump') is None or not os.path.exists(lib):
+        pytest.skip('needs cuobjdump and the built library')
+    _sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+    import k1_cost_model as k
+    import re
+    for name, ins in k.functions(lib):
+        if re.search('heun_single_balanced_kernelILb1ELb1ELb0', name):
+            body = k.inner_loop(ins)
+            cycles, hist, other = k.cost(body)
+            pairs = 2                                  # two step pairs per loop trip
+            fp64 = sum(hist.values())
+            assert fp64 == 2 * 37 * pairs              # 37 FP64 instructions per Heun step
+            assert len(body) <= 168 * pairs            # round 1: 182 per step pair
+            assert cycles <= 275 * pairs               # issue-cost model; round 1: 297, measured 300.6
+            res = subprocess.run(['cuobjdump', '-res-usage', lib], capture_output=True, text=True).stdout
+            m = re.search(re.escape(name) + r':\s*\n\s*REG:(\d+) STACK:(\d+)', res)
+            assert m and int(m.group(1)) <= 80 and int(m.group(2)) == 0      # six CTAs of 128 threads per SM, no spills
+            return
+    raise AssertionError('bench kernel not found in the library')
