@@ -1,7 +1,7 @@
 // heun_single_balanced.cu — K1b: heun_single_kernel as a persistent kernel over (time segment, member block) tasks.
 //
-// K1 is bound by the FP64-side issue time of a warp-step, so the time of a launch is (warps per SM sub-partition,
-// rounded UP) x steps x 151 cycles: a shard of 125,000 members (1M members over 8 GPUs) is 6.6 warps per sub-partition
+// K1 is bound by the issue time of a warp-step, so the time of a launch is (warps per SM sub-partition,
+// rounded UP) x steps x 145 cycles (151 with the round-1 instruction stream these measurements were taken with): a shard of 125,000 members (1M members over 8 GPUs) is 6.6 warps per sub-partition
 // and pays for 7 (0.92 measured, profiles/r02_probe_k1_variants.log); 250,000 members pay 14 for 13.2.  Members are
 // independent but a member's steps are sequential, so the only way to hand a sub-partition a FRACTION of a warp's work
 // is to cut the time axis: the launch's step range is cut into segments, the ensemble into blocks of 128 members

@@ -383,7 +383,7 @@ int validate(const magpy_b200_ensemble* a) {
     return MAGPY_B200_OK;
 }
 
-// K1 (heun_single.cu) is bound by the FP64-side issue time of a warp-step (~151 cycles per sub-partition): a wave with k
+// K1 (heun_single.cu) is bound by the issue time of a warp-step (~145 cycles per sub-partition): a wave with k
 // CTAs per SM takes k issue times per step, and a lone warp is hardly faster than that (155 cycles).  With ptxas left
 // alone the kernel takes 76 registers = 6 resident CTAs per SM (888 per device).  Measured over shard sizes
 // (profiles/r02_probe_k1_variants.log): a shard slightly larger than one wave does NOT pay a whole extra wave — its few
